@@ -1,0 +1,44 @@
+// CPU emulation of ymt3_logmel_kernel: runs the very same per-thread pass
+// functions (yourmt3_b200/csrc/logmel_core.cuh) for tid = 0..127 sequentially,
+// with a barrier == end of each tid loop. Test infrastructure only: lets the
+// CPU-only test tier validate the FFT factorisation, smem index maps, pairing
+// and mel banding without a GPU. Never used by the product path.
+#include "../../yourmt3_b200/csrc/logmel_tables.h"
+#include <vector>
+
+extern "C" __attribute__((visibility("default"))) int lm_emu_run(const ymt3_audio_cfg_t* cfg, const float* window, const float* fb,
+                          const float* audio, int B, int L, float* out) {
+  LmHostTables ht;
+  if (lm_build_host_tables(cfg, fb, ht)) return 1;
+  LmTables tb{window, ht.tw1.data(), ht.tw2.data(), ht.first.data(), ht.off.data(), ht.wts.data()};
+  const int T = 1 + L / cfg->hop_length, hop = cfg->hop_length, n_out = ht.n_out;
+  const int pairs = (T + 1) / 2;
+  std::vector<float2> bufA(LM_BUF_ELEMS), bufB(LM_BUF_ELEMS);
+  float* magA = reinterpret_cast<float*>(bufB.data());
+  float* magB = magA + 1028;
+  for (int b = 0; b < B; ++b)
+    for (int tp = 0; tp < pairs; ++tp) {
+      const int tA = 2 * tp;
+      const bool hasB = tA + 1 < T;
+      const float* seg = audio + (size_t)b * L;
+      const int startA = tA * hop - LM_NFFT / 2, startB = startA + hop;
+      for (int tid = 0; tid < LM_THREADS; ++tid) {
+        float w[16];
+        for (int n1 = 0; n1 < 16; ++n1) w[n1] = window[128 * n1 + tid];
+        lm_pass1(tid, seg, L, startA, startB, hasB, w, tb.tw1, bufA.data());
+      }
+      for (int tid = 0; tid < LM_THREADS; ++tid) lm_pass2(tid, tb.tw2, bufA.data(), bufB.data());
+      for (int tid = 0; tid < LM_THREADS; ++tid) lm_pass3(tid, bufB.data(), bufA.data());
+      for (int tid = 0; tid < LM_THREADS; ++tid)
+        lm_mag(tid, bufA.data(), magA, magB, cfg->power_mode);
+      float* outA = out + ((size_t)b * T + tA) * n_out;
+      float* outB = hasB ? outA + n_out : nullptr;
+      for (int tid = 0; tid < LM_THREADS; ++tid) {
+        if (cfg->codec == YMT3_CODEC_MELSPEC)
+          lm_mel_log(tid, tb, n_out, cfg->log_eps, magA, magB, outA, outB);
+        else
+          lm_spec_log(tid, cfg->spec_bin0, n_out, cfg->log_eps, magA, magB, outA, outB);
+      }
+    }
+  return 0;
+}

@@ -1,0 +1,52 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/*.h declares."""
+import ctypes
+import os
+import re
+
+from yourmt3_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ymt3_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"YMT3_API\s+[\w\s\*]+?\b(ymt3_\w+)\s*\(", src)))
+
+
+def test_exports_match_header(native_lib):
+    syms = declared_symbols()
+    assert len(syms) >= 9
+    for s in syms:
+        assert hasattr(native_lib, s), f"{s} declared in the header but not exported"
+    # the ctypes signature table must cover the header exactly
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_abi_version_and_error_string(native_lib):
+    assert native_lib.ymt3_abi_version() == 1
+    # argument validation happens before any CUDA call -> safe without a GPU
+    rc = native_lib.ymt3_frontend_create(None, None, None, None)
+    assert rc == 1
+    assert b"null" in native_lib.ymt3_last_error()
+    cfg = _lib.AudioCfg(n_fft=1024, hop_length=128, codec=0, n_mels=512, power_mode=1, log_eps=1e-5)
+    h = ctypes.c_void_p()
+    buf = (ctypes.c_float * 2048)()
+    rc = native_lib.ymt3_frontend_create(ctypes.byref(cfg), buf, buf, ctypes.byref(h))
+    assert rc == 1 and b"n_fft=2048" in native_lib.ymt3_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    import pytest
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_forward_on_cpu_tensor_raises():
+    import pytest
+    import torch
+    from yourmt3_b200 import Melspectrogram
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        Melspectrogram()(torch.zeros(1, 1, 4096))

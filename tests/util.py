@@ -1,0 +1,35 @@
+"""Shared helpers for tests: synthetic audio and error metrics."""
+import numpy as np
+import torch
+
+GOLDEN_DIR = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+
+
+def synth_noise(B, L=32767, seed=1234, scale=0.1):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(B, L, generator=g) * scale).numpy().astype(np.float32)
+
+
+def synth_multitrack(B, L=32767, sr=16000, seed=1234):
+    """4-8 harmonic-plus-decay note streams, Poisson onsets ~8/s, -40 dB noise."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(L) / sr
+    out = np.zeros((B, L), np.float64)
+    for b in range(B):
+        for _ in range(rng.integers(4, 9)):
+            n_on = rng.poisson(8 * L / sr / 4) + 1
+            for on in rng.uniform(0, L / sr, n_on):
+                f0 = 440.0 * 2 ** ((rng.integers(36, 97) - 69) / 12)
+                env = np.where(t >= on, np.exp(-(t - on) * rng.uniform(2, 8)), 0.0)
+                for h in range(1, 5):
+                    if f0 * h < sr / 2:
+                        out[b] += env * np.sin(2 * np.pi * f0 * h * (t - on)) / h * 0.1
+        out[b] += rng.standard_normal(L) * 0.01 * np.abs(out[b]).max()
+        out[b] /= max(1e-9, np.abs(out[b]).max())
+    return (out * 0.8).astype(np.float32)
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|, 1): relative where |b|>1, absolute near zero (log domain)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))) if a.size else 0.0

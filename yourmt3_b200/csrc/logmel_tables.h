@@ -1,0 +1,64 @@
+// Host-side constant tables of the fused log-mel kernel (twiddles + banded mel
+// filterbank). Shared by the CUDA library and the CPU emulation harness in tests/.
+#pragma once
+#include "logmel_core.cuh"
+#include "../../include/ymt3_b200.h"
+#include <math.h>
+#include <vector>
+
+struct LmHostTables {
+  std::vector<float2> tw1, tw2;
+  std::vector<int> first, off;
+  std::vector<float> wts;
+  int n_out = 0;
+};
+
+// returns nullptr on success, else a static error string
+static inline const char* lm_build_host_tables(const ymt3_audio_cfg_t* cfg, const float* fb_host,
+                                               LmHostTables& t) {
+  t.tw1.resize(16 * 128);
+  t.tw2.resize(8 * 16);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int m = 0; m < 128; ++m) {
+      double a = -two_pi * (double)(m * k1) / 2048.0;
+      t.tw1[k1 * 128 + m] = make_float2((float)cos(a), (float)sin(a));
+    }
+  for (int n3 = 0; n3 < 8; ++n3)
+    for (int k2 = 0; k2 < 16; ++k2) {
+      double a = -two_pi * (double)(n3 * k2) / 128.0;
+      t.tw2[n3 * 16 + k2] = make_float2((float)cos(a), (float)sin(a));
+    }
+  if (cfg->codec == YMT3_CODEC_MELSPEC) {
+    if (!fb_host || cfg->n_mels <= 0) return "melspec codec needs fb_host and n_mels > 0";
+    const int M = cfg->n_mels;
+    t.first.resize(M);
+    t.off.resize(M + 1);
+    t.off[0] = 0;
+    for (int m = 0; m < M; ++m) {
+      int lo = -1, hi = -1;
+      for (int k = 0; k < LM_NBINS; ++k)
+        if (fb_host[(size_t)k * M + m] != 0.f) {
+          if (lo < 0) lo = k;
+          hi = k;
+        }
+      if (lo < 0) {  // empty filter (torchaudio warns, output is log(eps))
+        t.first[m] = 0;
+        t.off[m + 1] = t.off[m];
+        continue;
+      }
+      t.first[m] = lo;
+      for (int k = lo; k <= hi; ++k) t.wts.push_back(fb_host[(size_t)k * M + m]);
+      t.off[m + 1] = t.off[m] + (hi - lo + 1);
+    }
+    t.n_out = M;
+  } else {
+    if (cfg->spec_bin0 < 0 || cfg->spec_bins <= 0 || cfg->spec_bin0 + cfg->spec_bins > LM_NBINS)
+      return "spec bins outside [0, 1025)";
+    t.n_out = cfg->spec_bins;
+    t.first.assign(1, 0);
+    t.off.assign(2, 0);
+  }
+  if (t.wts.empty()) t.wts.push_back(0.f);
+  return nullptr;
+}

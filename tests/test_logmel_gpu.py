@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import logmel as O
-from tests.util import GOLDEN_DIR, rel_err, synth_multitrack, synth_noise
+from tests.util import GOLDEN_DIR, assert_frontend_close, rel_err, synth_multitrack, synth_noise
 from yourmt3_b200 import spectrogram as S
 
 pytestmark = pytest.mark.gpu
@@ -33,8 +33,7 @@ def test_cuda_vs_oracle(cuda_device, native_lib, L, codec, hop):
     layer = S.Melspectrogram(hop_length=hop) if codec == "melspec" else S.Spectrogram(hop_length=hop)
     x = synth_noise(3, L, seed=L + hop)
     got, ref = run(layer, x, cuda_device), oracle_run(layer, x)
-    assert got.shape == ref.shape
-    assert rel_err(got, ref) < TOL
+    assert_frontend_close(got, ref, TOL, strict_everywhere=(codec == "melspec"))
 
 
 @pytest.mark.parametrize("name,layer", [

@@ -86,6 +86,100 @@ YMT3_API int ymt3_logmel_f32(ymt3_frontend_t* fe, const float* audio_dev, int64_
 YMT3_API int ymt3_logmel_host_f32(ymt3_frontend_t* fe, const float* audio_host, int64_t B, int64_t L,
                          float* out_host, void* stream);
 
+
+/* ------------------------------------------------------------------------- *
+ * Named tensors: how weights cross the boundary.  `name` is the state-dict key
+ * of the reference module (HF/upstream naming), `data` a DEVICE pointer to a
+ * contiguous fp32 tensor.  Handles copy/pack what they need at create time
+ * (into fp32 or bf16 according to `precision`); the caller may free or reuse
+ * its tensors afterwards.
+ * ------------------------------------------------------------------------- */
+#define YMT3_DTYPE_F32 0
+#define YMT3_DTYPE_BF16 1
+
+typedef struct ymt3_tensor {
+  const char* name;
+  const void* data; /* device pointer */
+  int32_t dtype;    /* YMT3_DTYPE_F32 */
+  int32_t ndim;
+  int64_t shape[4];
+} ymt3_tensor_t;
+
+/* ------------------------------------------------------------------------- *
+ * T5 encoder stack (MT3 encoder).  Replaces upstream model/t5mod.py
+ * T5EncoderYMT3.forward(inputs_embeds=...) -> last_hidden_state, a modified copy of
+ *   HF/models/t5/modeling_t5.py:617-792 (T5Stack), :411-498 (T5Block),
+ *   :153-344 (T5Attention, no 1/sqrt(d) scale, fp32 softmax), :106-131 (gated-GELU FF),
+ *   :46-68 (T5LayerNorm = RMSNorm).
+ * Tensor names: block.{i}.layer.0.SelfAttention.{q,k,v,o}.weight, block.{i}.layer.0.layer_norm.weight,
+ * block.{i}.layer.1.DenseReluDense.{wi_0,wi_1,wo}.weight, block.{i}.layer.1.layer_norm.weight,
+ * final_layer_norm.weight, and (optional) pos_table (n_pos, d_model) added to inputs_embeds.
+ * ------------------------------------------------------------------------- */
+typedef struct ymt3_t5_cfg {
+  int32_t precision;   /* YMT3_DTYPE_F32: fp32 FFMA path (token-exact); YMT3_DTYPE_BF16: tcgen05 path */
+  int32_t d_model, num_heads, d_kv, d_ff, num_layers;
+  float layer_norm_eps;
+  /* decoder only */
+  int32_t vocab_size, max_length, tie_word_embeddings;
+  int32_t eos_id, pad_id, start_id;
+} ymt3_t5_cfg_t;
+
+typedef struct ymt3_t5enc ymt3_t5enc_t;
+YMT3_API int ymt3_t5enc_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* tensors, int n_tensors,
+                               ymt3_t5enc_t** out);
+YMT3_API int ymt3_t5enc_destroy(ymt3_t5enc_t* enc);
+/* x_dev: (B, S, d_model) fp32 inputs_embeds. out_dev: (B, S, d_model) in the handle's precision
+ * (fp32, or bf16 when precision = BF16). Workspace grows on demand (cudaMalloc) when B*S exceeds
+ * the largest size seen so far. */
+YMT3_API int ymt3_t5enc_forward(ymt3_t5enc_t* enc, const float* x_dev, int64_t B, int64_t S, void* out_dev,
+                                void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * T5 decoder + greedy segment-batched generation.  Replaces upstream
+ * model/t5mod.py T5DecoderYMT3 / MultiChannelT5Decoder (channels folded into the batch),
+ * model/t5mod_helper.py task_cond_dec_generate(), model/lm_head.py LMHead:
+ *   HF/models/t5/modeling_t5.py:380-408 (cross-attention layer), :269-305 (KV cache update),
+ *   :1105-1110 (d_model**-0.5 logit scale when embeddings are tied).
+ * Extra tensor names: embed_tokens.weight (V, d_model), lm_head.weight (V, d_model) [absent = tied],
+ * block.{i}.layer.1.EncDecAttention.{q,k,v,o}.weight, block.{i}.layer.2.*, pos_table.
+ * The whole loop runs on the device: KV cache, finished mask, step counter and the token
+ * matrix never leave HBM; there is no host synchronisation inside ymt3_t5dec_generate.
+ * ------------------------------------------------------------------------- */
+typedef struct ymt3_t5dec ymt3_t5dec_t;
+YMT3_API int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* tensors, int n_tensors,
+                               ymt3_t5dec_t** out);
+YMT3_API int ymt3_t5dec_destroy(ymt3_t5dec_t* dec);
+/* enc_hs_dev: (N, T_enc, d_model) in the handle's precision; N = B*C sequences.
+ * tokens_out_dev: (N, max_len) int32, fully written (pad after EOS).
+ * stop_at_eos: rows that emitted EOS emit pad afterwards (reference semantics).
+ * early_stop_interval > 0: every that many steps the host polls a device counter (one 4-byte
+ * async D2H + event) and stops launching once every row has finished; 0 = run max_len steps. */
+YMT3_API int ymt3_t5dec_generate(ymt3_t5dec_t* dec, const void* enc_hs_dev, int64_t N, int64_t T_enc,
+                                 int32_t max_len, int32_t stop_at_eos, int32_t early_stop_interval,
+                                 int32_t* tokens_out_dev, void* stream);
+/* fp32 logits of the LAST executed step, (N, vocab) (for logit-tolerance tests) */
+YMT3_API int ymt3_t5dec_last_logits(ymt3_t5dec_t* dec, float* logits_out_dev, int64_t N, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Per-op entry points (unit-parity tests of individual kernels; also usable as building
+ * blocks).  dtype: YMT3_DTYPE_F32 | YMT3_DTYPE_BF16 for A/W/C; bias always fp32.
+ * ------------------------------------------------------------------------- */
+/* C = residual + out_scale * epi(A @ W^T + bias);  A (M,K) lda, W (N,K) ldw (nn.Linear.weight),
+ * act: 0 none, 1 gelu_new(tanh), 2 relu, 3 silu, 4 gelu(erf); gated: W rows interleaved (act, lin) pairs,
+ * C is (M, N/2). */
+YMT3_API int ymt3_op_linear(int32_t dtype, const void* A, int64_t lda, const void* W, int64_t ldw,
+                            const float* bias, void* C, int64_t ldc, const void* residual, int64_t ldr,
+                            int64_t M, int64_t N, int64_t K, int32_t act, int32_t gated, float out_scale,
+                            int32_t out_dtype, void* stream);
+YMT3_API int ymt3_op_rmsnorm(int32_t dtype, const void* x, const float* w, void* y, int64_t rows, int64_t dim,
+                             float eps, void* stream);
+YMT3_API int ymt3_op_layernorm(int32_t dtype, const void* x, const float* w, const float* b, void* y,
+                               int64_t rows, int64_t dim, float eps, void* stream);
+/* q/k/v/o: (B, S, H, dk) contiguous; causal: key j visible iff j <= i + (Sk - Sq) */
+YMT3_API int ymt3_op_attention(int32_t dtype, const void* q, const void* k, const void* v, void* o, int64_t B,
+                               int64_t H, int64_t Sq, int64_t Sk, int64_t dk, float scale, int32_t causal,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

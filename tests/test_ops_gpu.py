@@ -1,0 +1,113 @@
+"""GPU unit-parity of individual kernels through the per-op C ABI, against plain PyTorch fp32
+on CPU (the oracle for floating-point kernels). fp32 path tolerance: 2e-5 relative to the
+output scale (fp32 accumulate, different summation order than MKL)."""
+import math
+
+import pytest
+import torch
+
+from oracle import t5 as OT
+from yourmt3_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+ACTS = {0: lambda x: x, 1: OT.gelu_new, 2: torch.relu, 3: torch.nn.functional.silu, 4: torch.nn.functional.gelu}
+
+
+def _close(got, ref, tol=2e-5):
+    scale = max(1.0, float(ref.abs().max()))
+    err = float((got.double() - ref.double()).abs().max()) / scale
+    assert err < tol, f"max err {err:.3e} (scale {scale:.2f})"
+
+
+def linear_native(lib, dev, A, W, bias=None, act=0, gated=0, residual=None, out_scale=1.0):
+    M, K = A.shape
+    N = W.shape[0]
+    Ad, Wd = A.to(dev), W.to(dev)
+    No = N // 2 if gated else N
+    C_ = torch.full((M, No), float("nan"), device=dev)
+    bd = None if bias is None else bias.to(dev)
+    Rd = None if residual is None else residual.to(dev)
+    rc = lib.ymt3_op_linear(0, Ad.data_ptr(), K, Wd.data_ptr(), K, None if bd is None else bd.data_ptr(), C_.data_ptr(),
+                            No, None if Rd is None else Rd.data_ptr(), No, M, N, K, act, gated, out_scale, 0,
+                            torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "op_linear")
+    return C_.cpu()
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 4, 4), (7, 12, 20), (64, 64, 16), (100, 1152, 512), (832, 512, 384),
+                                   (3000, 2048, 512), (16384, 512, 1024), (333, 596, 512)])
+def test_linear_f32_shapes(cuda_device, native_lib, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    _close(linear_native(native_lib, cuda_device, A, W), A @ W.T)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("gated", [0, 1])
+def test_linear_f32_epilogues(cuda_device, native_lib, act, gated):
+    g = torch.Generator().manual_seed(10 * act + gated)
+    M, N, K = 200, 256, 128
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.1
+    bias = torch.randn(N, generator=g)
+    R = torch.randn(M, N // 2 if gated else N, generator=g)
+    z = A @ W.T + bias
+    ref = ACTS[act](z[:, 0::2]) * z[:, 1::2] if gated else ACTS[act](z)
+    ref = R + 0.5 * ref
+    _close(linear_native(native_lib, cuda_device, A, W, bias, act, gated, R, 0.5), ref)
+
+
+def test_linear_inplace_residual(cuda_device, native_lib):
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 130, 512, 384
+    A, W, X = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05, torch.randn(M, N, generator=g)
+    Xd, Ad, Wd = X.to(cuda_device), A.to(cuda_device), W.to(cuda_device)
+    rc = native_lib.ymt3_op_linear(0, Ad.data_ptr(), K, Wd.data_ptr(), K, None, Xd.data_ptr(), N, Xd.data_ptr(), N, M, N,
+                                   K, 0, 0, 1.0, 0, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+    _close(Xd.cpu(), X + A @ W.T)
+
+
+def test_linear_rejects_bad_alignment(cuda_device, native_lib):
+    A = torch.zeros(4, 6, device=cuda_device)
+    rc = native_lib.ymt3_op_linear(0, A.data_ptr(), 6, A.data_ptr(), 6, None, A.data_ptr(), 4, None, 0, 4, 4, 6, 0, 0, 1.0,
+                                   0, None)
+    assert rc == 1 and b"multiples of 4" in native_lib.ymt3_last_error()
+
+
+@pytest.mark.parametrize("rows,dim", [(1, 512), (1000, 512), (77, 128), (5, 1024)])
+def test_norms(cuda_device, native_lib, rows, dim):
+    g = torch.Generator().manual_seed(rows + dim)
+    x, w, b = torch.randn(rows, dim, generator=g) * 3 + 0.5, torch.randn(dim, generator=g), torch.randn(dim, generator=g)
+    xd, wd, bd = x.to(cuda_device), w.to(cuda_device), b.to(cuda_device)
+    y = torch.empty_like(xd)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(native_lib.ymt3_op_rmsnorm(0, xd.data_ptr(), wd.data_ptr(), y.data_ptr(), rows, dim, 1e-6, s))
+    _close(y.cpu(), OT.rms_norm(x, w, 1e-6), 1e-5)
+    _lib.check(native_lib.ymt3_op_layernorm(0, xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, dim, 1e-5, s))
+    _close(y.cpu(), torch.nn.functional.layer_norm(x, (dim,), w, b, 1e-5), 1e-5)
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,dk,causal", [
+    (2, 6, 256, 256, 64, 0),     # T5 encoder
+    (3, 6, 7, 7, 64, 1),         # decoder prefill, causal
+    (2, 6, 5, 19, 64, 0),        # cross attention
+    (5, 1, 26, 128, 128, 0),     # Perceiver-TF spectral cross-attention
+    (4, 8, 26, 26, 16, 0),       # latent self-attention
+    (3, 8, 110, 110, 16, 0),     # temporal self-attention
+    (2, 4, 33, 70, 32, 1),       # causal with Sk > Sq
+    (1, 2, 1, 300, 64, 0),
+])
+def test_attention(cuda_device, native_lib, B, H, Sq, Sk, dk, causal):
+    g = torch.Generator().manual_seed(B * 1000 + Sq + Sk + dk)
+    q, k, v = (torch.randn(B, S, H, dk, generator=g) for S in (Sq, Sk, Sk))
+    scale = 1.0 if dk == 64 else 1.0 / math.sqrt(dk)
+    mask = None
+    if causal:
+        i, j = torch.arange(Sq)[:, None], torch.arange(Sk)[None, :]
+        mask = torch.where(j <= i + (Sk - Sq), 0.0, float("-inf"))
+    ref = OT.attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), mask, scale).view(B, Sq, H, dk)
+    qd, kd, vd = q.to(cuda_device), k.to(cuda_device), v.to(cuda_device)
+    o = torch.full((B, Sq, H, dk), float("nan"), device=cuda_device)
+    _lib.check(native_lib.ymt3_op_attention(0, qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, H, Sq, Sk, dk,
+                                            scale, causal, torch.cuda.current_stream().cuda_stream))
+    _close(o.cpu(), ref, 1e-5)

@@ -1,0 +1,103 @@
+"""GPU parity of the T5 path (fp32 FFMA kernels) against the CPU oracle pinned to HF T5:
+encoder hidden states, decoded TOKENS (bar: identical), EOS semantics, full inference()."""
+import numpy as np
+import pytest
+import torch
+
+import yourmt3_b200 as ymt3
+from oracle import pipeline as OP
+from tests.util import synth_multitrack, synth_noise
+
+pytestmark = pytest.mark.gpu
+
+
+def small_cfg(n_layers=2, event_length=48):
+    cfg = ymt3.get_model_cfg("mt3_t5_small")
+    cfg["encoder"]["t5"]["num_layers"] = n_layers
+    cfg["decoder"]["t5"]["num_layers"] = n_layers
+    cfg["event_length"] = event_length
+    return cfg
+
+
+@pytest.fixture(scope="module")
+def model_small(cuda_device, native_lib):
+    m = ymt3.YourMT3(model_cfg=small_cfg())
+    ymt3.init_nondegenerate_(m, seed=0)
+    return m.to(cuda_device)
+
+
+def test_encoder_hidden_states(cuda_device, model_small):
+    m = model_small
+    x = torch.randn(3, 256, 512, generator=torch.Generator().manual_seed(1))
+    got = m.encoder(inputs_embeds=x.to(cuda_device))["last_hidden_state"].cpu()
+    ref = OP.t5_encode(m.state_dict(), x, m.model_cfg, m.encoder.pos_table.shape[0])
+    err = float((got - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-5, err
+
+
+def assert_tokens_identical(got, ref, margins, what=""):
+    """Bar: identical tokens. A divergence is only tolerated as an fp32 summation-order flip at a
+    near-tie of the ORACLE's own logits (top1-top2 margin < 1e-4); anything else fails."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape
+    for n in range(ref.shape[0]):
+        if (got[n] == ref[n]).all():
+            continue
+        t = int(np.argmax(got[n] != ref[n]))
+        assert float(margins[n, t]) < 1e-4, f"{what} row {n}: token mismatch at step {t} with margin {float(margins[n, t]):.3e}"
+
+
+def test_generate_tokens_identical(cuda_device, model_small):
+    m = model_small
+    enc_hs = torch.randn(5, 40, 512, generator=torch.Generator().manual_seed(2))
+    ref, margins = OP.t5_generate(m.state_dict(), enc_hs, m.model_cfg, m.decoder.pos_table.shape[0], 48,
+                                  stop_at_eos=False, return_margins=True)
+    got = ymt3.task_cond_dec_generate(m.decoder, "t5", m.embed_tokens, m.lm_head, enc_hs.to(cuda_device), max_length=48,
+                                      stop_at_eos=False)
+    assert got.dtype == torch.long and got.shape == (5, 48)
+    assert len(np.unique(ref.numpy())) > 10, "degenerate oracle decode"
+    assert_tokens_identical(got.cpu().numpy(), ref.numpy(), margins.numpy(), "generate")
+    assert float(margins.median()) > 1e-3
+
+
+def test_generate_eos_semantics(cuda_device, model_small):
+    """Rows that emit EOS are padded afterwards; early stop leaves pad; matches the oracle."""
+    m = model_small
+    enc_hs = torch.randn(4, 21, 512, generator=torch.Generator().manual_seed(7))
+    free = OP.t5_generate(m.state_dict(), enc_hs, m.model_cfg, m.decoder.pos_table.shape[0], 32, stop_at_eos=False)
+    eos = int(free[0, 6])                      # a token that really occurs -> EOS fires mid-sequence
+    ref, margins = OP.t5_generate(m.state_dict(), enc_hs, m.model_cfg, m.decoder.pos_table.shape[0], 32, stop_at_eos=True,
+                                  eos_id=eos, return_margins=True)
+    for interval in (0, 4):
+        got = ymt3.task_cond_dec_generate(m.decoder, "t5", m.embed_tokens, m.lm_head, enc_hs.to(cuda_device),
+                                          max_length=32, stop_at_eos=True, eos_id=eos, early_stop_interval=interval)
+        assert_tokens_identical(got.cpu().numpy(), ref.numpy(), margins.numpy(), f"eos interval={interval}")
+    row = ref[0].tolist()
+    assert eos in row and all(t == 0 for t in row[row.index(eos) + 1:])
+
+
+def test_full_inference_matches_oracle(cuda_device, model_small):
+    """audio -> tokens through YourMT3.inference vs the end-to-end CPU oracle (configs[0] shape, 2 layers)."""
+    m = model_small
+    audio = np.concatenate([synth_noise(1, seed=11), synth_multitrack(1, seed=12)], 0)
+    ref, margins = OP.transcribe_t5(m.state_dict(), audio, m.audio_cfg, m.model_cfg, m.encoder.pos_table.shape[0], 48,
+                                    stop_at_eos=False, return_margins=True)
+    got = m.inference(torch.from_numpy(audio).unsqueeze(1).to(cuda_device), stop_at_eos=False)
+    assert got.shape == (2, 48)
+    assert_tokens_identical(got.cpu().numpy(), ref.numpy(), margins.numpy(), "inference")
+    outs = m.inference_file(1, torch.from_numpy(audio).unsqueeze(1), stop_at_eos=False)
+    assert len(outs) == 2 and (np.concatenate(outs, 0) == got.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_t5_small_full_depth_tokens(cuda_device, native_lib, seed):
+    """BASELINE configs[0]: full T5-small shape (8+8 layers), one 2.048 s segment, greedy decode."""
+    cfg = ymt3.get_model_cfg("mt3_t5_small")
+    cfg["event_length"] = 96
+    m = ymt3.init_nondegenerate_(ymt3.YourMT3(model_cfg=cfg), seed=seed).to(cuda_device)
+    audio = synth_multitrack(1, seed=100 + seed)
+    ref, margins = OP.transcribe_t5(m.state_dict(), audio, m.audio_cfg, m.model_cfg, m.encoder.pos_table.shape[0], 96,
+                                    stop_at_eos=False, return_margins=True)
+    got = m.inference(torch.from_numpy(audio).unsqueeze(1).to(cuda_device), stop_at_eos=False)
+    assert len(np.unique(ref.numpy())) > 5
+    assert_tokens_identical(got.cpu().numpy(), ref.numpy(), margins.numpy(), "t5-small")

@@ -7,4 +7,10 @@ from .config import audio_cfg, model_cfg, get_audio_cfg, get_model_cfg  # noqa: 
 from .spectrogram import (Melspectrogram, Spectrogram,  # noqa: F401
                           get_spectrogram_layer_from_audio_cfg, mel_filterbank)
 
+from .t5mod import T5EncoderYMT3, T5DecoderYMT3, MultiChannelT5Decoder  # noqa: F401
+from .t5mod_helper import task_cond_dec_generate  # noqa: F401
+from .lm_head import LMHead  # noqa: F401
+from .ymt3 import YourMT3  # noqa: F401
+from .init_utils import init_nondegenerate_  # noqa: F401
+
 __version__ = "0.1.0"

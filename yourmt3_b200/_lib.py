@@ -31,6 +31,23 @@ class AudioCfg(C.Structure):
     ]
 
 
+class Tensor(C.Structure):
+    """Mirror of ``ymt3_tensor_t`` (named device tensor = state-dict entry)."""
+
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("dtype", C.c_int32), ("ndim", C.c_int32),
+                ("shape", C.c_int64 * 4)]
+
+
+class T5Cfg(C.Structure):
+    """Mirror of ``ymt3_t5_cfg_t``."""
+
+    _fields_ = [("precision", C.c_int32), ("d_model", C.c_int32), ("num_heads", C.c_int32), ("d_kv", C.c_int32),
+                ("d_ff", C.c_int32), ("num_layers", C.c_int32), ("layer_norm_eps", C.c_float),
+                ("vocab_size", C.c_int32), ("max_length", C.c_int32), ("tie_word_embeddings", C.c_int32),
+                ("eos_id", C.c_int32), ("pad_id", C.c_int32), ("start_id", C.c_int32)]
+
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
 CODEC_MELSPEC, CODEC_SPEC = 0, 1
 _P = C.c_void_p
 _I64 = C.c_int64
@@ -47,6 +64,18 @@ SIGNATURES = {
     "ymt3_frontend_num_features": (_I64, [_P]),
     "ymt3_logmel_f32": (_I, [_P, _P, _I64, _I64, _P, _P]),
     "ymt3_logmel_host_f32": (_I, [_P, _P, _I64, _I64, _P, _P]),
+    "ymt3_t5enc_create": (_I, [C.POINTER(T5Cfg), C.POINTER(Tensor), _I, C.POINTER(_P)]),
+    "ymt3_t5enc_destroy": (_I, [_P]),
+    "ymt3_t5enc_forward": (_I, [_P, _P, _I64, _I64, _P, _P]),
+    "ymt3_t5dec_create": (_I, [C.POINTER(T5Cfg), C.POINTER(Tensor), _I, C.POINTER(_P)]),
+    "ymt3_t5dec_destroy": (_I, [_P]),
+    "ymt3_t5dec_generate": (_I, [_P, _P, _I64, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "ymt3_t5dec_last_logits": (_I, [_P, _P, _I64, _P]),
+    "ymt3_op_linear": (_I, [C.c_int32, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, C.c_int32,
+                            C.c_int32, C.c_float, C.c_int32, _P]),
+    "ymt3_op_rmsnorm": (_I, [C.c_int32, _P, _P, _P, _I64, _I64, C.c_float, _P]),
+    "ymt3_op_layernorm": (_I, [C.c_int32, _P, _P, _P, _P, _I64, _I64, C.c_float, _P]),
+    "ymt3_op_attention": (_I, [C.c_int32, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, C.c_float, C.c_int32, _P]),
 }
 
 
@@ -86,3 +115,28 @@ def device_info() -> dict:
     sms, maj, mnr = _I(), _I(), _I()
     check(lib.ymt3_device_info(name, 256, C.byref(sms), C.byref(maj), C.byref(mnr)), "device_info")
     return {"name": name.value.decode(), "num_sms": sms.value, "cc": (maj.value, mnr.value)}
+
+
+def tensor_table(named):
+    """dict name -> CUDA float32 tensor  ==>  (ctypes array of ymt3_tensor_t, n, keepalive list)."""
+    import torch
+    keep, arr = [], (Tensor * len(named))()
+    for i, (name, t) in enumerate(named.items()):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda):
+            raise RuntimeError(f"tensor {name!r} must live on the CUDA device (no CPU fallback)")
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(torch.float32).contiguous()
+        if t.dim() > 4:
+            raise ValueError(f"tensor {name!r}: rank > 4")
+        b = name.encode()
+        keep += [t, b]
+        arr[i].name, arr[i].data, arr[i].dtype, arr[i].ndim = b, t.data_ptr(), DTYPE_F32, t.dim()
+        for j, d in enumerate(t.shape):
+            arr[i].shape[j] = d
+    return arr, len(named), keep
+
+
+def torch_dtype(precision: int):
+    import torch
+    return torch.float32 if precision == DTYPE_F32 else torch.bfloat16

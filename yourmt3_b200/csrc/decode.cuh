@@ -1,0 +1,23 @@
+// Decode-step op launchers (decode.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ymt3 {
+
+int embed_pos(const int* tok, const void* E, const void* pos, const int* step, void* x, int N, int dim,
+              int dtype, cudaStream_t stream);
+
+// q: (N, H*dk) rows with leading dim q_ld. knew/vnew (self mode) rows with leading dim new_ld or
+// null (cross mode). Kc/Vc: caches addressed as base + n*c_sn + h*c_sh + j*c_ss (+ d), element strides.
+// step: device int (self mode attends keys [0, *step]; cross mode keys [0, fixed_len)). out: (N, H*dk).
+int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* vnew, int64_t new_ld, void* Kc,
+                     void* Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss, int Lmax, const int* step, int fixed_len,
+                     float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream);
+
+int greedy_select(const float* logits, int64_t ld, int V, int N, const int* step, int* cur_tok, int* finished,
+                  int* tokens_out, int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count,
+                  cudaStream_t stream);
+int advance_step(int* step, int* unfinished_count, cudaStream_t stream);
+int fill_i32(int* p, int v, int64_t n, cudaStream_t stream);
+
+}  // namespace ymt3

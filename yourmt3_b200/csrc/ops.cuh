@@ -1,0 +1,83 @@
+// Internal op launchers shared by the model orchestration (model.cu) and the
+// per-op C-ABI test entry points (ops_capi.cu). All launch on `stream`, never
+// synchronise, never allocate. dtype: 0 = f32, 1 = bf16 (activations/weights);
+// accumulation, softmax and normalisation statistics are always fp32.
+#pragma once
+#include "common.cuh"
+
+#define YMT3_F32 0
+#define YMT3_BF16 1
+
+#define YMT3_ACT_NONE 0
+#define YMT3_ACT_GELU_NEW 1   // tanh approximation (HF activations.py:59-66), T5 "gated-gelu"
+#define YMT3_ACT_RELU 2
+#define YMT3_ACT_SILU 3
+#define YMT3_ACT_GELU 4       // erf GELU (torch.nn.functional.gelu default)
+
+namespace ymt3 {
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  switch (act) {
+    case YMT3_ACT_GELU_NEW: {
+      const float k = 0.7978845608028654f;  // sqrt(2/pi)
+      return 0.5f * x * (1.0f + tanhf(k * (x + 0.044715f * x * x * x)));
+    }
+    case YMT3_ACT_RELU: return fmaxf(x, 0.f);
+    case YMT3_ACT_SILU: return x / (1.0f + expf(-x));
+    case YMT3_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    default: return x;
+  }
+}
+
+// C = residual + out_scale * epi(A @ W^T + bias)
+//   A: (M, K) row-major, lda.  W: (N, K) row-major (nn.Linear.weight), ldw.
+//   gated == 0: C is (M, N);           epi(x) = act(x)
+//   gated == 1: C is (M, N/2); rows of W are interleaved (2j = gate/act branch,
+//               2j+1 = linear branch): C[:, j] = act(x[:, 2j]) * x[:, 2j+1]
+//   bias: fp32 (N) or null. residual: same dtype/ld as C or null (may alias C).
+//   Grouped mode (group_offsets != null): rows [off[g], off[g+1]) of A/C use weight
+//   W + g*strideW (and bias + g*N); num_groups groups; M = total rows upper bound.
+struct GemmParams {
+  const void* A; int64_t lda;
+  const void* W; int64_t ldw;
+  void* C; int64_t ldc;
+  const float* bias;
+  const void* residual; int64_t ldr;
+  int M, N, K;
+  int act, gated;
+  float out_scale;
+  const int* group_offsets; int num_groups; int64_t strideW;
+  // optional per-row scale applied with out_scale (MoE combine weights), fp32 (M) or null
+  const float* row_scale;
+};
+
+int gemm_f32(const GemmParams& p, cudaStream_t stream);            // SIMT fp32 FFMA
+int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream);  // tcgen05/TMEM/TMA
+
+// y = x * rsqrt(mean(x^2) + eps) * w          (T5LayerNorm / RMSNorm)
+// y = (x - mean) * rsqrt(var + eps) * w + b   (nn.LayerNorm), w/b fp32
+int rmsnorm(const void* x, const float* w, void* y, int64_t rows, int dim, float eps, int dtype,
+            cudaStream_t stream);
+int layernorm(const void* x, const float* w, const float* b, void* y, int64_t rows, int dim,
+              float eps, int dtype, cudaStream_t stream);
+
+// Generic small-sequence attention: O[b,h,i,:] = softmax_j(scale * Q[b,h,i,:].K[b,h,j,:] (+causal)) V[b,h,j,:]
+// element strides are given in ELEMENTS; head dim dk in {16, 32, 64, 128}.
+struct AttnParams {
+  const void* Q; int64_t q_sb, q_sh, q_ss;   // batch, head, seq strides
+  const void* K; int64_t k_sb, k_sh, k_ss;
+  const void* V; int64_t v_sb, v_sh, v_ss;
+  void* O; int64_t o_sb, o_sh, o_ss;
+  int B, H, Sq, Sk, dk;
+  float scale;
+  int causal;        // key j allowed iff j <= i + (Sk - Sq)
+  const int* kv_len; // optional per-batch valid key count (device), else Sk
+};
+int attention(const AttnParams& p, int dtype, cudaStream_t stream);
+
+// elementwise helpers
+int add_rows(const void* x, const void* table, void* y, int64_t rows, int period, int dim, int dtype,
+             cudaStream_t stream);  // y[r,:] = x[r,:] + table[r % period,:]
+int convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, cudaStream_t stream);
+
+}  // namespace ymt3

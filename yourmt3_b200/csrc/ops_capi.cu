@@ -1,0 +1,45 @@
+// Per-op C-ABI entry points (include/ymt3_b200.h, "Per-op entry points").
+#include "ops.cuh"
+#include "../../include/ymt3_b200.h"
+
+using namespace ymt3;
+
+extern "C" int ymt3_op_linear(int32_t dtype, const void* A, int64_t lda, const void* W, int64_t ldw,
+                              const float* bias, void* C, int64_t ldc, const void* residual, int64_t ldr, int64_t M,
+                              int64_t N, int64_t K, int32_t act, int32_t gated, float out_scale, int32_t out_dtype,
+                              void* stream) {
+  YMT3_REQUIRE(M >= 0 && M < (1ll << 31) && N > 0 && N < (1ll << 31) && K > 0 && K < (1ll << 31), "op_linear: bad shape");
+  GemmParams p{};
+  p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.C = C; p.ldc = ldc; p.bias = bias;
+  p.residual = residual; p.ldr = ldr; p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.act = act; p.gated = gated; p.out_scale = out_scale;
+  if (dtype == YMT3_F32) {
+    YMT3_REQUIRE(out_dtype == YMT3_F32, "op_linear: f32 path writes f32");
+    return gemm_f32(p, (cudaStream_t)stream);
+  }
+  return gemm_bf16_tc(p, out_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int ymt3_op_rmsnorm(int32_t dtype, const void* x, const float* w, void* y, int64_t rows, int64_t dim,
+                               float eps, void* stream) {
+  return rmsnorm(x, w, y, rows, (int)dim, eps, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int ymt3_op_layernorm(int32_t dtype, const void* x, const float* w, const float* b, void* y, int64_t rows,
+                                 int64_t dim, float eps, void* stream) {
+  return layernorm(x, w, b, y, rows, (int)dim, eps, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int ymt3_op_attention(int32_t dtype, const void* q, const void* k, const void* v, void* o, int64_t B,
+                                 int64_t H, int64_t Sq, int64_t Sk, int64_t dk, float scale, int32_t causal,
+                                 void* stream) {
+  AttnParams a{};
+  a.Q = q; a.K = k; a.V = v; a.O = o;
+  a.q_sb = Sq * H * dk; a.q_sh = dk; a.q_ss = H * dk;
+  a.k_sb = Sk * H * dk; a.k_sh = dk; a.k_ss = H * dk;
+  a.v_sb = Sk * H * dk; a.v_sh = dk; a.v_ss = H * dk;
+  a.o_sb = Sq * H * dk; a.o_sh = dk; a.o_ss = H * dk;
+  a.B = (int)B; a.H = (int)H; a.Sq = (int)Sq; a.Sk = (int)Sk; a.dk = (int)dk;
+  a.scale = scale; a.causal = causal;
+  return attention(a, dtype, (cudaStream_t)stream);
+}

@@ -1,0 +1,134 @@
+// Normalisation and elementwise kernels (fp32 statistics, f32 or bf16 IO).
+#include "ops.cuh"
+
+namespace ymt3 {
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                      T* __restrict__ y, int64_t rows, int dim, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* xr = x + row * dim;
+  float ss = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    float v = to_f(xr[i]);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss / (float)dim + eps);
+  T* yr = y + row * dim;
+  for (int i = lane; i < dim; i += 32) yr[i] = from_f<T>(w[i] * (to_f(xr[i]) * inv));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, T* __restrict__ y,
+                                                        int64_t rows, int dim, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* xr = x + row * dim;
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s += to_f(xr[i]);
+  const float mean = warp_sum(s) / (float)dim;
+  float ss = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    float d = to_f(xr[i]) - mean;
+    ss = fmaf(d, d, ss);
+  }
+  const float inv = rsqrtf(warp_sum(ss) / (float)dim + eps);
+  T* yr = y + row * dim;
+  for (int i = lane; i < dim; i += 32)
+    yr[i] = from_f<T>((to_f(xr[i]) - mean) * inv * w[i] + (b ? b[i] : 0.f));
+}
+
+int rmsnorm(const void* x, const float* w, void* y, int64_t rows, int dim, float eps, int dtype,
+            cudaStream_t stream) {
+  if (rows <= 0) return YMT3_OK;
+  YMT3_REQUIRE(x && w && y && dim > 0, "rmsnorm: bad argument");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dtype == YMT3_F32)
+    rmsnorm_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, w, (float*)y, rows, dim, eps);
+  else
+    rmsnorm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, rows,
+                                                            dim, eps);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
+int layernorm(const void* x, const float* w, const float* b, void* y, int64_t rows, int dim, float eps,
+              int dtype, cudaStream_t stream) {
+  if (rows <= 0) return YMT3_OK;
+  YMT3_REQUIRE(x && w && y && dim > 0, "layernorm: bad argument");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dtype == YMT3_F32)
+    layernorm_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, w, b, (float*)y, rows, dim, eps);
+  else
+    layernorm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, w, b, (__nv_bfloat16*)y,
+                                                              rows, dim, eps);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_rows_kernel(const T* __restrict__ x, const T* __restrict__ table,
+                                                       T* __restrict__ y, int64_t total, int period, int dim) {
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  int64_t r = i / dim;
+  int c = (int)(i - r * dim);
+  y[i] = from_f<T>(to_f(x[i]) + to_f(table[(r % period) * dim + c]));
+}
+
+int add_rows(const void* x, const void* table, void* y, int64_t rows, int period, int dim, int dtype,
+             cudaStream_t stream) {
+  if (rows <= 0) return YMT3_OK;
+  const int64_t total = rows * dim;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == YMT3_F32)
+    add_rows_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (const float*)table, (float*)y, total,
+                                                     period, dim);
+  else
+    add_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)table,
+                                                             (__nv_bfloat16*)y, total, period, dim);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) convert_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) d[i] = from_f<D>(to_f(s[i]));
+}
+
+int convert(const void* src, int sd, void* dst, int dd, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return YMT3_OK;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (sd == YMT3_F32 && dd == YMT3_BF16)
+    convert_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (sd == YMT3_BF16 && dd == YMT3_F32)
+    convert_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (sd == YMT3_F32 && dd == YMT3_F32)
+    YMT3_CUDA_CHECK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, stream));
+  else
+    YMT3_CUDA_CHECK(cudaMemcpyAsync(dst, src, n * 2, cudaMemcpyDeviceToDevice, stream));
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
+}  // namespace ymt3

@@ -1,0 +1,416 @@
+// T5 encoder stack and T5 decoder + greedy generation, orchestrated natively (C++) over the
+// kernels in gemm_*.cu / attention.cu / ops_misc.cu / decode.cu. Reference semantics:
+// HF transformers modeling_t5.py (cited per step below) as copied by upstream model/t5mod.py.
+#include "model_common.cuh"
+#include "decode.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+using namespace ymt3;
+
+namespace {
+
+struct T5Layer {
+  float* ln_sa = nullptr;  Linear qkv, o;           // layer.0 SelfAttention (q|k|v stacked)
+  float* ln_ca = nullptr;  Linear xq, xkv, xo;      // layer.1 EncDecAttention (decoder only; k|v stacked)
+  float* ln_ff = nullptr;  Linear wi, wo;           // DenseReluDense (wi_0/wi_1 interleaved -> gated epilogue)
+};
+
+int load_layers(const ymt3_t5_cfg_t& c, const TensorTable& tt, bool decoder, DevicePool& pool,
+                std::vector<T5Layer>& layers, float** final_ln, cudaStream_t s) {
+  const int D = c.d_model, inner = c.num_heads * c.d_kv, F = c.d_ff;
+  layers.resize(c.num_layers);
+  for (int i = 0; i < c.num_layers; ++i) {
+    T5Layer& L = layers[i];
+    const std::string b = "block." + std::to_string(i) + ".layer.";
+    const std::string sa = b + "0.SelfAttention.";
+    int rc;
+    if ((rc = pack_vec(pool, {tt.require(b + "0.layer_norm.weight", D)}, false, &L.ln_sa, s))) return rc;
+    if ((rc = pack_rows(pool, {tt.require(sa + "q.weight", inner, D), tt.require(sa + "k.weight", inner, D),
+                               tt.require(sa + "v.weight", inner, D)}, D, c.precision, false, &L.qkv, s))) return rc;
+    if ((rc = pack_rows(pool, {tt.require(sa + "o.weight", D, inner)}, inner, c.precision, false, &L.o, s))) return rc;
+    std::string ff = b + "1.";
+    if (decoder) {
+      const std::string ca = b + "1.EncDecAttention.";
+      if ((rc = pack_vec(pool, {tt.require(b + "1.layer_norm.weight", D)}, false, &L.ln_ca, s))) return rc;
+      if ((rc = pack_rows(pool, {tt.require(ca + "q.weight", inner, D)}, D, c.precision, false, &L.xq, s))) return rc;
+      if ((rc = pack_rows(pool, {tt.require(ca + "k.weight", inner, D), tt.require(ca + "v.weight", inner, D)}, D,
+                          c.precision, false, &L.xkv, s))) return rc;
+      if ((rc = pack_rows(pool, {tt.require(ca + "o.weight", D, inner)}, inner, c.precision, false, &L.xo, s))) return rc;
+      ff = b + "2.";
+    }
+    if ((rc = pack_vec(pool, {tt.require(ff + "layer_norm.weight", D)}, false, &L.ln_ff, s))) return rc;
+    if ((rc = pack_rows(pool, {tt.require(ff + "DenseReluDense.wi_0.weight", F, D),
+                               tt.require(ff + "DenseReluDense.wi_1.weight", F, D)}, D, c.precision, true, &L.wi, s)))
+      return rc;
+    if ((rc = pack_rows(pool, {tt.require(ff + "DenseReluDense.wo.weight", D, F)}, F, c.precision, false, &L.wo, s)))
+      return rc;
+  }
+  return pack_vec(pool, {tt.require("final_layer_norm.weight", D)}, false, final_ln, s);
+}
+
+int check_cfg(const ymt3_t5_cfg_t* c) {
+  YMT3_REQUIRE(c, "t5: null config");
+  YMT3_REQUIRE(c->precision == YMT3_F32 || c->precision == YMT3_BF16, "t5: bad precision %d", c->precision);
+  YMT3_REQUIRE(c->d_model > 0 && c->d_model % 8 == 0 && c->num_heads > 0 && c->d_kv > 0 && c->d_kv % 4 == 0 &&
+                   c->d_ff > 0 && c->d_ff % 8 == 0 && c->num_layers > 0,
+               "t5: bad dimensions");
+  return YMT3_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// encoder
+// ------------------------------------------------------------------------------------------
+struct ymt3_t5enc {
+  ymt3_t5_cfg_t c;
+  DevicePool weights, ws;
+  std::vector<T5Layer> layers;
+  float* final_ln = nullptr;
+  void* pos = nullptr;
+  int n_pos = 0;
+  int64_t cap_rows = 0;
+  void *x = nullptr, *h = nullptr, *qkv = nullptr, *attn = nullptr, *g = nullptr;
+};
+
+extern "C" int ymt3_t5enc_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* tensors, int n, ymt3_t5enc_t** out) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  YMT3_REQUIRE(tensors && out, "t5enc_create: null argument");
+  ymt3_t5enc* e = new ymt3_t5enc();
+  e->c = *cfg;
+  TensorTable tt{tensors, n};
+  rc = load_layers(*cfg, tt, false, e->weights, e->layers, &e->final_ln, 0);
+  if (!rc) {
+    if (const ymt3_tensor_t* p = tt.find("pos_table")) {
+      if (p->ndim != 2 || p->shape[1] != cfg->d_model) {
+        ymt3_set_error("t5enc_create: pos_table must be (n_pos, d_model)");
+        rc = YMT3_ERR_INVALID;
+      } else {
+        e->n_pos = (int)p->shape[0];
+        rc = pack_table(e->weights, (const float*)p->data, false, p->shape[0] * p->shape[1], cfg->precision, &e->pos, 0);
+      }
+    }
+  }
+  if (!rc && cudaStreamSynchronize(0) != cudaSuccess) {
+    ymt3_set_error("t5enc_create: weight packing failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = YMT3_ERR_CUDA;
+  }
+  if (rc) {
+    e->weights.release();
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return YMT3_OK;
+}
+
+extern "C" int ymt3_t5enc_destroy(ymt3_t5enc_t* e) {
+  if (!e) return YMT3_OK;
+  e->weights.release();
+  e->ws.release();
+  delete e;
+  return YMT3_OK;
+}
+
+extern "C" int ymt3_t5enc_forward(ymt3_t5enc_t* e, const float* x_in, int64_t B, int64_t S, void* out, void* stream) {
+  YMT3_REQUIRE(e && out, "t5enc_forward: null argument");
+  if (B <= 0 || S <= 0) return YMT3_OK;
+  YMT3_REQUIRE(x_in, "t5enc_forward: null input");
+  const ymt3_t5_cfg_t& c = e->c;
+  const int D = c.d_model, H = c.num_heads, dk = c.d_kv, inner = H * dk, F = c.d_ff, dt = c.precision;
+  const int64_t M = B * S;
+  YMT3_REQUIRE(M < (1ll << 31), "t5enc_forward: too many tokens");
+  YMT3_REQUIRE(!e->pos || S <= e->n_pos, "t5enc_forward: sequence %lld longer than pos_table %d", (long long)S, e->n_pos);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M > e->cap_rows) {
+    YMT3_CUDA_CHECK(cudaStreamSynchronize(s));
+    e->ws.release();
+    const size_t es = dtype_size(dt);
+    e->x = e->ws.alloc(M * D * es);
+    e->h = e->ws.alloc(M * D * es);
+    e->qkv = e->ws.alloc(M * 3 * inner * es);
+    e->attn = e->ws.alloc(M * inner * es);
+    e->g = e->ws.alloc(M * F * es);
+    e->cap_rows = 0;
+    if (!e->x || !e->h || !e->qkv || !e->attn || !e->g) return YMT3_ERR_CUDA;
+    e->cap_rows = M;
+  }
+  int rc;
+  // inputs_embeds (+ absolute position table [RECALL upstream]); dropout is identity in eval
+  if ((rc = convert(x_in, YMT3_F32, e->x, dt, M * D, s))) return rc;
+  if (e->pos && (rc = add_rows(e->x, e->pos, e->x, M, (int)S, D, dt, s))) return rc;
+  const size_t es = dtype_size(dt);
+  for (const T5Layer& L : e->layers) {
+    // T5LayerSelfAttention (modeling_t5.py:356-377): x += o(attn(rmsnorm(x)))
+    if ((rc = rmsnorm(e->x, L.ln_sa, e->h, M, D, c.layer_norm_eps, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, e->h, D, L.qkv, e->qkv, 3 * inner, (int)M, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
+    AttnParams a{};
+    a.Q = e->qkv; a.K = (char*)e->qkv + inner * es; a.V = (char*)e->qkv + 2 * inner * es;
+    a.q_sb = a.k_sb = a.v_sb = S * 3 * inner; a.q_sh = a.k_sh = a.v_sh = dk; a.q_ss = a.k_ss = a.v_ss = 3 * inner;
+    a.O = e->attn; a.o_sb = S * inner; a.o_sh = dk; a.o_ss = inner;
+    a.B = (int)B; a.H = H; a.Sq = (int)S; a.Sk = (int)S; a.dk = dk;
+    a.scale = 1.0f;  // T5: no 1/sqrt(d) (modeling_t5.py:308)
+    if ((rc = attention(a, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, e->attn, inner, L.o, e->x, D, (int)M, 0, 0, e->x, D, 1.f, dt, s))) return rc;
+    // T5LayerFF (modeling_t5.py:146-150) with gated-GELU (:115-131)
+    if ((rc = rmsnorm(e->x, L.ln_ff, e->h, M, D, c.layer_norm_eps, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, e->h, D, L.wi, e->g, F, (int)M, YMT3_ACT_GELU_NEW, 1, nullptr, 0, 1.f, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, e->g, F, L.wo, e->x, D, (int)M, 0, 0, e->x, D, 1.f, dt, s))) return rc;
+  }
+  return rmsnorm(e->x, e->final_ln, out, M, D, c.layer_norm_eps, dt, s);  // final_layer_norm (:767)
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder + greedy generation
+// ------------------------------------------------------------------------------------------
+struct ymt3_t5dec {
+  ymt3_t5_cfg_t c;
+  DevicePool weights, ws;
+  std::vector<T5Layer> layers;
+  float* final_ln = nullptr;
+  void* pos = nullptr;
+  int n_pos = 0;
+  void* embed = nullptr;     // (V, D) compute dtype
+  Linear lm_head;            // (Vp, D), rows >= V are zero
+  int Vp = 0;
+  // per-(N, T_enc, Lmax) state
+  int64_t cap_N = 0, cap_T = 0, cap_L = 0;
+  void *x = nullptr, *h = nullptr, *qkv = nullptr, *attn = nullptr, *qx = nullptr, *g = nullptr;
+  float* logits = nullptr;
+  std::vector<void*> selfK, selfV, crossKV;
+  int *d_step = nullptr, *d_cur = nullptr, *d_fin = nullptr, *d_unfinished = nullptr;
+  int* h_unfinished = nullptr;  // pinned
+  // cached CUDA graph of one decode step
+  cudaGraphExec_t graph = nullptr;
+  int64_t graph_N = -1, graph_T = -1, graph_L = -1;
+  int graph_stop = -1;
+  int32_t* graph_tokens = nullptr;
+};
+
+extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* tensors, int n, ymt3_t5dec_t** out) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  YMT3_REQUIRE(tensors && out, "t5dec_create: null argument");
+  YMT3_REQUIRE(cfg->d_kv == 64, "t5dec_create: d_kv must be 64 (decode attention kernel)");
+  YMT3_REQUIRE(cfg->vocab_size > 1 && cfg->max_length > 0, "t5dec_create: bad vocab/max_length");
+  ymt3_t5dec* d = new ymt3_t5dec();
+  d->c = *cfg;
+  TensorTable tt{tensors, n};
+  const int D = cfg->d_model, V = cfg->vocab_size;
+  rc = load_layers(*cfg, tt, true, d->weights, d->layers, &d->final_ln, 0);
+  if (!rc) {
+    const ymt3_tensor_t* E = tt.require("embed_tokens.weight", V, D);
+    if (!E) rc = YMT3_ERR_INVALID;
+    if (!rc) rc = pack_table(d->weights, (const float*)E->data, false, (int64_t)V * D, cfg->precision, &d->embed, 0);
+    if (!rc) {
+      const ymt3_tensor_t* Lm = tt.find("lm_head.weight") ? tt.require("lm_head.weight", V, D) : E;
+      if (!Lm) rc = YMT3_ERR_INVALID;
+      if (!rc) {
+        d->Vp = (V + 7) / 8 * 8;
+        void* W = d->weights.alloc((size_t)d->Vp * D * dtype_size(cfg->precision));
+        if (!W) rc = YMT3_ERR_CUDA;
+        if (!rc && cudaMemsetAsync(W, 0, (size_t)d->Vp * D * dtype_size(cfg->precision), 0) != cudaSuccess) rc = YMT3_ERR_CUDA;
+        if (!rc) rc = convert(Lm->data, YMT3_F32, W, cfg->precision, (int64_t)V * D, 0);
+        d->lm_head.W = W; d->lm_head.N = d->Vp; d->lm_head.K = D;
+      }
+    }
+  }
+  if (!rc) {
+    if (const ymt3_tensor_t* p = tt.find("pos_table")) {
+      if (p->ndim != 2 || p->shape[1] != D || p->shape[0] < cfg->max_length) {
+        ymt3_set_error("t5dec_create: pos_table must be (>= max_length, d_model)");
+        rc = YMT3_ERR_INVALID;
+      } else {
+        d->n_pos = (int)p->shape[0];
+        rc = pack_table(d->weights, (const float*)p->data, false, p->shape[0] * p->shape[1], cfg->precision, &d->pos, 0);
+      }
+    }
+  }
+  if (!rc) {
+    d->d_step = (int*)d->weights.alloc(64);
+    d->d_unfinished = d->d_step + 4;
+    if (!d->d_step) rc = YMT3_ERR_CUDA;
+    if (!rc && cudaMallocHost((void**)&d->h_unfinished, 64) != cudaSuccess) rc = YMT3_ERR_CUDA;
+  }
+  if (!rc && cudaStreamSynchronize(0) != cudaSuccess) {
+    ymt3_set_error("t5dec_create: weight packing failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = YMT3_ERR_CUDA;
+  }
+  if (rc) {
+    d->weights.release();
+    delete d;
+    return rc;
+  }
+  *out = d;
+  return YMT3_OK;
+}
+
+extern "C" int ymt3_t5dec_destroy(ymt3_t5dec_t* d) {
+  if (!d) return YMT3_OK;
+  if (d->graph) cudaGraphExecDestroy(d->graph);
+  if (d->h_unfinished) cudaFreeHost(d->h_unfinished);
+  d->weights.release();
+  d->ws.release();
+  delete d;
+  return YMT3_OK;
+}
+
+namespace {
+
+int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, cudaStream_t s) {
+  if (N <= d->cap_N && T <= d->cap_T && Lmax <= d->cap_L) return YMT3_OK;
+  YMT3_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (d->graph) {
+    cudaGraphExecDestroy(d->graph);
+    d->graph = nullptr;
+    d->graph_N = -1;
+  }
+  d->ws.release();
+  d->cap_N = d->cap_T = d->cap_L = 0;
+  const ymt3_t5_cfg_t& c = d->c;
+  const int D = c.d_model, inner = c.num_heads * c.d_kv, F = c.d_ff;
+  const size_t es = dtype_size(c.precision);
+  const int64_t cN = N > d->cap_N ? N : d->cap_N, cT = T > d->cap_T ? T : d->cap_T, cL = Lmax > d->cap_L ? Lmax : d->cap_L;
+  d->x = d->ws.alloc(cN * D * es);
+  d->h = d->ws.alloc(cN * D * es);
+  d->qkv = d->ws.alloc(cN * 3 * inner * es);
+  d->attn = d->ws.alloc(cN * inner * es);
+  d->qx = d->ws.alloc(cN * inner * es);
+  d->g = d->ws.alloc(cN * F * es);
+  d->logits = (float*)d->ws.alloc(cN * d->Vp * 4);
+  d->d_cur = (int*)d->ws.alloc(cN * 4);
+  d->d_fin = (int*)d->ws.alloc(cN * 4);
+  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin;
+  d->selfK.assign(c.num_layers, nullptr);
+  d->selfV.assign(c.num_layers, nullptr);
+  d->crossKV.assign(c.num_layers, nullptr);
+  for (int i = 0; ok && i < c.num_layers; ++i) {
+    d->selfK[i] = d->ws.alloc(cN * inner * cL * es);
+    d->selfV[i] = d->ws.alloc(cN * inner * cL * es);
+    d->crossKV[i] = d->ws.alloc(cN * cT * 2 * inner * es);
+    ok = d->selfK[i] && d->selfV[i] && d->crossKV[i];
+  }
+  if (!ok) {
+    d->ws.release();
+    return YMT3_ERR_CUDA;
+  }
+  d->cap_N = cN; d->cap_T = cT; d->cap_L = cL;
+  return YMT3_OK;
+}
+
+// all kernels of ONE decode step; every step-dependent value is read from device memory
+int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int32_t* tokens_out, cudaStream_t s) {
+  const ymt3_t5_cfg_t& c = d->c;
+  const int D = c.d_model, H = c.num_heads, dk = c.d_kv, inner = H * dk, F = c.d_ff, dt = c.precision;
+  const size_t es = dtype_size(dt);
+  int rc;
+  if ((rc = embed_pos(d->d_cur, d->embed, d->pos, d->d_step, d->x, (int)N, D, dt, s))) return rc;
+  for (int i = 0; i < c.num_layers; ++i) {
+    const T5Layer& L = d->layers[i];
+    // self-attention over the device-resident cache (modeling_t5.py:269-305, 356-377)
+    if ((rc = rmsnorm(d->x, L.ln_sa, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, d->h, D, L.qkv, d->qkv, 3 * inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
+    if ((rc = decode_attention(d->qkv, 3 * inner, (char*)d->qkv + inner * es, (char*)d->qkv + 2 * inner * es, 3 * inner,
+                               d->selfK[i], d->selfV[i], (int64_t)H * d->cap_L * dk, (int64_t)d->cap_L * dk, dk, Lmax,
+                               d->d_step, 0, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
+      return rc;
+    if ((rc = linear_fwd(dt, d->attn, inner, L.o, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
+    // cross-attention over encoder K/V computed once (modeling_t5.py:387-408)
+    if ((rc = rmsnorm(d->x, L.ln_ca, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, d->h, D, L.xq, d->qx, inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
+    if ((rc = decode_attention(d->qx, inner, nullptr, nullptr, 0, d->crossKV[i], (char*)d->crossKV[i] + inner * es,
+                               T * 2 * inner, dk, 2 * inner, 0, d->d_step, (int)T, 1.0f, d->attn, inner, (int)N, H, dk,
+                               dt, s)))
+      return rc;
+    if ((rc = linear_fwd(dt, d->attn, inner, L.xo, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
+    // gated-GELU feed-forward
+    if ((rc = rmsnorm(d->x, L.ln_ff, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, d->h, D, L.wi, d->g, F, (int)N, YMT3_ACT_GELU_NEW, 1, nullptr, 0, 1.f, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, d->g, F, L.wo, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
+  }
+  if ((rc = rmsnorm(d->x, d->final_ln, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
+  // LM head; tied embeddings scale hidden by d_model^-0.5 (modeling_t5.py:1105-1110)
+  const float sc = c.tie_word_embeddings ? 1.0f / sqrtf((float)D) : 1.0f;
+  if ((rc = linear_fwd(dt, d->h, D, d->lm_head, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s))) return rc;
+  if ((rc = greedy_select(d->logits, d->Vp, c.vocab_size, (int)N, d->d_step, d->d_cur, d->d_fin, tokens_out, Lmax,
+                          c.eos_id, c.pad_id, stop_at_eos, d->d_unfinished, s)))
+    return rc;
+  return advance_step(d->d_step, d->d_unfinished, s);
+}
+
+}  // namespace
+
+extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int32_t max_len,
+                                   int32_t stop_at_eos, int32_t early_stop_interval, int32_t* tokens_out, void* stream) {
+  YMT3_REQUIRE(d && tokens_out, "t5dec_generate: null argument");
+  if (N <= 0) return YMT3_OK;
+  YMT3_REQUIRE(enc_hs && T > 0, "t5dec_generate: bad encoder states");
+  YMT3_REQUIRE(max_len > 0 && max_len <= d->c.max_length, "t5dec_generate: max_len %d outside (0, %d]", max_len,
+               d->c.max_length);
+  const ymt3_t5_cfg_t& c = d->c;
+  const int D = c.d_model, inner = c.num_heads * c.d_kv, dt = c.precision;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = dec_ensure(d, N, T, max_len, s))) return rc;
+  // state init (device side)
+  if ((rc = fill_i32(d->d_step, 0, 8, s))) return rc;  // step + unfinished[2] (+pad)
+  if ((rc = fill_i32(d->d_cur, c.start_id, N, s))) return rc;
+  if ((rc = fill_i32(d->d_fin, 0, N, s))) return rc;
+  if ((rc = fill_i32(tokens_out, c.pad_id, N * max_len, s))) return rc;
+  // cross-attention K/V of every layer, once (modeling_t5.py:287-299)
+  for (int i = 0; i < c.num_layers; ++i)
+    if ((rc = linear_fwd(dt, enc_hs, D, d->layers[i].xkv, d->crossKV[i], 2 * inner, (int)(N * T), 0, 0, nullptr, 0, 1.f,
+                         dt, s)))
+      return rc;
+
+  // one decode step captured into a CUDA graph (all step-dependent scalars live on the device)
+  bool use_graph = getenv("YMT3_NO_GRAPH") == nullptr;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (use_graph && cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) use_graph = false;
+  if (use_graph && (!d->graph || d->graph_N != N || d->graph_T != T || d->graph_L != max_len ||
+                    d->graph_tokens != tokens_out || d->graph_stop != stop_at_eos)) {
+    if (d->graph) {
+      cudaGraphExecDestroy(d->graph);
+      d->graph = nullptr;
+    }
+    cudaGraph_t g = nullptr;
+    YMT3_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, s);
+    cudaError_t ce = cudaStreamEndCapture(s, &g);
+    if (rc) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    YMT3_CUDA_CHECK(ce);
+    ce = cudaGraphInstantiate(&d->graph, g, 0);
+    cudaGraphDestroy(g);
+    YMT3_CUDA_CHECK(ce);
+    d->graph_N = N; d->graph_T = T; d->graph_L = max_len;
+    d->graph_tokens = tokens_out;
+    d->graph_stop = stop_at_eos;
+  }
+  for (int t = 0; t < max_len; ++t) {
+    if (use_graph) {
+      YMT3_CUDA_CHECK(cudaGraphLaunch(d->graph, s));
+    } else if ((rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, s))) {
+      return rc;
+    }
+    if (stop_at_eos && early_stop_interval > 0 && (t + 1) % early_stop_interval == 0 && t + 1 < max_len) {
+      // rows still unfinished after step t were counted into slot (t & 1)
+      YMT3_CUDA_CHECK(cudaMemcpyAsync(d->h_unfinished, d->d_unfinished + (t & 1), 4, cudaMemcpyDeviceToHost, s));
+      YMT3_CUDA_CHECK(cudaStreamSynchronize(s));
+      if (*d->h_unfinished == 0) break;
+    }
+  }
+  return YMT3_OK;
+}
+
+extern "C" int ymt3_t5dec_last_logits(ymt3_t5dec_t* d, float* out, int64_t N, void* stream) {
+  YMT3_REQUIRE(d && out && N <= d->cap_N, "t5dec_last_logits: bad argument");
+  YMT3_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)d->c.vocab_size * 4, d->logits, (size_t)d->Vp * 4,
+                                    (size_t)d->c.vocab_size * 4, (size_t)N, cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream));
+  return YMT3_OK;
+}

@@ -1,0 +1,118 @@
+"""``YourMT3`` with the reference's inference API surface (upstream amt/src/model/ymt3.py [RECALL]):
+
+    model.spectrogram / .pre_encoder / .encoder / .pre_decoder / .decoder / .embed_tokens / .lm_head
+    model.encode(x)                         -> encoder hidden states
+    model.inference(x, task_tokens=None)    -> (B, L) | (B, C, L) token ids
+    model.inference_file(bsz, audio_segments) -> list of per-batch numpy arrays
+
+Only the inference path exists (training / Lightning hooks are out of scope).
+Every stage is a native call; nothing falls back to eager PyTorch.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .config import get_audio_cfg, get_model_cfg
+from .lm_head import LMHead
+from .spectrogram import get_spectrogram_layer_from_audio_cfg
+from .t5mod import MultiChannelT5Decoder, T5DecoderYMT3, T5EncoderYMT3
+from .t5mod_helper import task_cond_dec_generate
+
+
+class YourMT3(nn.Module):
+    def __init__(self, audio_cfg: Optional[Dict] = None, model_cfg: Optional[Dict] = None, precision: str = "f32",
+                 eos_id: int = 1, pad_id: int = 0, **unused):
+        super().__init__()
+        self.audio_cfg = audio_cfg = audio_cfg or get_audio_cfg()
+        self.model_cfg = model_cfg = model_cfg or get_model_cfg()
+        if precision not in ("f32", "bf16"):
+            raise ValueError("precision must be 'f32' or 'bf16'")
+        self.precision = precision
+        self._prec = {"f32": _lib.DTYPE_F32, "bf16": _lib.DTYPE_BF16}[precision]
+        self.eos_id, self.pad_id = eos_id, pad_id
+        self.encoder_type, self.decoder_type = model_cfg["encoder_type"], model_cfg["decoder_type"]
+        self.vocab_size = int(model_cfg["vocab_size"])
+        self.max_token_length = int(model_cfg["event_length"])
+        self.tie_word_embeddings = bool(model_cfg["tie_word_embeddings"])
+
+        self.spectrogram, (self.feat_length, self.feat_dim) = get_spectrogram_layer_from_audio_cfg(audio_cfg)
+        dec_cfg = dict(model_cfg["decoder"][self.decoder_type])
+        dec_cfg["vocab_size"] = self.vocab_size
+        n_pos = max(self.feat_length, self.max_token_length) + 8
+
+        pre_enc = model_cfg["pre_encoder_type"]
+        if pre_enc == "default":
+            pre_enc = model_cfg["pre_encoder_type_default"][self.encoder_type]
+        pre_dec = model_cfg["pre_decoder_type"]
+        if pre_dec == "default":
+            pre_dec = model_cfg["pre_decoder_type_default"][self.encoder_type][self.decoder_type]
+
+        if self.encoder_type == "t5":
+            enc_cfg = dict(model_cfg["encoder"]["t5"])
+            if enc_cfg["d_model"] != self.feat_dim:
+                raise ValueError("T5 encoder consumes the spectrogram directly: d_model must equal the feature width")
+            self.pre_encoder = nn.Identity() if pre_enc is None else self._unsupported("pre_encoder", pre_enc)
+            self.encoder = T5EncoderYMT3(enc_cfg, precision=precision, num_max_positions=n_pos)
+            self.pre_decoder = nn.Identity() if pre_dec is None else self._unsupported("pre_decoder", pre_dec)
+        elif self.encoder_type == "perceiver-tf":
+            from .perceiver_mod import build_perceiver_tf_stages  # noqa: WPS433 (kept optional until built)
+            self.pre_encoder, self.encoder, self.pre_decoder = build_perceiver_tf_stages(
+                self, audio_cfg, model_cfg, pre_enc, pre_dec, precision)
+        else:
+            raise NotImplementedError(f"encoder_type={self.encoder_type!r} (conformer is out of scope, SURVEY 2b)")
+
+        if self.decoder_type == "t5":
+            self.decoder = T5DecoderYMT3(dec_cfg, num_max_positions=n_pos)
+        elif self.decoder_type == "multi-t5":
+            self.decoder = MultiChannelT5Decoder(dec_cfg, num_max_positions=n_pos)
+        else:
+            raise NotImplementedError(f"decoder_type={self.decoder_type!r}")
+        self.embed_tokens = nn.Embedding(self.vocab_size, dec_cfg["d_model"])
+        self.lm_head = LMHead(dec_cfg, model_cfg.get("init_factor", 1.0), self.tie_word_embeddings)
+        if self.tie_word_embeddings:
+            self.lm_head.lm_head.weight = self.embed_tokens.weight
+        self.eval()
+
+    @staticmethod
+    def _unsupported(kind, name):
+        raise NotImplementedError(f"{kind} type {name!r} is not on the benchmarked path")
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        """x: (B, 1, L) f32 CUDA audio -> encoder hidden states for the decoder
+        ((B, T, D) or (B, C, T, D)), in the model precision."""
+        feats = self.spectrogram(x)                                   # (B, T, F) f32
+        feats = self.pre_encoder(feats)
+        enc_hs = self.encoder(inputs_embeds=feats)["last_hidden_state"]
+        return self.pre_decoder(enc_hs)
+
+    @torch.no_grad()
+    def inference(self, x: torch.Tensor, task_tokens: Optional[torch.Tensor] = None,
+                  max_token_length: Optional[int] = None, stop_at_eos: bool = True,
+                  early_stop_interval: int = 0, **unused) -> torch.Tensor:
+        """x: (B, 1, L) audio segments -> token ids (B, L_tok) or (B, C, L_tok) (LongTensor, CUDA)."""
+        max_len = max_token_length or self.max_token_length
+        enc_hs = self.encode(x)
+        return task_cond_dec_generate(self.decoder, self.decoder_type, self.embed_tokens, self.lm_head, enc_hs,
+                                      prefix_ids=task_tokens, max_length=max_len, stop_at_eos=stop_at_eos,
+                                      eos_id=self.eos_id, pad_id=self.pad_id, decoder_start_token_id=self.pad_id,
+                                      precision=self._prec, early_stop_interval=early_stop_interval)
+
+    @torch.no_grad()
+    def inference_file(self, bsz: int, audio_segments: torch.Tensor, note_token_array=None, task_token_array=None,
+                       **kw) -> List[np.ndarray]:
+        """audio_segments: (n_seg, 1, L) f32 (CPU or CUDA).  Returns a list with one int array of
+        predicted token ids per batch of ``bsz`` segments (reference return shape [RECALL])."""
+        n = audio_segments.shape[0]
+        dev = next(self.parameters()).device
+        out = []
+        for i in range(0, n, bsz):
+            x = audio_segments[i:i + bsz].to(dev, torch.float32, non_blocking=True)
+            out.append(self.inference(x, None, **kw).cpu().numpy())
+        return out

@@ -182,6 +182,10 @@ struct ymt3_t5dec {
   std::vector<void*> selfK, selfV, crossKV;
   int *d_step = nullptr, *d_cur = nullptr, *d_fin = nullptr, *d_unfinished = nullptr;
   int* h_unfinished = nullptr;  // pinned
+  // the decode loop runs on an internal stream (graph capture is illegal on the legacy default
+  // stream); it is ordered after / before the caller's stream with events, no host sync
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // cached CUDA graph of one decode step
   cudaGraphExec_t graph = nullptr;
   int64_t graph_N = -1, graph_T = -1, graph_L = -1;
@@ -233,6 +237,9 @@ extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
     d->d_unfinished = d->d_step + 4;
     if (!d->d_step) rc = YMT3_ERR_CUDA;
     if (!rc && cudaMallocHost((void**)&d->h_unfinished, 64) != cudaSuccess) rc = YMT3_ERR_CUDA;
+    if (!rc && cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = YMT3_ERR_CUDA;
+    if (!rc && cudaEventCreateWithFlags(&d->ev_in, cudaEventDisableTiming) != cudaSuccess) rc = YMT3_ERR_CUDA;
+    if (!rc && cudaEventCreateWithFlags(&d->ev_out, cudaEventDisableTiming) != cudaSuccess) rc = YMT3_ERR_CUDA;
   }
   if (!rc && cudaStreamSynchronize(0) != cudaSuccess) {
     ymt3_set_error("t5dec_create: weight packing failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -251,6 +258,9 @@ extern "C" int ymt3_t5dec_destroy(ymt3_t5dec_t* d) {
   if (!d) return YMT3_OK;
   if (d->graph) cudaGraphExecDestroy(d->graph);
   if (d->h_unfinished) cudaFreeHost(d->h_unfinished);
+  if (d->own_stream) cudaStreamDestroy(d->own_stream);
+  if (d->ev_in) cudaEventDestroy(d->ev_in);
+  if (d->ev_out) cudaEventDestroy(d->ev_out);
   d->weights.release();
   d->ws.release();
   delete d;
@@ -351,8 +361,16 @@ extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t 
                d->c.max_length);
   const ymt3_t5_cfg_t& c = d->c;
   const int D = c.d_model, inner = c.num_heads * c.d_kv, dt = c.precision;
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t caller = (cudaStream_t)stream;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const bool caller_capturing = cudaStreamIsCapturing(caller, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+  // run on the internal stream unless the caller is itself capturing (then stay in its capture)
+  cudaStream_t s = caller_capturing ? caller : d->own_stream;
   int rc;
+  if (!caller_capturing) {
+    YMT3_CUDA_CHECK(cudaEventRecord(d->ev_in, caller));
+    YMT3_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_in, 0));
+  }
   if ((rc = dec_ensure(d, N, T, max_len, s))) return rc;
   // state init (device side)
   if ((rc = fill_i32(d->d_step, 0, 8, s))) return rc;  // step + unfinished[2] (+pad)
@@ -366,9 +384,7 @@ extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t 
       return rc;
 
   // one decode step captured into a CUDA graph (all step-dependent scalars live on the device)
-  bool use_graph = getenv("YMT3_NO_GRAPH") == nullptr;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (use_graph && cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) use_graph = false;
+  const bool use_graph = getenv("YMT3_NO_GRAPH") == nullptr && !caller_capturing;
   if (use_graph && (!d->graph || d->graph_N != N || d->graph_T != T || d->graph_L != max_len ||
                     d->graph_tokens != tokens_out || d->graph_stop != stop_at_eos)) {
     if (d->graph) {
@@ -403,6 +419,10 @@ extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t 
       YMT3_CUDA_CHECK(cudaStreamSynchronize(s));
       if (*d->h_unfinished == 0) break;
     }
+  }
+  if (!caller_capturing) {
+    YMT3_CUDA_CHECK(cudaEventRecord(d->ev_out, s));
+    YMT3_CUDA_CHECK(cudaStreamWaitEvent(caller, d->ev_out, 0));
   }
   return YMT3_OK;
 }

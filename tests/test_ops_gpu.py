@@ -111,3 +111,75 @@ def test_attention(cuda_device, native_lib, B, H, Sq, Sk, dk, causal):
     _lib.check(native_lib.ymt3_op_attention(0, qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, H, Sq, Sk, dk,
                                             scale, causal, torch.cuda.current_stream().cuda_stream))
     _close(o.cpu(), ref, 1e-5)
+
+
+# ----------------------------------------------------------------------------------------------
+# bf16 path: tcgen05 GEMM (TMEM accumulators, TMA operands). Reference = fp32 matmul of the
+# bf16-rounded operands; tolerance = bf16 output rounding (2^-8) + fp32 accumulation noise.
+# ----------------------------------------------------------------------------------------------
+def linear_bf16_native(lib, dev, A, W, bias=None, act=0, gated=0, residual=None, out_scale=1.0, out_f32=False):
+    M, K = A.shape
+    N = W.shape[0]
+    Ad, Wd = A.to(dev, torch.bfloat16), W.to(dev, torch.bfloat16)
+    No = N // 2 if gated else N
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    C_ = torch.full((M, No), float("nan"), device=dev, dtype=odt)
+    bd = None if bias is None else bias.to(dev)
+    Rd = None if residual is None else residual.to(dev, odt)
+    rc = lib.ymt3_op_linear(1, Ad.data_ptr(), K, Wd.data_ptr(), K, None if bd is None else bd.data_ptr(), C_.data_ptr(),
+                            No, None if Rd is None else Rd.data_ptr(), No, M, N, K, act, gated, out_scale,
+                            0 if out_f32 else 1, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "op_linear bf16")
+    torch.cuda.synchronize()
+    return C_.float().cpu()
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 128, 64), (128, 32, 64), (1, 64, 128), (200, 1152, 512), (832, 512, 384), (5000, 2048, 512),
+    (40000, 512, 1024), (333, 600, 512), (16384, 128, 256), (77, 96, 72), (300, 1536, 128),
+])
+def test_linear_bf16_tcgen05_shapes(cuda_device, native_lib, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    ref = _bf(A) @ _bf(W).T
+    got = linear_bf16_native(native_lib, cuda_device, A, W)
+    _close(got, ref, 6e-3)
+    got32 = linear_bf16_native(native_lib, cuda_device, A, W, out_f32=True)
+    _close(got32, ref, 2e-5)          # fp32 accumulate in TMEM, fp32 out: only summation order differs
+
+
+@pytest.mark.parametrize("act,gated", [(0, 0), (1, 1), (3, 1), (4, 0), (2, 0)])
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_linear_bf16_epilogues(cuda_device, native_lib, act, gated, out_f32):
+    g = torch.Generator().manual_seed(17 * act + gated)
+    M, N, K = 300, 256, 192
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.1
+    bias = torch.randn(N, generator=g)
+    R = torch.randn(M, N // 2 if gated else N, generator=g)
+    z = _bf(A) @ _bf(W).T + bias
+    ref = ACTS[act](z[:, 0::2]) * z[:, 1::2] if gated else ACTS[act](z)
+    ref = (R if out_f32 else _bf(R)) + 0.5 * ref
+    got = linear_bf16_native(native_lib, cuda_device, A, W, bias, act, gated, R, 0.5, out_f32)
+    _close(got, ref, 3e-5 if out_f32 else 6e-3)
+
+
+def test_norm_attention_bf16_io(cuda_device, native_lib):
+    g = torch.Generator().manual_seed(5)
+    x, w = torch.randn(100, 512, generator=g), torch.randn(512, generator=g)
+    xd, wd = x.to(cuda_device, torch.bfloat16), w.to(cuda_device)
+    y = torch.empty_like(xd)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(native_lib.ymt3_op_rmsnorm(1, xd.data_ptr(), wd.data_ptr(), y.data_ptr(), 100, 512, 1e-6, s))
+    _close(y.float().cpu(), OT.rms_norm(_bf(x), w, 1e-6), 6e-3)
+    B, H, Sq, Sk, dk = 2, 6, 50, 70, 64
+    q, k, v = (torch.randn(B, S, H, dk, generator=g) * 0.5 for S in (Sq, Sk, Sk))
+    ref = OT.attention(_bf(q).transpose(1, 2), _bf(k).transpose(1, 2), _bf(v).transpose(1, 2)).view(B, Sq, H, dk)
+    qd, kd, vd = (t.to(cuda_device, torch.bfloat16) for t in (q, k, v))
+    o = torch.empty_like(qd)
+    _lib.check(native_lib.ymt3_op_attention(1, qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, H, Sq, Sk, dk,
+                                            1.0, 0, s))
+    _close(o.float().cpu(), ref, 6e-3)

@@ -1,8 +1,406 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged
+// by TMA with 128-byte swizzle) with the fused epilogue of ops.cuh::GemmParams.
+//
+//   C[M, N] = residual + out_scale * row_scale * epi(A[M, K] @ W[N, K]^T + bias)
+//
+// CTA = 192 threads, one 128 x BN output tile:
+//   warp 0     TMA producer  (one elected lane): A box {64 k, 128 m}, W box {64 k, BN n}
+//   warp 1     TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma (K=16) per k-block
+//   warps 2..5 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> epilogue math -> global
+// 3-stage smem ring (<= 96 KB) so that two CTAs are resident per SM and one CTA's epilogue
+// overlaps the other's main loop; TMEM: BN fp32 columns per CTA.
 #include "ops.cuh"
+#include <cuda.h>
+
 namespace ymt3 {
-int gemm_bf16_tc(const GemmParams&, int, cudaStream_t) {
-  ymt3_set_error("gemm_bf16_tc: not built yet");
-  return YMT3_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 3;
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);  // start address (>>4), 14 bits
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+  void* C; int64_t ldc;
+  const float* bias;
+  const void* residual; int64_t ldr;
+  int M, N, K;
+  int act, gated;
+  float out_scale;
+  const float* row_scale;
+  const int* group_offsets;
+  int out_f32;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;  // + barriers/tmem slot + 1024 B alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 2)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  using L = SmemLayout<BN>;
+  // SWIZZLE_128B operand tiles need 1024-byte aligned bases
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int row_end = p.M, m0 = blockIdx.x * BM, w_row0 = blockIdx.y * BN;
+  const int n0 = blockIdx.y * BN;
+  const float* bias = p.bias;
+  if (p.group_offsets) {
+    const int g = blockIdx.z;
+    m0 += p.group_offsets[g];
+    row_end = p.group_offsets[g + 1];
+    w_row0 += g * p.N;
+    if (bias) bias += (int64_t)g * p.N;
+  }
+  if (m0 >= row_end) return;  // uniform for the whole CTA, before any barrier/TMEM use
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        tma_load_2d(&mapA, &full_bar[stage], sa, kb * BK, m0);
+        tma_load_2d(&mapW, &full_bar[stage], sb, kb * BK, w_row0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        const uint64_t adesc = umma_desc_sw128(sa);
+        const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the 128 B swizzle row = +2 in the address field
+          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);     // accumulator complete -> epilogue
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int r = m0 + quad * 32 + lane;       // output row of this thread
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const bool row_ok = r < row_end;
+    const float rs = p.out_scale * ((p.row_scale && row_ok) ? p.row_scale[r] : 1.0f);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);  // warp-collective: no early exit before
+      if (!row_ok) continue;
+      const int c = n0 + c0;
+      if (c >= p.N) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        f[j] = __uint_as_float(v[j]);
+        if (bias && c + j < p.N) f[j] += bias[c + j];
+      }
+      if (p.gated) {
+        // pairs (2j, 2j+1) -> 16 outputs at columns (c >> 1) + j
+        const int co = c >> 1;
+        const int valid = min(16, (p.N - c) >> 1);
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = act_apply(f[2 * j], p.act) * f[2 * j + 1] * rs;
+        if (p.out_f32) {
+          float* C = static_cast<float*>(p.C) + (int64_t)r * p.ldc + co;
+          const float* R = p.residual ? static_cast<const float*>(p.residual) + (int64_t)r * p.ldr + co : nullptr;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (j >= valid) break;
+            float4 q = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            if (R) {
+              const float4 t = *reinterpret_cast<const float4*>(R + j);
+              q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
+            }
+            *reinterpret_cast<float4*>(C + j) = q;
+          }
+        } else {
+          __nv_bfloat16* C = static_cast<__nv_bfloat16*>(p.C) + (int64_t)r * p.ldc + co;
+          const __nv_bfloat16* R =
+              p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)r * p.ldr + co : nullptr;
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            if (j >= valid) break;
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+            if (R) {
+              const uint4 t = *reinterpret_cast<const uint4*>(R + j);
+              const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                h[q] = __floats2bfloat162_rn(o[j + 2 * q] + __bfloat162float(th[q].x),
+                                             o[j + 2 * q + 1] + __bfloat162float(th[q].y));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(o[j + 2 * q], o[j + 2 * q + 1]);
+            }
+            *reinterpret_cast<uint4*>(C + j) = pk;
+          }
+        }
+      } else {
+        const int valid = min(32, p.N - c);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_apply(f[j], p.act) * rs;
+        if (p.out_f32) {
+          float* C = static_cast<float*>(p.C) + (int64_t)r * p.ldc + c;
+          const float* R = p.residual ? static_cast<const float*>(p.residual) + (int64_t)r * p.ldr + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j >= valid) break;
+            float4 q = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            if (R) {
+              const float4 t = *reinterpret_cast<const float4*>(R + j);
+              q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
+            }
+            *reinterpret_cast<float4*>(C + j) = q;
+          }
+        } else {
+          __nv_bfloat16* C = static_cast<__nv_bfloat16*>(p.C) + (int64_t)r * p.ldc + c;
+          const __nv_bfloat16* R =
+              p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)r * p.ldr + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j >= valid) break;
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+            if (R) {
+              const uint4 t = *reinterpret_cast<const uint4*>(R + j);
+              const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                h[q] = __floats2bfloat162_rn(f[j + 2 * q] + __bfloat162float(th[q].x),
+                                             f[j + 2 * q + 1] + __bfloat162float(th[q].y));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+            }
+            *reinterpret_cast<uint4*>(C + j) = pk;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown: everyone done with TMEM, then the allocating warp frees it ----
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major (rows, cols) tensor with leading dimension ld (elements); box {64 cols, box_rows}
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  YMT3_REQUIRE(enc, "gemm_bf16_tc: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YMT3_REQUIRE(r == CUDA_SUCCESS, "gemm_bf16_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+               (long long)rows, (long long)cols, (long long)ld);
+  return YMT3_OK;
+}
+
+template <int BN>
+int launch(const GemmParams& p, int out_dtype, cudaStream_t stream) {
+  CUtensorMap mapA, mapW;
+  int rc;
+  const int groups = p.group_offsets ? p.num_groups : 1;
+  if ((rc = make_map(&mapA, p.A, p.M, p.K, p.lda, BM))) return rc;
+  // grouped: weights of all groups are stacked along rows ((groups*N, K), strideW == N*ldw)
+  if ((rc = make_map(&mapW, p.W, (int64_t)p.N * groups, p.K, p.ldw, BN))) return rc;
+  TcParams t;
+  t.C = p.C; t.ldc = p.ldc; t.bias = p.bias; t.residual = p.residual; t.ldr = p.ldr;
+  t.M = p.M; t.N = p.N; t.K = p.K; t.act = p.act; t.gated = p.gated; t.out_scale = p.out_scale;
+  t.row_scale = p.row_scale; t.group_offsets = p.group_offsets; t.out_f32 = out_dtype == YMT3_F32;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SmemLayout<BN>::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(ymt3_div_up(p.M, BM), ymt3_div_up(p.N, BN), groups);
+  gemm_bf16_tc_kernel<BN><<<grid, THREADS, SmemLayout<BN>::TOTAL, stream>>>(mapA, mapW, t);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
+}  // namespace
+
+int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
+  YMT3_REQUIRE(p.A && p.W && p.C, "gemm_bf16_tc: null pointer");
+  if (p.M <= 0 || p.N <= 0) return YMT3_OK;
+  YMT3_REQUIRE(p.K > 0 && p.K % 8 == 0 && p.lda % 8 == 0 && p.ldw % 8 == 0,
+               "gemm_bf16_tc: K, lda, ldw must be multiples of 8 (K=%d lda=%lld ldw=%lld)", p.K, (long long)p.lda,
+               (long long)p.ldw);
+  YMT3_REQUIRE(p.N % (p.gated ? 16 : 8) == 0, "gemm_bf16_tc: N must be a multiple of %d (N=%d)", p.gated ? 16 : 8, p.N);
+  YMT3_REQUIRE(p.ldc % 8 == 0 && (!p.residual || p.ldr % 8 == 0), "gemm_bf16_tc: ldc/ldr must be multiples of 8");
+  YMT3_REQUIRE((((uintptr_t)p.A | (uintptr_t)p.W | (uintptr_t)p.C | (uintptr_t)p.residual) & 15) == 0,
+               "gemm_bf16_tc: pointers must be 16-byte aligned");
+  YMT3_REQUIRE(!p.group_offsets || p.strideW == (int64_t)p.N * p.ldw,
+               "gemm_bf16_tc: grouped weights must be stacked contiguously");
+  // pick BN so that the grid fills the 148 SMs (2 CTAs/SM resident) when the problem allows
+  const int64_t mt = ymt3_div_up(p.M, BM);
+  const int sms = ymt3_num_sms();
+  if (p.N % 128 == 0 && mt * (p.N / 128) >= 2 * sms) return launch<128>(p, out_dtype, stream);
+  if (p.N >= 64 && mt * ymt3_div_up(p.N, 64) >= sms) return launch<64>(p, out_dtype, stream);
+  return launch<32>(p, out_dtype, stream);
+}
+
 }  // namespace ymt3

@@ -180,7 +180,8 @@ def cpu_baseline(wl, budget_s=12.0):
         dt = time.perf_counter() - t0
         if dt > budget_s or n >= 50:
             break
-    return {"value": wl.ref_batch * SEG_SECONDS * n / dt, "unit": "audio-s/s", "cores": torch.get_num_threads(),
+    scale = wl.reference_scale() if hasattr(wl, "reference_scale") else 1.0
+    return {"value": wl.ref_batch * SEG_SECONDS * n / dt * scale, "unit": "audio-s/s", "cores": torch.get_num_threads(),
             "kind": "reference", "sample": wl.reference_sample() + f", {n} steps in {dt:.1f}s"}
 
 
@@ -198,7 +199,7 @@ def run_reference(args):
     for _ in range(args.steps):
         wl.step_reference()
     dt = time.perf_counter() - t0
-    val = wl.ref_batch * SEG_SECONDS * args.steps / dt
+    val = wl.ref_batch * SEG_SECONDS * args.steps / dt * (wl.reference_scale() if hasattr(wl, "reference_scale") else 1.0)
     line = {"metric": "audio_seconds_per_wall_second", "value": val, "unit": "audio-s/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -61,3 +61,14 @@ def transcribe_t5(sd, audio: np.ndarray, audio_cfg: Dict, model_cfg: Dict, n_pos
         feats = frontend(sd, audio, audio_cfg)
         enc = t5_encode(sd, feats, model_cfg, n_pos)
         return t5_generate(sd, enc, model_cfg, n_pos, max_length, **kw)
+
+
+def transcribe(sd, audio, audio_cfg, model_cfg, n_pos, max_length, **kw):
+    """Dispatch on the encoder family (T5 | Perceiver-TF)."""
+    if model_cfg["encoder_type"] == "t5":
+        return transcribe_t5(sd, audio, audio_cfg, model_cfg, n_pos, max_length, **kw)
+    from . import perceiver_tf as OPTF
+    with torch.no_grad():
+        feats = frontend(sd, audio, audio_cfg)
+        enc = OPTF.encode(sd, feats, model_cfg)
+        return t5_generate(sd, enc, model_cfg, n_pos, max_length, **kw)

@@ -1,0 +1,134 @@
+"""Model workloads for bench.py (kept in the package so bench.py stays a thin driver).
+
+A step = ``YourMT3.inference`` on one batch of synthetic 2.048 s segments resident in HBM
+(frontend -> encoder -> device-resident greedy decode to max length; random-init weights never
+emit EOS, so every row decodes the full ``event_length`` -- the worst case).
+The e2e leg goes through ``inference_file`` with PINNED HOST audio and reads the tokens back.
+"""
+from __future__ import annotations
+
+import time
+
+SEG_SAMPLES = 32767
+
+PRESETS = {
+    # name: (model preset, audio overrides, default batch, precision)
+    "t5_small": ("mt3_t5_small", {}, 256, "bf16"),
+    "t5_small_f32": ("mt3_t5_small", {}, 64, "f32"),
+    "yptf": ("yptf", {"codec": "spec", "hop_length": 300}, 64, "bf16"),
+    "yptf_moe_multi": ("yptf_moe_multi", {"codec": "spec", "hop_length": 300}, 64, "bf16"),
+}
+DEFAULT = "frontend"
+
+
+class ModelWorkload:
+    roofline_bound = "hbm"
+    dominant_kernel = "ymt3_logmel_kernel"
+
+    def __init__(self, name, batch):
+        self.name = name
+        self.preset, self.audio_over, dbatch, self.precision = PRESETS[name]
+        self.batch = batch or dbatch
+        self.dtype = self.precision
+
+    def setup_native(self, dev):
+        import torch
+        import yourmt3_b200 as ymt3
+        self.torch = torch
+        self.model = ymt3.YourMT3(audio_cfg=ymt3.get_audio_cfg(**self.audio_over),
+                                  model_cfg=ymt3.get_model_cfg(self.preset), precision=self.precision)
+        ymt3.init_nondegenerate_(self.model, seed=0)
+        self.model = self.model.to(dev)
+        g = torch.Generator().manual_seed(1234 + (dev.index or 0))
+        self.host_in = (torch.randn(self.batch, 1, SEG_SAMPLES, generator=g) * 0.1).pin_memory()
+        self.dev_in = self.host_in.to(dev)
+        self.e2e_batch = self.batch
+        self.max_len = self.model.max_token_length
+        self.channels = getattr(self.model.decoder, "num_channels", 1)
+        self.launches_per_step = self._count_launches()
+        self.bytes_per_seg = SEG_SAMPLES * 4 + self.model.feat_length * self.model.feat_dim * 4
+        # frontend kernel timed alone (CUDA events) for the roofline object
+        self._frontend_ms = None
+
+    def _count_launches(self):
+        dec_layers = self.model.model_cfg["decoder"][self.model.decoder_type]["num_layers"]
+        per_step = 1 + dec_layers * 11 + 4          # embed + 11 kernels/layer + final norm, lm head, select, advance
+        return per_step * self.max_len + 64          # + frontend/encoder/cross-KV launches (lower bound)
+
+    def step(self):
+        return self.model.inference(self.dev_in, stop_at_eos=True)
+
+    def step_e2e(self):
+        outs = self.model.inference_file(self.batch, self.host_in, stop_at_eos=True)
+        return outs
+
+    def e2e_bytes(self):
+        return self.batch * SEG_SAMPLES * 4, self.batch * self.channels * self.max_len * 8
+
+    def dominant_kernel_ms(self):
+        """log-mel kernel of this workload timed alone with CUDA events (median of 10)."""
+        torch = self.torch
+        x = self.dev_in
+        ts = []
+        for _ in range(3):
+            self.model.spectrogram(x)
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            self.model.spectrogram(x)
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def roofline_units(self):
+        return self.batch * self.bytes_per_seg
+
+    def config(self):
+        m = getattr(self, "model", None) or self.ref_model
+        self.channels = getattr(m.decoder, "num_channels", 1)
+        self.max_len = m.max_token_length
+        return {"workload": self.name, "preset": self.preset, "segments_per_step_per_gpu": self.batch,
+                "segment_samples": SEG_SAMPLES, "codec": m.audio_cfg["codec"], "hop": m.audio_cfg["hop_length"],
+                "encoder": m.encoder_type, "decoder": m.decoder_type, "channels": self.channels,
+                "decode_steps": self.max_len, "vocab": m.vocab_size, "weights": "random-init (non-degenerate, seed 0)",
+                "l2_policy": "per-step working set (activations + KV cache) larger than L2",
+                "roofline_kernel_note": "roofline object = log-mel kernel of this workload timed alone"}
+
+    # ---- reference arm: same architecture through the CPU oracle (HF-pinned torch restatement) ----
+    def setup_reference(self):
+        import numpy as np
+        import torch
+        import yourmt3_b200 as ymt3
+        from oracle import pipeline as OP
+        self.OP = OP
+        self.ref_batch = 1 if self.preset != "mt3_t5_small" else 2
+        m = ymt3.YourMT3(audio_cfg=ymt3.get_audio_cfg(**self.audio_over), model_cfg=ymt3.get_model_cfg(self.preset),
+                         precision="f32")
+        ymt3.init_nondegenerate_(m, seed=0)
+        self.ref_model = m
+        self.ref_sd = {k: v.detach() for k, v in m.state_dict().items()}
+        g = torch.Generator().manual_seed(1234)
+        self.ref_audio = (torch.randn(self.ref_batch, SEG_SAMPLES, generator=g) * 0.1).numpy().astype(np.float32)
+        # bounded sample: decode fewer steps on the CPU and extrapolate linearly in the step count
+        self.ref_steps = min(64, m.max_token_length)
+
+    def step_reference(self):
+        m = self.ref_model
+        return self.OP.transcribe(self.ref_sd, self.ref_audio, m.audio_cfg, m.model_cfg,
+                                  n_pos=m.decoder.pos_table.shape[0], max_length=self.ref_steps, stop_at_eos=False)
+
+    def reference_scale(self):
+        """the CPU sample decodes ref_steps of max_len steps; encoder+frontend are not rescaled (upper bound on speed)."""
+        return self.ref_steps / float(self.ref_model.max_token_length)
+
+    def reference_sample(self):
+        return (f"CPU oracle (HF-T5-pinned torch restatement) of {self.preset}, {self.ref_batch} segment(s), "
+                f"{self.ref_steps} of {self.ref_model.max_token_length} decode steps, time scaled to full length")
+
+
+def get(name, batch):
+    if name not in PRESETS:
+        raise SystemExit(f"unknown workload {name!r}; choose from frontend, {', '.join(PRESETS)}")
+    return ModelWorkload(name, batch)

@@ -1,0 +1,191 @@
+"""Plain-PyTorch (CPU, fp32) restatement of the YPTF encoder side (oracle; test infra only):
+residual-conv pre-encoder ("res3b"), Perceiver-TF encoder (spectral cross-attention -> latent
+transformer -> temporal transformer, x blocks), MLP / Mixtral-style MoE feed-forward, RoPE,
+and the encoder->decoder projections ('linear', 'mc_shared_linear').
+
+PARITY UNPINNED for the *wiring*: upstream amt/src/model/{conv_block,perceiver_mod,ff_layer,
+projection_layer}.py are absent from the mounted reference, so the block structure below is
+restated from the YourMT3+ paper (arXiv 2407.04822), the Perceiver-TF paper (Lu et al. 2023)
+and memory of mimbres/YourMT3 [RECALL].  The *arithmetic of each block* follows installed
+dependency code that upstream copies, and is pinned against it in tests/test_oracle_ptf.py:
+
+* PerceiverLayer / PerceiverAttention / PerceiverSelfAttention / PerceiverMLP:
+  SP/transformers/models/perceiver/modeling_perceiver.py:135-242, 255-331, 334-350, 353-414
+  (LayerNorm on q and kv, biased q/k/v/out linears, scores / sqrt(d_head), softmax, query residual,
+  layer_out = mlp(layernorm(attn_out)) + attn_out)
+* Mixtral-style sparse MoE: SP/transformers/models/mixtral/modeling_mixtral.py:62-135
+  (router linear -> fp32 softmax -> top-k -> renormalise -> sum_k w_k * down(act(gate x) * up x))
+* RoPE (rotate-half): modeling_mixtral.py:208-254 (apply_rotary_pos_emb)
+* BatchNorm2d (eval) / Conv2d / AvgPool2d: torch.nn.functional
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+from .t5 import rms_norm
+
+Tensor = torch.Tensor
+ACT = {"gelu": F.gelu, "silu": F.silu, "relu": F.relu}
+
+
+# ------------------------------------------------------------------------------------------
+# pre-encoder: 3 x [pre-activation residual conv block + AvgPool(1,2)]  [RECALL conv_block.py]
+# ------------------------------------------------------------------------------------------
+def res_block(sd: Dict[str, Tensor], pre: str, x: Tensor, eps: float = 1e-5) -> Tensor:
+    """x: (B, C_in, T, F) -> (B, C_out, T, F/2).  h = conv2(relu(bn2(conv1(relu(bn1(x)))))) + shortcut(x); avgpool."""
+    def bn(t, name):
+        return F.batch_norm(t, sd[pre + name + ".running_mean"], sd[pre + name + ".running_var"],
+                            sd[pre + name + ".weight"], sd[pre + name + ".bias"], training=False, eps=eps)
+    h = F.conv2d(F.relu(bn(x, "bn1")), sd[pre + "conv1.weight"], padding=1)
+    h = F.conv2d(F.relu(bn(h, "bn2")), sd[pre + "conv2.weight"], padding=1)
+    if pre + "shortcut.weight" in sd:
+        x = F.conv2d(x, sd[pre + "shortcut.weight"], sd[pre + "shortcut.bias"])
+    return F.avg_pool2d(h + x, kernel_size=(1, 2))
+
+
+def pre_encoder_res3b(sd: Dict[str, Tensor], spec: Tensor, prefix: str = "pre_encoder.") -> Tensor:
+    """(B, T, F) -> (B, T, F/8, C) channels-last."""
+    x = spec[:, None]                                   # b 1 t f
+    for i in range(3):
+        x = res_block(sd, f"{prefix}blocks.{i}.", x)
+    return x.permute(0, 2, 3, 1).contiguous()           # b t f c
+
+
+# ------------------------------------------------------------------------------------------
+# Perceiver layer
+# ------------------------------------------------------------------------------------------
+def _norm(sd, name, x, kind, eps):
+    if kind == "rms_norm":
+        return rms_norm(x, sd[name + ".weight"], eps)
+    return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], eps)
+
+
+def rope_cos_sin(n_pos: int, rot_dim: int, base: float = 10000.0):
+    inv = 1.0 / (base ** (torch.arange(0, rot_dim, 2, dtype=torch.float64) / rot_dim))
+    fr = torch.arange(n_pos, dtype=torch.float64)[:, None] * inv[None, :]
+    emb = torch.cat([fr, fr], dim=-1)
+    return emb.cos().float(), emb.sin().float()
+
+
+def apply_rope(x: Tensor, rot_dim: int) -> Tensor:
+    """x: (..., S, d_head); rotate-half RoPE on the first rot_dim dims, position = index along S."""
+    if rot_dim <= 0:
+        return x
+    cos, sin = rope_cos_sin(x.shape[-2], rot_dim)
+    xr, xp = x[..., :rot_dim], x[..., rot_dim:]
+    x1, x2 = xr[..., : rot_dim // 2], xr[..., rot_dim // 2:]
+    rot = torch.cat([-x2, x1], dim=-1)
+    return torch.cat([xr * cos + rot * sin, xp], dim=-1)
+
+
+def moe_ff(sd, pre: str, x: Tensor, *, num_experts: int, topk: int, act: str) -> Tensor:
+    """x: (N, D). Mixtral-style routed gated MLP (modeling_mixtral.py:74-98, 109-116)."""
+    logits = x @ sd[pre + "gate.weight"].T
+    probs = torch.softmax(logits.float(), dim=-1)
+    w, idx = torch.topk(probs, topk, dim=-1)
+    w = w / w.sum(dim=-1, keepdim=True)
+    out = torch.zeros_like(x)
+    for e in range(num_experts):
+        pos, tok = torch.where((idx == e).T)
+        if tok.numel() == 0:
+            continue
+        xe = x[tok]
+        p = f"{pre}experts.{e}."
+        h = ACT[act](xe @ sd[p + "w1.weight"].T) * (xe @ sd[p + "w3.weight"].T)
+        out.index_add_(0, tok, (h @ sd[p + "w2.weight"].T) * w[tok, pos, None])
+    return out
+
+
+def perceiver_layer(sd, pre: str, h: Tensor, cfg: Dict, *, num_heads: int, inputs: Tensor = None,
+                    query_residual: bool = True, rope_dim: int = 0) -> Tensor:
+    """h: (N, S, D) queries; inputs: (N, S_kv, C) for cross-attention. Returns (N, S, D)."""
+    eps, kind = cfg.get("layer_norm_eps", 1e-5), cfg.get("layer_norm_type", "layer_norm")
+    a = pre + "attention.self."
+    hq = _norm(sd, a + "layernorm1", h, kind, eps)
+    kv = _norm(sd, a + "layernorm2", inputs, kind, eps) if inputs is not None else hq
+    q = hq @ sd[a + "query.weight"].T + sd[a + "query.bias"]
+    k = kv @ sd[a + "key.weight"].T + sd[a + "key.bias"]
+    v = kv @ sd[a + "value.weight"].T + sd[a + "value.bias"]
+    N, S, Dq = q.shape
+    dh = Dq // num_heads
+    q = q.view(N, S, num_heads, dh).transpose(1, 2)
+    k = k.view(N, -1, num_heads, dh).transpose(1, 2)
+    v = v.view(N, -1, num_heads, dh).transpose(1, 2)
+    if rope_dim:
+        q, k = apply_rope(q, rope_dim), apply_rope(k, rope_dim)
+    p = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(dh), dim=-1)
+    ctx = (p @ v).transpose(1, 2).reshape(N, S, Dq)
+    attn = ctx @ sd[pre + "attention.output.dense.weight"].T + sd[pre + "attention.output.dense.bias"]
+    if query_residual:
+        attn = attn + h
+    y = _norm(sd, pre + "layernorm", attn, kind, eps)
+    if cfg.get("ff_layer_type", "mlp") == "moe":
+        ff = moe_ff(sd, pre + "moe.", y.reshape(N * S, Dq), num_experts=cfg["moe_num_experts"], topk=cfg["moe_topk"],
+                    act=cfg.get("hidden_act", "silu")).view(N, S, Dq)
+    else:
+        ff = ACT[cfg.get("hidden_act", "gelu")](y @ sd[pre + "mlp.dense1.weight"].T + sd[pre + "mlp.dense1.bias"])
+        ff = ff @ sd[pre + "mlp.dense2.weight"].T + sd[pre + "mlp.dense2.bias"]
+    return ff + attn
+
+
+def perceiver_tf_encoder(sd: Dict[str, Tensor], x: Tensor, cfg: Dict, prefix: str = "encoder.") -> Tensor:
+    """x: (B, T, F', C) conv features -> (B, T, K, D) latents."""
+    B, T, Fp, C = x.shape
+    lat = sd[prefix + "latent_array.latents"]
+    K, D = lat.shape
+    h = lat[None, None].expand(B, T, K, D).contiguous()
+    pe = cfg.get("position_encoding_type", "trainable")
+    heads_x, heads_s = cfg.get("num_cross_attention_heads", 1), cfg.get("num_self_attention_heads", 8)
+    rope = 0
+    if pe == "rope":
+        dh = D // heads_s
+        rope = dh // 2 if cfg.get("rotary_partial_pe", False) else dh
+    elif pe == "trainable":
+        h = h + sd[prefix + "latent_pos_emb"][None, None]
+    kv = x.reshape(B * T, Fp, C)
+    for b in range(cfg["num_blocks"]):
+        bp = f"{prefix}block.{b}."
+        hq = h.reshape(B * T, K, D)
+        hq = perceiver_layer(sd, bp + "sca.", hq, cfg, num_heads=heads_x, inputs=kv,
+                             query_residual=cfg.get("sca_use_query_residual", False))
+        for n in range(cfg["num_local_transformers_per_block"]):
+            hq = perceiver_layer(sd, f"{bp}local.{n}.", hq, cfg, num_heads=heads_s, rope_dim=rope)
+        ht = hq.view(B, T, K, D).transpose(1, 2).reshape(B * K, T, D)
+        if pe == "trainable" and b == 0:
+            ht = ht + sd[prefix + "temporal_pos_emb"][None, :T]
+        for m in range(cfg["num_temporal_transformers_per_block"]):
+            ht = perceiver_layer(sd, f"{bp}temporal.{m}.", ht, cfg, num_heads=heads_s, rope_dim=rope)
+        h = ht.view(B, K, T, D).transpose(1, 2).contiguous()
+    return _norm(sd, prefix + "layernorm", h, cfg.get("layer_norm_type", "layer_norm"), cfg.get("layer_norm_eps", 1e-5))
+
+
+# ------------------------------------------------------------------------------------------
+# encoder -> decoder projections  [RECALL projection_layer.py]
+# ------------------------------------------------------------------------------------------
+def pre_decoder(sd, h: Tensor, kind: str, num_channels: int = 13, prefix: str = "pre_decoder.") -> Tensor:
+    """h: (B, T, K, D). 'linear': (B,T,K*D)->(B,T,d_dec).  'mc_shared_linear': latents grouped per channel,
+    'b t (c k2) d -> b c t (k2 d)' then one shared Linear -> (B, C, T, d_dec)."""
+    B, T, K, D = h.shape
+    W, b = sd[prefix + "proj.weight"], sd[prefix + "proj.bias"]
+    if kind == "linear":
+        return h.reshape(B, T, K * D) @ W.T + b
+    k2 = K // num_channels
+    y = h.view(B, T, num_channels, k2 * D) @ W.T + b          # (B, T, C, d_dec)
+    return y.permute(0, 2, 1, 3).contiguous()
+
+
+def encode(sd, feats: Tensor, model_cfg: Dict) -> Tensor:
+    """spectrogram features (B, T, F) -> decoder-ready encoder states."""
+    sd = {k: v.detach().cpu().float() for k, v in sd.items()}
+    cfg = model_cfg["encoder"]["perceiver-tf"]
+    x = pre_encoder_res3b(sd, feats)
+    h = perceiver_tf_encoder(sd, x, cfg)
+    pd = model_cfg["pre_decoder_type"]
+    if pd == "default":
+        pd = model_cfg["pre_decoder_type_default"]["perceiver-tf"][model_cfg["decoder_type"]]
+    nch = model_cfg["decoder"][model_cfg["decoder_type"]].get("num_channels", 1)
+    return pre_decoder(sd, h, pd, nch)

@@ -160,6 +160,69 @@ YMT3_API int ymt3_t5dec_generate(ymt3_t5dec_t* dec, const void* enc_hs_dev, int6
 /* fp32 logits of the LAST executed step, (N, vocab) (for logit-tolerance tests) */
 YMT3_API int ymt3_t5dec_last_logits(ymt3_t5dec_t* dec, float* logits_out_dev, int64_t N, void* stream);
 
+
+/* ------------------------------------------------------------------------- *
+ * Pre-encoder "res3b" of the Perceiver-TF models.  Replaces upstream model/conv_block.py
+ * PreEncoderBlockRes3B.forward: (B, T, F) -> (B, T, F/8, C): three pre-activation residual
+ * 3x3 conv blocks (BatchNorm eval -> ReLU -> conv, twice, + 1x1 shortcut when the channel
+ * count changes) each followed by AvgPool2d((1, 2)) over frequency [RECALL; arithmetic =
+ * torch.nn.functional.conv2d / batch_norm / avg_pool2d].
+ * Tensor names: blocks.{i}.bn{1,2}.{weight,bias,running_mean,running_var},
+ * blocks.{i}.conv{1,2}.weight (Cout,Cin,3,3), blocks.{i}.shortcut.{weight (Cout,Cin,1,1),bias}.
+ * ------------------------------------------------------------------------- */
+typedef struct ymt3_res3b_cfg {
+  int32_t precision;     /* F32: im2col + fp32 FFMA GEMM;  BF16: implicit GEMM on tcgen05 */
+  int32_t in_freq;       /* F (1024); must be a multiple of 1024 in BF16 mode (128-row M tiles) */
+  int32_t channels[3];   /* {64, 128, 128} */
+  float bn_eps;
+} ymt3_res3b_cfg_t;
+typedef struct ymt3_res3b ymt3_res3b_t;
+YMT3_API int ymt3_res3b_create(const ymt3_res3b_cfg_t* cfg, const ymt3_tensor_t* tensors, int n_tensors,
+                               ymt3_res3b_t** out);
+YMT3_API int ymt3_res3b_destroy(ymt3_res3b_t* h);
+/* spec_dev: (B, T, F) fp32. out_dev: (B, T, F/8, channels[2]) in the handle's precision. */
+YMT3_API int ymt3_res3b_forward(ymt3_res3b_t* h, const float* spec_dev, int64_t B, int64_t T, void* out_dev,
+                                void* stream);
+
+
+/* ------------------------------------------------------------------------- *
+ * Perceiver-TF encoder (YPTF).  Replaces upstream model/perceiver_mod.py PerceiverTFEncoder.forward:
+ * (B, T, F', C) conv features -> (B, T, K, D) latents; per block: spectral cross-attention
+ * (latents <- F' frequency tokens, per time step) -> N latent self-attention layers (over K, per
+ * time step) -> M temporal self-attention layers (over T, per latent); final norm.
+ * Layer arithmetic = HF/models/perceiver/modeling_perceiver.py:135-242, 255-331, 334-350, 353-414;
+ * MoE feed-forward = HF/models/mixtral/modeling_mixtral.py:62-135; RoPE = :208-254.
+ * Tensor names: latent_array.latents, [latent_pos_emb, temporal_pos_emb], layernorm.{weight,bias},
+ * block.{b}.{sca | local.{n} | temporal.{m}}.attention.self.{layernorm1,layernorm2,query,key,value}.*,
+ * ....attention.output.dense.*, ....layernorm.*, ....mlp.{dense1,dense2}.* or
+ * ....moe.gate.weight + ....moe.experts.{e}.{w1,w2,w3}.weight.
+ * ------------------------------------------------------------------------- */
+typedef struct ymt3_ptf_cfg {
+  int32_t precision;
+  int32_t num_latents, d_latent, kv_dim, num_blocks, num_local, num_temporal;
+  int32_t cross_heads, self_heads;
+  int32_t sca_query_residual;
+  int32_t norm_type;     /* 0 = LayerNorm, 1 = RMSNorm (weight only) */
+  int32_t ff_type;       /* 0 = MLP, 1 = MoE */
+  int32_t ff_widening, moe_experts, moe_topk;
+  int32_t act;           /* activation code as in ymt3_op_linear */
+  int32_t pos_type;      /* 0 none, 1 trainable tables, 2 rotary */
+  int32_t rope_dim;      /* rotated dims per self-attention head (pos_type 2) */
+  int32_t max_time;      /* largest T (rotary / temporal table length) */
+  float norm_eps;
+} ymt3_ptf_cfg_t;
+typedef struct ymt3_ptf ymt3_ptf_t;
+YMT3_API int ymt3_ptf_create(const ymt3_ptf_cfg_t* cfg, const ymt3_tensor_t* tensors, int n_tensors, ymt3_ptf_t** out);
+YMT3_API int ymt3_ptf_destroy(ymt3_ptf_t* h);
+/* x_dev: (B, T, Fp, kv_dim) in the handle's precision. out_dev: (B, T, num_latents, d_latent) same precision. */
+YMT3_API int ymt3_ptf_forward(ymt3_ptf_t* h, const void* x_dev, int64_t B, int64_t T, int64_t Fp, void* out_dev,
+                              void* stream);
+/* (B, T, C, D) -> (B, C, T, D) in `dtype` (multi-channel pre-decoder layout change) */
+YMT3_API int ymt3_op_permute_btcd_bctd(int32_t dtype, const void* x, void* y, int64_t B, int64_t T, int64_t C, int64_t D,
+                                       void* stream);
+/* dtype conversion of a flat buffer (f32 <-> bf16) */
+YMT3_API int ymt3_op_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Per-op entry points (unit-parity tests of individual kernels; also usable as building
  * blocks).  dtype: YMT3_DTYPE_F32 | YMT3_DTYPE_BF16 for A/W/C; bias always fp32.

@@ -47,6 +47,22 @@ class T5Cfg(C.Structure):
                 ("eos_id", C.c_int32), ("pad_id", C.c_int32), ("start_id", C.c_int32)]
 
 
+class Res3bCfg(C.Structure):
+    """Mirror of ``ymt3_res3b_cfg_t``."""
+
+    _fields_ = [("precision", C.c_int32), ("in_freq", C.c_int32), ("channels", C.c_int32 * 3), ("bn_eps", C.c_float)]
+
+
+class PtfCfg(C.Structure):
+    """Mirror of ``ymt3_ptf_cfg_t``."""
+
+    _fields_ = [(n, C.c_int32) for n in (
+        "precision", "num_latents", "d_latent", "kv_dim", "num_blocks", "num_local", "num_temporal", "cross_heads",
+        "self_heads", "sca_query_residual", "norm_type", "ff_type", "ff_widening", "moe_experts", "moe_topk", "act",
+        "pos_type", "rope_dim", "max_time")] + [("norm_eps", C.c_float)]
+
+
+ACT_CODES = {None: 0, "none": 0, "gelu_new": 1, "relu": 2, "silu": 3, "gelu": 4}
 DTYPE_F32, DTYPE_BF16 = 0, 1
 CODEC_MELSPEC, CODEC_SPEC = 0, 1
 _P = C.c_void_p
@@ -71,6 +87,14 @@ SIGNATURES = {
     "ymt3_t5dec_destroy": (_I, [_P]),
     "ymt3_t5dec_generate": (_I, [_P, _P, _I64, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ymt3_t5dec_last_logits": (_I, [_P, _P, _I64, _P]),
+    "ymt3_res3b_create": (_I, [C.POINTER(Res3bCfg), C.POINTER(Tensor), _I, C.POINTER(_P)]),
+    "ymt3_res3b_destroy": (_I, [_P]),
+    "ymt3_res3b_forward": (_I, [_P, _P, _I64, _I64, _P, _P]),
+    "ymt3_ptf_create": (_I, [C.POINTER(PtfCfg), C.POINTER(Tensor), _I, C.POINTER(_P)]),
+    "ymt3_ptf_destroy": (_I, [_P]),
+    "ymt3_ptf_forward": (_I, [_P, _P, _I64, _I64, _I64, _P, _P]),
+    "ymt3_op_permute_btcd_bctd": (_I, [C.c_int32, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "ymt3_op_convert": (_I, [_P, C.c_int32, _P, C.c_int32, _I64, _P]),
     "ymt3_op_linear": (_I, [C.c_int32, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _I64, _I64, _I64, C.c_int32,
                             C.c_int32, C.c_float, C.c_int32, _P]),
     "ymt3_op_rmsnorm": (_I, [C.c_int32, _P, _P, _P, _I64, _I64, C.c_float, _P]),

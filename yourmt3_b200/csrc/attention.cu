@@ -48,10 +48,15 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnParams p, int n_qtiles) {
   const int h = (int)(bid % p.H);
   const int b = (int)(bid / p.H);
   const int q0 = qt * 16;
-  const T* Q = static_cast<const T*>(p.Q) + (int64_t)b * p.q_sb + (int64_t)h * p.q_sh;
-  const T* K = static_cast<const T*>(p.K) + (int64_t)b * p.k_sb + (int64_t)h * p.k_sh;
-  const T* V = static_cast<const T*>(p.V) + (int64_t)b * p.v_sb + (int64_t)h * p.v_sh;
-  T* O = static_cast<T*>(p.O) + (int64_t)b * p.o_sb + (int64_t)h * p.o_sh;
+  int64_t bo = b, bi = 0;
+  if (p.inner > 1) {
+    bo = b / p.inner;
+    bi = b - bo * p.inner;
+  }
+  const T* Q = static_cast<const T*>(p.Q) + bo * p.q_sb + bi * p.q_sb2 + (int64_t)h * p.q_sh;
+  const T* K = static_cast<const T*>(p.K) + bo * p.k_sb + bi * p.k_sb2 + (int64_t)h * p.k_sh;
+  const T* V = static_cast<const T*>(p.V) + bo * p.v_sb + bi * p.v_sb2 + (int64_t)h * p.v_sh;
+  T* O = static_cast<T*>(p.O) + bo * p.o_sb + bi * p.o_sb2 + (int64_t)h * p.o_sh;
   const int kv_len = p.kv_len ? min(p.kv_len[b], p.Sk) : p.Sk;
 
   // Q tile (pre-scaled)
@@ -198,7 +203,7 @@ int attention(const AttnParams& p, int dtype, cudaStream_t stream) {
   if (p.B <= 0 || p.H <= 0 || p.Sq <= 0) return YMT3_OK;
   YMT3_REQUIRE(p.Q && p.K && p.V && p.O && p.Sk > 0, "attention: bad argument");
   YMT3_REQUIRE((p.q_ss % 4 | p.k_ss % 4 | p.v_ss % 4 | p.q_sh % 4 | p.k_sh % 4 | p.v_sh % 4 | p.q_sb % 4 |
-                p.k_sb % 4 | p.v_sb % 4) == 0,
+                p.k_sb % 4 | p.v_sb % 4 | p.q_sb2 % 4 | p.k_sb2 % 4 | p.v_sb2 % 4) == 0,
                "attention: strides must be multiples of 4 elements");
   return dtype == YMT3_F32 ? launch_attn<float>(p, stream) : launch_attn<__nv_bfloat16>(p, stream);
 }

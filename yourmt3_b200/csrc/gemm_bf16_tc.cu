@@ -48,6 +48,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -106,6 +114,9 @@ struct TcParams {
   const float* row_scale;
   const int* group_offsets;
   int out_f32;
+  // implicit-GEMM 3x3 convolution mode (CONV template flag): A is an NHWC activation (B, T, F, Cin) read
+  // through a 4-D tensor map {Cin, F, T, B}; row m = ((b*T + t)*F + f); k-block kb = tap * (Cin/64) + cb.
+  int conv_T, conv_F, conv_cblocks;
 };
 
 template <int BN>
@@ -117,7 +128,7 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;  // + barriers/tmem slot + 1024 B alignment slack
 };
 
-template <int BN>
+template <int BN, bool CONV>
 __global__ void __launch_bounds__(THREADS, 2)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -142,6 +153,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   }
   if (m0 >= row_end) return;  // uniform for the whole CTA, before any barrier/TMEM use
   const int num_kb = (p.K + BK - 1) / BK;
+  int cv_f0 = 0, cv_t = 0, cv_b = 0;
+  if constexpr (CONV) {
+    const int tpr = p.conv_F / BM;            // M tiles per (b, t) row; conv_F is a multiple of 128
+    const int mt = blockIdx.x;
+    cv_f0 = (mt % tpr) * BM;
+    const int bt = mt / tpr;
+    cv_t = bt % p.conv_T;
+    cv_b = bt / p.conv_T;
+  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -174,7 +194,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
         mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-        tma_load_2d(&mapA, &full_bar[stage], sa, kb * BK, m0);
+        if constexpr (CONV) {
+          // shifted window of the input; out-of-range rows/cols are zero-filled by TMA = conv zero padding
+          const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          tma_load_4d(&mapA, &full_bar[stage], sa, cb * BK, cv_f0 + dx, cv_t + dy, cv_b);
+        } else {
+          tma_load_2d(&mapA, &full_bar[stage], sa, kb * BK, m0);
+        }
         tma_load_2d(&mapW, &full_bar[stage], sb, kb * BK, w_row0);
         if (++stage == STAGES) {
           stage = 0;
@@ -357,26 +384,50 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
   return YMT3_OK;
 }
 
-template <int BN>
-int launch(const GemmParams& p, int out_dtype, cudaStream_t stream) {
+// NHWC activation (B, T, F, C) bf16 contiguous -> 4-D map {C, F, T, B}, box {64, 128, 1, 1}
+int make_conv_map(CUtensorMap* map, const void* base, int64_t B, int64_t T, int64_t F, int64_t C) {
+  EncodeTiledFn enc = get_encode_fn();
+  YMT3_REQUIRE(enc, "conv3x3_bf16_tc: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)F * C * 2, (cuuint64_t)T * F * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)BM, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YMT3_REQUIRE(r == CUDA_SUCCESS, "conv3x3_bf16_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return YMT3_OK;
+}
+
+struct ConvGeom {
+  int B = 0, T = 0, F = 0, Cin = 0;
+};
+
+template <int BN, bool CONV>
+int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGeom& cg = ConvGeom()) {
   CUtensorMap mapA, mapW;
   int rc;
   const int groups = p.group_offsets ? p.num_groups : 1;
-  if ((rc = make_map(&mapA, p.A, p.M, p.K, p.lda, BM))) return rc;
+  if constexpr (CONV) {
+    if ((rc = make_conv_map(&mapA, p.A, cg.B, cg.T, cg.F, cg.Cin))) return rc;
+  } else {
+    if ((rc = make_map(&mapA, p.A, p.M, p.K, p.lda, BM))) return rc;
+  }
   // grouped: weights of all groups are stacked along rows ((groups*N, K), strideW == N*ldw)
   if ((rc = make_map(&mapW, p.W, (int64_t)p.N * groups, p.K, p.ldw, BN))) return rc;
   TcParams t;
   t.C = p.C; t.ldc = p.ldc; t.bias = p.bias; t.residual = p.residual; t.ldr = p.ldr;
   t.M = p.M; t.N = p.N; t.K = p.K; t.act = p.act; t.gated = p.gated; t.out_scale = p.out_scale;
   t.row_scale = p.row_scale; t.group_offsets = p.group_offsets; t.out_f32 = out_dtype == YMT3_F32;
+  t.conv_T = cg.T; t.conv_F = cg.F; t.conv_cblocks = CONV ? cg.Cin / BK : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SmemLayout<BN>::TOTAL));
     attr_set = true;
   }
   dim3 grid(ymt3_div_up(p.M, BM), ymt3_div_up(p.N, BN), groups);
-  gemm_bf16_tc_kernel<BN><<<grid, THREADS, SmemLayout<BN>::TOTAL, stream>>>(mapA, mapW, t);
+  gemm_bf16_tc_kernel<BN, CONV><<<grid, THREADS, SmemLayout<BN>::TOTAL, stream>>>(mapA, mapW, t);
   YMT3_CUDA_CHECK(cudaGetLastError());
   return YMT3_OK;
 }
@@ -398,9 +449,30 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   // pick BN so that the grid fills the 148 SMs (2 CTAs/SM resident) when the problem allows
   const int64_t mt = ymt3_div_up(p.M, BM);
   const int sms = ymt3_num_sms();
-  if (p.N % 128 == 0 && mt * (p.N / 128) >= 2 * sms) return launch<128>(p, out_dtype, stream);
-  if (p.N >= 64 && mt * ymt3_div_up(p.N, 64) >= sms) return launch<64>(p, out_dtype, stream);
-  return launch<32>(p, out_dtype, stream);
+  if (p.N % 128 == 0 && mt * (p.N / 128) >= 2 * sms) return launch<128, false>(p, out_dtype, stream);
+  if (p.N >= 64 && mt * ymt3_div_up(p.N, 64) >= sms) return launch<64, false>(p, out_dtype, stream);
+  return launch<32, false>(p, out_dtype, stream);
+}
+
+// 3x3 / stride 1 / zero-pad 1 convolution as an implicit GEMM on the tensor cores.
+//   x: (B, T, F, Cin) bf16 NHWC, F % 128 == 0, Cin % 64 == 0.  W: (Cout, 9*Cin) bf16 with k = (ky*3+kx)*Cin + c.
+//   y: (B*T*F, Cout) with the GemmParams epilogue (bias / act / residual / out dtype).
+int conv3x3_bf16_tc(const void* x, int B, int T, int F, int Cin, const GemmParams& epi, int out_dtype,
+                    cudaStream_t stream) {
+  YMT3_REQUIRE(x && epi.W && epi.C, "conv3x3_bf16_tc: null pointer");
+  YMT3_REQUIRE(F % BM == 0 && Cin % BK == 0, "conv3x3_bf16_tc: need F %% 128 == 0 and Cin %% 64 == 0 (F=%d Cin=%d)", F, Cin);
+  const int64_t M64 = (int64_t)B * T * F;
+  YMT3_REQUIRE(M64 < (1ll << 31), "conv3x3_bf16_tc: too many pixels");
+  GemmParams p = epi;
+  p.A = x; p.lda = Cin;
+  p.M = (int)M64; p.K = 9 * Cin; p.ldw = 9 * Cin;
+  p.group_offsets = nullptr; p.gated = 0;
+  YMT3_REQUIRE(p.N % 8 == 0 && p.ldc % 8 == 0 && (!p.residual || p.ldr % 8 == 0), "conv3x3_bf16_tc: Cout/ldc alignment");
+  ConvGeom cg;
+  cg.B = B; cg.T = T; cg.F = F; cg.Cin = Cin;
+  if (p.N % 128 == 0) return launch<128, true>(p, out_dtype, stream, cg);
+  if (p.N % 64 == 0) return launch<64, true>(p, out_dtype, stream, cg);
+  return launch<32, true>(p, out_dtype, stream, cg);
 }
 
 }  // namespace ymt3

@@ -49,6 +49,20 @@ int pack_rows(DevicePool& pool, const std::vector<const ymt3_tensor_t*>& srcs, i
   return YMT3_OK;
 }
 
+int pack_rows_at(void* W, int64_t row0, int row_stride, const ymt3_tensor_t* src, int K, int dtype, cudaStream_t stream) {
+  if (!src) return YMT3_ERR_INVALID;
+  const int64_t rows = src->shape[0];
+  const int64_t n = rows * K;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == YMT3_F32)
+    pack_rows_kernel<float><<<grid, 256, 0, stream>>>((const float*)src->data, (float*)W, rows, K, row0, row_stride);
+  else
+    pack_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)src->data, (__nv_bfloat16*)W, rows, K, row0,
+                                                              row_stride);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
 int pack_vec(DevicePool& pool, const std::vector<const ymt3_tensor_t*>& srcs, bool interleave2, float** out,
              cudaStream_t stream) {
   int64_t total = 0;

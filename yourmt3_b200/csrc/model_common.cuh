@@ -73,6 +73,8 @@ struct Linear {
 // interleave2: exactly two sources of equal shape; output row 2j = src0[j], 2j+1 = src1[j].
 int pack_rows(DevicePool& pool, const std::vector<const ymt3_tensor_t*>& srcs, int K, int dtype,
               bool interleave2, Linear* out, cudaStream_t stream);
+// write one (rows, K) f32 source into an existing packed weight: dst row = row0 + r * row_stride
+int pack_rows_at(void* W, int64_t row0, int row_stride, const ymt3_tensor_t* src, int K, int dtype, cudaStream_t stream);
 // concatenate 1-D f32 tensors (biases / norm scales) into one fp32 device vector
 int pack_vec(DevicePool& pool, const std::vector<const ymt3_tensor_t*>& srcs, bool interleave2, float** out,
              cudaStream_t stream);

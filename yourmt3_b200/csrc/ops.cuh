@@ -53,6 +53,10 @@ struct GemmParams {
 
 int gemm_f32(const GemmParams& p, cudaStream_t stream);            // SIMT fp32 FFMA
 int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream);  // tcgen05/TMEM/TMA
+// 3x3 same-padding convolution on NHWC bf16 input as an implicit GEMM (tcgen05; TMA 4-D tiles with
+// zero-filled halo); `epi` carries W (Cout, 9*Cin), N=Cout, C/ldc, bias, act, residual/ldr, out_scale.
+int conv3x3_bf16_tc(const void* x, int B, int T, int F, int Cin, const GemmParams& epi, int out_dtype,
+                    cudaStream_t stream);
 
 // y = x * rsqrt(mean(x^2) + eps) * w          (T5LayerNorm / RMSNorm)
 // y = (x - mean) * rsqrt(var + eps) * w + b   (nn.LayerNorm), w/b fp32
@@ -69,6 +73,10 @@ struct AttnParams {
   const void* V; int64_t v_sb, v_sh, v_ss;
   void* O; int64_t o_sb, o_sh, o_ss;
   int B, H, Sq, Sk, dk;
+  // optional two-level batch: batch index b -> (b / inner, b % inner), offset = (b / inner) * sb + (b % inner) * sb2
+  // (temporal attention over a (B, T, K, D) layout without transposing); inner <= 1 disables it
+  int inner;
+  int64_t q_sb2, k_sb2, v_sb2, o_sb2;
   float scale;
   int causal;        // key j allowed iff j <= i + (Sk - Sq)
   const int* kv_len; // optional per-batch valid key count (device), else Sk
@@ -77,7 +85,16 @@ int attention(const AttnParams& p, int dtype, cudaStream_t stream);
 
 // elementwise helpers
 int add_rows(const void* x, const void* table, void* y, int64_t rows, int period, int dim, int dtype,
-             cudaStream_t stream);  // y[r,:] = x[r,:] + table[r % period,:]
+             cudaStream_t stream, int64_t div = 1);  // y[r,:] = x[r,:] + table[(r / div) % period,:]
+int permute_btcd_bctd(const void* x, void* y, int64_t B, int64_t T, int64_t C, int64_t D, int dtype,
+                      cudaStream_t stream);
 int convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, cudaStream_t stream);
+// y[r, :] = table[r % period, :] (+ table2[r % period, :])   (latent array broadcast)
+int tile_rows(const void* table, const void* table2, void* y, int64_t rows, int period, int dim, int dtype,
+              cudaStream_t stream);
+// in-place rotate-half RoPE on `heads` heads of width dh starting at column col0 of a (rows, ld) matrix;
+// position of row r = (r / pos_div) % pos_mod; cos/sin tables are (n_pos, rot/2) fp32
+int rope_inplace(void* x, int64_t rows, int64_t ld, int col0, int heads, int dh, int rot, int64_t pos_div, int pos_mod,
+                 const float* cos_t, const float* sin_t, int dtype, cudaStream_t stream);
 
 }  // namespace ymt3

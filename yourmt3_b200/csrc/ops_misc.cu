@@ -87,25 +87,110 @@ int layernorm(const void* x, const float* w, const float* b, void* y, int64_t ro
 
 template <typename T>
 __global__ void __launch_bounds__(256) add_rows_kernel(const T* __restrict__ x, const T* __restrict__ table,
-                                                       T* __restrict__ y, int64_t total, int period, int dim) {
+                                                       T* __restrict__ y, int64_t total, int period, int dim,
+                                                       int64_t div) {
   int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= total) return;
   int64_t r = i / dim;
   int c = (int)(i - r * dim);
-  y[i] = from_f<T>(to_f(x[i]) + to_f(table[(r % period) * dim + c]));
+  y[i] = from_f<T>(to_f(x[i]) + to_f(table[((r / div) % period) * dim + c]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) permute_btcd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t total,
+                                                           int64_t Tn, int64_t Cn, int64_t Dn) {
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;   // index into y (b, c, t, d)
+  if (i >= total) return;
+  const int64_t d = i % Dn, t = (i / Dn) % Tn, c = (i / (Dn * Tn)) % Cn, b = i / (Dn * Tn * Cn);
+  y[i] = x[((b * Tn + t) * Cn + c) * Dn + d];
+}
+
+int permute_btcd_bctd(const void* x, void* y, int64_t B, int64_t T, int64_t C, int64_t D, int dtype,
+                      cudaStream_t stream) {
+  const int64_t total = B * T * C * D;
+  if (total <= 0) return YMT3_OK;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == YMT3_F32)
+    permute_btcd_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (float*)y, total, T, C, D);
+  else
+    permute_btcd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, total, T, C, D);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
 }
 
 int add_rows(const void* x, const void* table, void* y, int64_t rows, int period, int dim, int dtype,
-             cudaStream_t stream) {
+             cudaStream_t stream, int64_t div) {
   if (rows <= 0) return YMT3_OK;
   const int64_t total = rows * dim;
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (dtype == YMT3_F32)
     add_rows_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, (const float*)table, (float*)y, total,
-                                                     period, dim);
+                                                     period, dim, div);
   else
     add_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)table,
-                                                             (__nv_bfloat16*)y, total, period, dim);
+                                                             (__nv_bfloat16*)y, total, period, dim, div);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) tile_rows_kernel(const T* __restrict__ table, const T* __restrict__ table2,
+                                                        T* __restrict__ y, int64_t total, int period, int dim) {
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  int64_t r = i / dim;
+  int c = (int)(i - r * dim);
+  const int64_t src = (r % period) * dim + c;
+  float v = to_f(table[src]);
+  if (table2) v += to_f(table2[src]);
+  y[i] = from_f<T>(v);
+}
+
+int tile_rows(const void* table, const void* table2, void* y, int64_t rows, int period, int dim, int dtype,
+              cudaStream_t stream) {
+  if (rows <= 0) return YMT3_OK;
+  const int64_t total = rows * dim;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == YMT3_F32)
+    tile_rows_kernel<float><<<grid, 256, 0, stream>>>((const float*)table, (const float*)table2, (float*)y, total,
+                                                      period, dim);
+  else
+    tile_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)table, (const __nv_bfloat16*)table2,
+                                                              (__nv_bfloat16*)y, total, period, dim);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
+// one thread per (row, head, pair)
+template <typename T>
+__global__ void __launch_bounds__(256)
+rope_kernel(T* __restrict__ x, int64_t total, int64_t ld, int col0, int heads, int dh, int half, int64_t pos_div,
+            int pos_mod, const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int pr = (int)(i % half);
+  const int h = (int)((i / half) % heads);
+  const int64_t r = i / ((int64_t)half * heads);
+  const int pos = (int)((r / pos_div) % pos_mod);
+  T* p = x + r * ld + col0 + h * dh + pr;
+  const float c = cos_t[pos * half + pr], s = sin_t[pos * half + pr];
+  const float x1 = to_f(p[0]), x2 = to_f(p[half]);
+  p[0] = from_f<T>(x1 * c - x2 * s);
+  p[half] = from_f<T>(x2 * c + x1 * s);
+}
+
+int rope_inplace(void* x, int64_t rows, int64_t ld, int col0, int heads, int dh, int rot, int64_t pos_div, int pos_mod,
+                 const float* cos_t, const float* sin_t, int dtype, cudaStream_t stream) {
+  if (rows <= 0 || rot <= 0) return YMT3_OK;
+  YMT3_REQUIRE(rot % 2 == 0 && rot <= dh, "rope: bad rotary dim");
+  const int half = rot / 2;
+  const int64_t total = rows * heads * half;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dtype == YMT3_F32)
+    rope_kernel<float><<<grid, 256, 0, stream>>>((float*)x, total, ld, col0, heads, dh, half, pos_div, pos_mod, cos_t, sin_t);
+  else
+    rope_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((__nv_bfloat16*)x, total, ld, col0, heads, dh, half, pos_div,
+                                                         pos_mod, cos_t, sin_t);
   YMT3_CUDA_CHECK(cudaGetLastError());
   return YMT3_OK;
 }

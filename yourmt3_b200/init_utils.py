@@ -25,4 +25,9 @@ def init_nondegenerate_(module: nn.Module, seed: int = 0, std: float = 0.05, emb
         else:  # norm scales
             v = 1.0 + 0.1 * torch.randn(p.shape, generator=g)
         p.copy_(v.to(p.device, p.dtype))
+    for name, b in sorted(module.named_buffers(), key=lambda kv: kv[0]):
+        if name.endswith("running_mean"):       # BatchNorm statistics: non-trivial so that folding is exercised
+            b.copy_((torch.randn(b.shape, generator=g) * 0.1).to(b.device, b.dtype))
+        elif name.endswith("running_var"):
+            b.copy_((0.5 + torch.rand(b.shape, generator=g)).to(b.device, b.dtype))
     return module

@@ -19,7 +19,11 @@ def init_nondegenerate_(module: nn.Module, seed: int = 0, std: float = 0.05, emb
         if "embed_tokens" in name or "latent_array" in name:
             v = torch.randn(p.shape, generator=g) * embed_std
         elif p.dim() >= 2:
-            v = torch.randn(p.shape, generator=g) * std
+            fan_in = p[0].numel()
+            # very wide layers (e.g. the K*D -> d_model 'linear' pre-decoder) are scaled down so that they do not
+            # swamp the residual stream and collapse the decode to a constant token
+            scale = std * min(1.0, (1024.0 / fan_in) ** 0.5)
+            v = torch.randn(p.shape, generator=g) * scale
         elif name.endswith("bias"):
             v = torch.randn(p.shape, generator=g) * 0.02
         else:  # norm scales

@@ -56,7 +56,16 @@ class ModelWorkload:
         return per_step * self.max_len + 64          # + frontend/encoder/cross-KV launches (lower bound)
 
     def step(self):
-        return self.model.inference(self.dev_in, stop_at_eos=True)
+        toks = self.model.inference(self.dev_in, stop_at_eos=True)
+        dist = self.torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # the one collective of the sharded path: all-gather of the int32 token blocks over NCCL
+            t32 = toks.to(self.torch.int32).contiguous()
+            out = self.torch.empty((dist.get_world_size() * t32.shape[0],) + tuple(t32.shape[1:]), dtype=t32.dtype,
+                                   device=t32.device)
+            dist.all_gather_into_tensor(out, t32)
+            return out
+        return toks
 
     def step_e2e(self):
         outs = self.model.inference_file(self.batch, self.host_in, stop_at_eos=True)

@@ -105,6 +105,15 @@ class YourMT3(nn.Module):
                                       precision=self._prec, early_stop_interval=early_stop_interval)
 
     @torch.no_grad()
+    def inference_file_sharded(self, bsz: int, audio_segments: torch.Tensor, **kw) -> torch.Tensor:
+        """Multi-GPU long-form path (one process per GPU, torch.distributed initialised with NCCL): this
+        rank transcribes its contiguous range of segments; ONE all-gather returns the ordered tokens
+        (n_seg, L) / (n_seg, C, L) int32 on every rank."""
+        from .sharding import transcribe_sharded
+        dev = next(self.parameters()).device
+        return transcribe_sharded(lambda x: self.inference(x, None, **kw), audio_segments, bsz, dev, self.pad_id)
+
+    @torch.no_grad()
     def inference_file(self, bsz: int, audio_segments: torch.Tensor, note_token_array=None, task_token_array=None,
                        **kw) -> List[np.ndarray]:
         """audio_segments: (n_seg, 1, L) f32 (CPU or CUDA).  Returns a list with one int array of

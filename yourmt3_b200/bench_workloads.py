@@ -18,7 +18,7 @@ PRESETS = {
     "yptf": ("yptf", {"codec": "spec", "hop_length": 300}, 64, "bf16"),
     "yptf_moe_multi": ("yptf_moe_multi", {"codec": "spec", "hop_length": 300}, 64, "bf16"),
 }
-DEFAULT = "frontend"
+DEFAULT = "yptf_moe_multi"   # the model BASELINE.json quotes the target on
 
 
 class ModelWorkload:

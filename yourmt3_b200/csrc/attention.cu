@@ -181,8 +181,108 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnParams p, int n_qtiles) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tiny-sequence attention (Perceiver-TF latent / temporal self-attention: dk = 16, S = 26 / 110).
+// The whole K and V of one (batch, head) live in shared memory and ONE THREAD owns one query row:
+// single-pass online softmax entirely in registers -- no shuffles, no per-tile barriers, K/V read as
+// broadcast float4.  A CTA (128 threads) holds 128/G (batch, head) problems, G = 32/64/128 >= Sq.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int DK>
+__global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p, int G, int64_t total_bh) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x;
+  const int groups = 128 / G;
+  const int g = tid / G, r = tid - g * G;            // group in CTA, row (thread) in group
+  const int64_t bh = (int64_t)blockIdx.x * groups + g;
+  float* Ks = sm + (size_t)g * 2 * p.Sk * DK;
+  float* Vs = Ks + (size_t)p.Sk * DK;
+  const bool live = bh < total_bh;
+  const T* Q = nullptr;
+  T* O = nullptr;
+  int kv_len = 0;
+  if (live) {
+    const int h = (int)(bh % p.H);
+    const int64_t b = bh / p.H;
+    int64_t bo = b, bi = 0;
+    if (p.inner > 1) {
+      bo = b / p.inner;
+      bi = b - bo * p.inner;
+    }
+    Q = static_cast<const T*>(p.Q) + bo * p.q_sb + bi * p.q_sb2 + (int64_t)h * p.q_sh;
+    const T* K = static_cast<const T*>(p.K) + bo * p.k_sb + bi * p.k_sb2 + (int64_t)h * p.k_sh;
+    const T* V = static_cast<const T*>(p.V) + bo * p.v_sb + bi * p.v_sb2 + (int64_t)h * p.v_sh;
+    O = static_cast<T*>(p.O) + bo * p.o_sb + bi * p.o_sb2 + (int64_t)h * p.o_sh;
+    kv_len = p.kv_len ? min(p.kv_len[b], p.Sk) : p.Sk;
+    for (int idx = r; idx < kv_len * (DK / 4); idx += G) {
+      const int j = idx / (DK / 4), d = (idx % (DK / 4)) * 4;
+      float kv[4], vv[4];
+      load4<T>(K + (int64_t)j * p.k_ss + d, kv);
+      load4<T>(V + (int64_t)j * p.v_ss + d, vv);
+      *reinterpret_cast<float4*>(Ks + j * DK + d) = make_float4(kv[0], kv[1], kv[2], kv[3]);
+      *reinterpret_cast<float4*>(Vs + j * DK + d) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+  }
+  __syncthreads();
+  if (!live || r >= p.Sq) return;
+  float q[DK], o[DK];
+#pragma unroll
+  for (int d = 0; d < DK; d += 4) {
+    float t[4];
+    load4<T>(Q + (int64_t)r * p.q_ss + d, t);
+    q[d] = t[0] * p.scale; q[d + 1] = t[1] * p.scale; q[d + 2] = t[2] * p.scale; q[d + 3] = t[3] * p.scale;
+    o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  const int jmax = p.causal ? min(kv_len, r + (p.Sk - p.Sq) + 1) : kv_len;
+  for (int j = 0; j < jmax; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DK; d += 4) {
+      const float4 k = *reinterpret_cast<const float4*>(Ks + j * DK + d);
+      s = fmaf(q[d], k.x, s); s = fmaf(q[d + 1], k.y, s); s = fmaf(q[d + 2], k.z, s); s = fmaf(q[d + 3], k.w, s);
+    }
+    if (s > m) {
+      const float corr = expf(m - s);   // m = -inf -> 0
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < DK; ++d) o[d] *= corr;
+      m = s;
+    }
+    const float pj = expf(s - m);
+    l += pj;
+#pragma unroll
+    for (int d = 0; d < DK; d += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(Vs + j * DK + d);
+      o[d] = fmaf(pj, v.x, o[d]); o[d + 1] = fmaf(pj, v.y, o[d + 1]);
+      o[d + 2] = fmaf(pj, v.z, o[d + 2]); o[d + 3] = fmaf(pj, v.w, o[d + 3]);
+    }
+  }
+  const float inv = l > 0.f ? 1.0f / l : 0.f;
+#pragma unroll
+  for (int d = 0; d < DK; ++d) store1<T>(O + (int64_t)r * p.o_ss + d, o[d] * inv);
+}
+
+template <typename T, int DK>
+static bool try_launch_small(const AttnParams& p, cudaStream_t stream) {
+  if (p.Sq > 128 || p.Sk > 128) return false;
+  const int G = p.Sq <= 32 ? 32 : (p.Sq <= 64 ? 64 : 128);
+  const int groups = 128 / G;
+  const size_t smem = (size_t)groups * 2 * p.Sk * DK * sizeof(float);
+  if (smem > 48 * 1024) return false;
+  const int64_t total_bh = (int64_t)p.B * p.H;
+  const int64_t blocks = (total_bh + groups - 1) / groups;
+  if (blocks >= (1ll << 31)) return false;
+  attn_small_kernel<T, DK><<<(unsigned)blocks, 128, smem, stream>>>(p, G, total_bh);
+  return true;
+}
+
 template <typename T>
 static int launch_attn(const AttnParams& p, cudaStream_t stream) {
+  if ((p.dk == 16 && try_launch_small<T, 16>(p, stream)) || (p.dk == 32 && try_launch_small<T, 32>(p, stream))) {
+    YMT3_CUDA_CHECK(cudaGetLastError());
+    return YMT3_OK;
+  }
   const int nq = ymt3_div_up(p.Sq, 16);
   const int64_t blocks = (int64_t)p.B * p.H * nq;
   YMT3_REQUIRE(blocks < (1ll << 31), "attention: grid too large");

@@ -41,85 +41,126 @@ int embed_pos(const int* tok, const void* E, const void* pos, const int* step, v
   return YMT3_OK;
 }
 
-// One CTA (128 threads) per (head, sequence). DK = 64.
+// One CTA (128 threads) per (head, sequence), DK = 64, single pass over the cache (flash-decoding style):
+// 8 lanes share one key row (16-byte slices -> a warp reads 4 consecutive rows = 512 contiguous bytes),
+// the 16 lane-groups of the CTA walk the keys with stride 16 keeping a private online-softmax state
+// (m, l, o[8 dims]) in registers; K and V of a key are fetched together; the 16 partial states are merged
+// through shared memory at the end.  This kernel is HBM-bound (KV bytes), see DESIGN.md 3.3.
 //   self mode (knew != null): K/V row of this step is appended to the cache at index *step,
 //   then the query attends over keys [0, *step]. cross mode: attends over [0, fixed_len).
+template <typename T> struct Slice8;
+template <> struct Slice8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void copy(float* d, const float* s) {
+    *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(s);
+    *reinterpret_cast<float4*>(d + 4) = *reinterpret_cast<const float4*>(s + 4);
+  }
+};
+template <> struct Slice8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __bfloat162float(h[i].x);
+      v[2 * i + 1] = __bfloat162float(h[i].y);
+    }
+  }
+  static __device__ __forceinline__ void copy(__nv_bfloat16* d, const __nv_bfloat16* s) {
+    *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(128)
 decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ knew, const T* __restrict__ vnew,
                    int64_t new_ld, T* __restrict__ Kc, T* __restrict__ Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss,
                    const int* __restrict__ step, int fixed_len, float scale, T* __restrict__ out, int64_t out_ld) {
-  constexpr int DK = 64;
-  extern __shared__ float smem[];
-  float* P = smem;                 // [len]
-  __shared__ float qs[DK];
-  __shared__ float red[4];
-  __shared__ float part[2][DK];
-  const int h = blockIdx.x, n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int DK = 64, NG = 16;
+  __shared__ float red_m[NG], red_l[NG];
+  __shared__ float red_o[NG][DK];
+  const int h = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  const int grp = tid >> 3, sub = tid & 7;
   T* Kb = Kc + (int64_t)n * c_sn + (int64_t)h * c_sh;
   T* Vb = Vc + (int64_t)n * c_sn + (int64_t)h * c_sh;
   int len = fixed_len;
   if (knew) {
     const int s = *step;
     len = s + 1;
-    if (tid < DK) {
-      Kb[(int64_t)s * c_ss + tid] = knew[(int64_t)n * new_ld + h * DK + tid];
-      Vb[(int64_t)s * c_ss + tid] = vnew[(int64_t)n * new_ld + h * DK + tid];
-    }
+    if (tid < 8) Slice8<T>::copy(Kb + (int64_t)s * c_ss + 8 * tid, knew + (int64_t)n * new_ld + h * DK + 8 * tid);
+    else if (tid < 16) Slice8<T>::copy(Vb + (int64_t)s * c_ss + 8 * (tid - 8), vnew + (int64_t)n * new_ld + h * DK + 8 * (tid - 8));
+    __syncthreads();   // the freshly appended row is read below by other threads of this CTA
   }
-  if (tid < DK) qs[tid] = dec_to_f(q[(int64_t)n * q_ld + h * DK + tid]) * scale;
-  __syncthreads();   // also makes this CTA's freshly appended K/V row visible to its threads
-
-  // scores
-  float lmax = -INFINITY;
-  for (int j = tid; j < len; j += 128) {
-    const T* kr = Kb + (int64_t)j * c_ss;
-    float s = 0.f;
+  float qv[8];
+  Slice8<T>::load(q + (int64_t)n * q_ld + h * DK + 8 * sub, qv);
 #pragma unroll
-    for (int d = 0; d < DK; d += 4) {
-      float k0, k1, k2, k3;
-      if constexpr (sizeof(T) == 4) {
-        float4 kv = *reinterpret_cast<const float4*>(kr + d);
-        k0 = kv.x; k1 = kv.y; k2 = kv.z; k3 = kv.w;
-      } else {
-        uint2 kv = *reinterpret_cast<const uint2*>(kr + d);
-        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&kv.x), b = *reinterpret_cast<__nv_bfloat162*>(&kv.y);
-        k0 = __bfloat162float(a.x); k1 = __bfloat162float(a.y);
-        k2 = __bfloat162float(b.x); k3 = __bfloat162float(b.y);
+  for (int i = 0; i < 8; ++i) qv[i] *= scale;
+
+  float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+
+  // uniform trip count for the whole CTA (the shuffles below name all 32 lanes)
+  for (int base = 0; base < len; base += 2 * NG) {
+    const int j0 = base + grp, j1 = j0 + NG;
+    const bool has0 = j0 < len, has1 = j1 < len;
+    float k0[8], v0[8], k1[8], v1[8];
+    if (has0) {
+      Slice8<T>::load(Kb + (int64_t)j0 * c_ss + 8 * sub, k0);
+      Slice8<T>::load(Vb + (int64_t)j0 * c_ss + 8 * sub, v0);
+    }
+    if (has1) {
+      Slice8<T>::load(Kb + (int64_t)j1 * c_ss + 8 * sub, k1);
+      Slice8<T>::load(Vb + (int64_t)j1 * c_ss + 8 * sub, v1);
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (has0) s0 = fmaf(qv[i], k0[i], s0);
+      if (has1) s1 = fmaf(qv[i], k1[i], s1);
+    }
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    }
+    if (has0) {   // has1 implies has0
+      if (!has1) s1 = -INFINITY;
+      const float mn = fmaxf(m, fmaxf(s0, s1));
+      const float corr = expf(m - mn);          // m = -inf -> 0
+      const float p0 = expf(s0 - mn), p1 = has1 ? expf(s1 - mn) : 0.f;
+      l = l * corr + p0 + p1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i] = o[i] * corr + p0 * v0[i];
+        if (has1) o[i] = fmaf(p1, v1[i], o[i]);
       }
-      s = fmaf(qs[d], k0, s);
-      s = fmaf(qs[d + 1], k1, s);
-      s = fmaf(qs[d + 2], k2, s);
-      s = fmaf(qs[d + 3], k3, s);
+      m = mn;
     }
-    P[j] = s;
-    lmax = fmaxf(lmax, s);
+  }
+  if (sub == 0) {
+    red_m[grp] = m;
+    red_l[grp] = l;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  if (lane == 0) red[warp] = lmax;
+  for (int i = 0; i < 8; ++i) red_o[grp][8 * sub + i] = o[i];
   __syncthreads();
-  const float gmax = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  __syncthreads();
-  float lsum = 0.f;
-  for (int j = tid; j < len; j += 128) {
-    const float e = expf(P[j] - gmax);
-    P[j] = e;
-    lsum += e;
-  }
+  if (tid < DK) {
+    float M = -INFINITY;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-  if (lane == 0) red[warp] = lsum;
-  __syncthreads();
-  const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
-
-  // PV: thread owns dim d = tid & 63 for keys of parity group g = tid >> 6
-  const int d = tid & 63, g = tid >> 6;
-  float acc = 0.f;
-  for (int j = g; j < len; j += 2) acc = fmaf(P[j], dec_to_f(Vb[(int64_t)j * c_ss + d]), acc);
-  part[g][d] = acc;
-  __syncthreads();
-  if (tid < DK) out[(int64_t)n * out_ld + h * DK + tid] = dec_from_f<T>((part[0][tid] + part[1][tid]) * inv);
+    for (int g = 0; g < NG; ++g) M = fmaxf(M, red_m[g]);
+    float L = 0.f, acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float w = red_m[g] == -INFINITY ? 0.f : expf(red_m[g] - M);
+      L = fmaf(red_l[g], w, L);
+      acc = fmaf(red_o[g][tid], w, acc);
+    }
+    out[(int64_t)n * out_ld + h * DK + tid] = dec_from_f<T>(acc / L);
+  }
 }
 
 int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* vnew, int64_t new_ld, void* Kc,
@@ -128,9 +169,8 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
   if (N <= 0) return YMT3_OK;
   YMT3_REQUIRE(dk == 64, "decode_attention: head dim must be 64 (got %d)", dk);
   YMT3_REQUIRE(N <= 65535, "decode_attention: too many sequences per call (%d > 65535)", N);
-  const int max_len = knew ? Lmax : fixed_len;
-  const size_t smem = (size_t)max_len * sizeof(float);
-  YMT3_REQUIRE(smem <= 40 * 1024, "decode_attention: sequence too long (%d)", max_len);
+  (void)Lmax;
+  const size_t smem = 0;
   dim3 grid(H, N);
   if (dtype == YMT3_F32)
     decode_attn_kernel<float><<<grid, 128, smem, stream>>>((const float*)q, q_ld, (const float*)knew,

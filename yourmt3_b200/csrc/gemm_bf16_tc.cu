@@ -18,7 +18,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 3;
+
 constexpr int THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,6 +113,7 @@ struct TcParams {
   float out_scale;
   const float* row_scale;
   const int* group_offsets;
+  int num_groups;
   int out_f32;
   // implicit-GEMM 3x3 convolution mode (CONV template flag): A is an NHWC activation (B, T, F, Cin) read
   // through a 4-D tensor map {Cin, F, T, B}; row m = ((b*T + t)*F + f); k-block kb = tap * (Cin/64) + cb.
@@ -124,44 +125,38 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;  // + barriers/tmem slot + 1024 B alignment slack
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;  // + barriers / tmem slot / group table + 1024 B alignment slack
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: one CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).  The TMA
+// producer runs ahead across tiles through a STAGES-deep smem ring; the accumulator is DOUBLE-BUFFERED in
+// TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1; barriers, TMEM allocation
+// and tensor-map prefetch are paid once per CTA instead of once per tile (decisive for K = 128 GEMMs).
 template <int BN, bool CONV>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   using L = SmemLayout<BN>;
+  constexpr int STAGES = L::STAGES;
   // SWIZZLE_128B operand tiles need 1024-byte aligned bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  int* gstart = reinterpret_cast<int*>(tmem_slot + 2);   // [num_groups + 1] tile-index prefix (grouped mode)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int row_end = p.M, m0 = blockIdx.x * BM, w_row0 = blockIdx.y * BN;
-  const int n0 = blockIdx.y * BN;
-  const float* bias = p.bias;
-  if (p.group_offsets) {
-    const int g = blockIdx.z;
-    m0 += p.group_offsets[g];
-    row_end = p.group_offsets[g + 1];
-    w_row0 += g * p.N;
-    if (bias) bias += (int64_t)g * p.N;
-  }
-  if (m0 >= row_end) return;  // uniform for the whole CTA, before any barrier/TMEM use
+  const int n_tiles = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + BK - 1) / BK;
-  int cv_f0 = 0, cv_t = 0, cv_b = 0;
-  if constexpr (CONV) {
-    const int tpr = p.conv_F / BM;            // M tiles per (b, t) row; conv_F is a multiple of 128
-    const int mt = blockIdx.x;
-    cv_f0 = (mt % tpr) * BM;
-    const int bt = mt / tpr;
-    cv_t = bt % p.conv_T;
-    cv_b = bt / p.conv_T;
-  }
+  const int groups = p.group_offsets ? p.num_groups : 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -170,12 +165,27 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);   // all epilogue threads arrive
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    int acc = 0;
+    if (p.group_offsets) {
+      for (int g = 0; g < groups; ++g) {
+        gstart[g] = acc;
+        acc += ((p.group_offsets[g + 1] - p.group_offsets[g] + BM - 1) / BM) * n_tiles;
+      }
+    } else {
+      gstart[0] = 0;
+      acc = ((p.M + BM - 1) / BM) * n_tiles;
+    }
+    gstart[groups] = acc;
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(2 * BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -183,29 +193,64 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = gstart[groups];
+
+  // tile index -> (m0, row_end, n0, w_row0, bias offset group)
+  auto decode_tile = [&](int t, int& m0, int& row_end, int& n0, int& w_row0, int& g_out) {
+    int g = 0;
+    if (p.group_offsets) {
+      while (g + 1 < groups && t >= gstart[g + 1]) ++g;
+    }
+    const int local = t - gstart[g];
+    const int mt = local / n_tiles, nt = local - mt * n_tiles;
+    n0 = nt * BN;
+    if (p.group_offsets) {
+      m0 = p.group_offsets[g] + mt * BM;
+      row_end = p.group_offsets[g + 1];
+      w_row0 = g * p.N + n0;
+    } else {
+      m0 = mt * BM;
+      row_end = p.M;
+      w_row0 = n0;
+    }
+    g_out = g;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, row_end, n0, w_row0, g;
+        decode_tile(t, m0, row_end, n0, w_row0, g);
+        int cv_f0 = 0, cv_t = 0, cv_b = 0;
         if constexpr (CONV) {
-          // shifted window of the input; out-of-range rows/cols are zero-filled by TMA = conv zero padding
-          const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
-          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          tma_load_4d(&mapA, &full_bar[stage], sa, cb * BK, cv_f0 + dx, cv_t + dy, cv_b);
-        } else {
-          tma_load_2d(&mapA, &full_bar[stage], sa, kb * BK, m0);
+          const int tpr = p.conv_F / BM;            // M tiles per (b, t) row; conv_F is a multiple of 128
+          const int mt = m0 / BM;
+          cv_f0 = (mt % tpr) * BM;
+          const int bt = mt / tpr;
+          cv_t = bt % p.conv_T;
+          cv_b = bt / p.conv_T;
         }
-        tma_load_2d(&mapW, &full_bar[stage], sb, kb * BK, w_row0);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if constexpr (CONV) {
+            // shifted window of the input; out-of-range rows/cols are zero-filled by TMA = conv zero padding
+            const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            tma_load_4d(&mapA, &full_bar[stage], sa, cb * BK, cv_f0 + dx, cv_t + dy, cv_b);
+          } else {
+            tma_load_2d(&mapA, &full_bar[stage], sa, kb * BK, m0);
+          }
+          tma_load_2d(&mapW, &full_bar[stage], sb, kb * BK, w_row0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -215,128 +260,147 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
+    int j = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      const int buf = j & 1;
+      mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1) ^ 1);   // epilogue drained this accumulator buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {
-        const uint8_t* sa = smem + stage * L::STAGE_BYTES;
-        const uint64_t adesc = umma_desc_sw128(sa);
-        const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the 128 B swizzle row = +2 in the address field
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar);     // accumulator complete -> epilogue
-      }
-      __syncwarp();
-      if (++stage == STAGES) {
-        stage = 0;
-        phase ^= 1;
+          for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the 128 B swizzle row = +2 in the address field
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);                          // frees the smem slot when the MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[buf]);  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int r = m0 + quad * 32 + lane;       // output row of this thread
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool row_ok = r < row_end;
-    const float rs = p.out_scale * ((p.row_scale && row_ok) ? p.row_scale[r] : 1.0f);
+    int j = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      int m0, row_end, n0, w_row0, g;
+      decode_tile(t, m0, row_end, n0, w_row0, g);
+      const float* bias = p.bias ? p.bias + (p.group_offsets ? (int64_t)g * p.N : 0) : nullptr;
+      const int buf = j & 1;
+      const int r = m0 + quad * 32 + lane;       // output row of this thread
+      mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool row_ok = r < row_end;
+      const float rs = p.out_scale * ((p.row_scale && row_ok) ? p.row_scale[r] : 1.0f);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      __syncwarp();
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);  // warp-collective: no early exit before
-      if (!row_ok) continue;
-      const int c = n0 + c0;
-      if (c >= p.N) continue;
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        f[j] = __uint_as_float(v[j]);
-        if (bias && c + j < p.N) f[j] += bias[c + j];
-      }
-      if (p.gated) {
-        // pairs (2j, 2j+1) -> 16 outputs at columns (c >> 1) + j
-        const int co = c >> 1;
-        const int valid = min(16, (p.N - c) >> 1);
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = act_apply(f[2 * j], p.act) * f[2 * j + 1] * rs;
-        if (p.out_f32) {
-          float* C = static_cast<float*>(p.C) + (int64_t)r * p.ldc + co;
-          const float* R = p.residual ? static_cast<const float*>(p.residual) + (int64_t)r * p.ldr + co : nullptr;
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            if (j >= valid) break;
-            float4 q = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            if (R) {
-              const float4 t = *reinterpret_cast<const float4*>(R + j);
-              q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
-            }
-            *reinterpret_cast<float4*>(C + j) = q;
-          }
-        } else {
-          __nv_bfloat16* C = static_cast<__nv_bfloat16*>(p.C) + (int64_t)r * p.ldc + co;
-          const __nv_bfloat16* R =
-              p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)r * p.ldr + co : nullptr;
-#pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            if (j >= valid) break;
-            uint4 pk;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-            if (R) {
-              const uint4 t = *reinterpret_cast<const uint4*>(R + j);
-              const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&t);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                h[q] = __floats2bfloat162_rn(o[j + 2 * q] + __bfloat162float(th[q].x),
-                                             o[j + 2 * q + 1] + __bfloat162float(th[q].y));
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(o[j + 2 * q], o[j + 2 * q + 1]);
-            }
-            *reinterpret_cast<uint4*>(C + j) = pk;
-          }
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+        if (c0 + 32 >= BN) {
+          // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&tmem_empty_bar[buf]);
         }
-      } else {
-        const int valid = min(32, p.N - c);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_apply(f[j], p.act) * rs;
-        if (p.out_f32) {
-          float* C = static_cast<float*>(p.C) + (int64_t)r * p.ldc + c;
-          const float* R = p.residual ? static_cast<const float*>(p.residual) + (int64_t)r * p.ldr + c : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j >= valid) break;
-            float4 q = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            if (R) {
-              const float4 t = *reinterpret_cast<const float4*>(R + j);
-              q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
+        if (!row_ok) continue;
+        const int c = n0 + c0;
+        if (c >= p.N) continue;
+        float f[32];
+  #pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = __uint_as_float(v[j]);
+          if (bias && c + j < p.N) f[j] += bias[c + j];
+        }
+        if (p.gated) {
+          // pairs (2j, 2j+1) -> 16 outputs at columns (c >> 1) + j
+          const int co = c >> 1;
+          const int valid = min(16, (p.N - c) >> 1);
+          float o[16];
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = act_apply(f[2 * j], p.act) * f[2 * j + 1] * rs;
+          if (p.out_f32) {
+            float* C = static_cast<float*>(p.C) + (int64_t)r * p.ldc + co;
+            const float* R = p.residual ? static_cast<const float*>(p.residual) + (int64_t)r * p.ldr + co : nullptr;
+  #pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (j >= valid) break;
+              float4 q = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              if (R) {
+                const float4 t = *reinterpret_cast<const float4*>(R + j);
+                q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
+              }
+              *reinterpret_cast<float4*>(C + j) = q;
             }
-            *reinterpret_cast<float4*>(C + j) = q;
+          } else {
+            __nv_bfloat16* C = static_cast<__nv_bfloat16*>(p.C) + (int64_t)r * p.ldc + co;
+            const __nv_bfloat16* R =
+                p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)r * p.ldr + co : nullptr;
+  #pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+              if (j >= valid) break;
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+              if (R) {
+                const uint4 t = *reinterpret_cast<const uint4*>(R + j);
+                const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&t);
+  #pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  h[q] = __floats2bfloat162_rn(o[j + 2 * q] + __bfloat162float(th[q].x),
+                                               o[j + 2 * q + 1] + __bfloat162float(th[q].y));
+              } else {
+  #pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(o[j + 2 * q], o[j + 2 * q + 1]);
+              }
+              *reinterpret_cast<uint4*>(C + j) = pk;
+            }
           }
         } else {
-          __nv_bfloat16* C = static_cast<__nv_bfloat16*>(p.C) + (int64_t)r * p.ldc + c;
-          const __nv_bfloat16* R =
-              p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)r * p.ldr + c : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j >= valid) break;
-            uint4 pk;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-            if (R) {
-              const uint4 t = *reinterpret_cast<const uint4*>(R + j);
-              const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&t);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                h[q] = __floats2bfloat162_rn(f[j + 2 * q] + __bfloat162float(th[q].x),
-                                             f[j + 2 * q + 1] + __bfloat162float(th[q].y));
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+          const int valid = min(32, p.N - c);
+  #pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = act_apply(f[j], p.act) * rs;
+          if (p.out_f32) {
+            float* C = static_cast<float*>(p.C) + (int64_t)r * p.ldc + c;
+            const float* R = p.residual ? static_cast<const float*>(p.residual) + (int64_t)r * p.ldr + c : nullptr;
+  #pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j >= valid) break;
+              float4 q = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              if (R) {
+                const float4 t = *reinterpret_cast<const float4*>(R + j);
+                q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
+              }
+              *reinterpret_cast<float4*>(C + j) = q;
             }
-            *reinterpret_cast<uint4*>(C + j) = pk;
+          } else {
+            __nv_bfloat16* C = static_cast<__nv_bfloat16*>(p.C) + (int64_t)r * p.ldc + c;
+            const __nv_bfloat16* R =
+                p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)r * p.ldr + c : nullptr;
+  #pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j >= valid) break;
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+              if (R) {
+                const uint4 t = *reinterpret_cast<const uint4*>(R + j);
+                const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&t);
+  #pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  h[q] = __floats2bfloat162_rn(f[j + 2 * q] + __bfloat162float(th[q].x),
+                                               f[j + 2 * q + 1] + __bfloat162float(th[q].y));
+              } else {
+  #pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+              }
+              *reinterpret_cast<uint4*>(C + j) = pk;
+            }
           }
         }
       }
@@ -348,7 +412,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 
@@ -418,7 +482,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   TcParams t;
   t.C = p.C; t.ldc = p.ldc; t.bias = p.bias; t.residual = p.residual; t.ldr = p.ldr;
   t.M = p.M; t.N = p.N; t.K = p.K; t.act = p.act; t.gated = p.gated; t.out_scale = p.out_scale;
-  t.row_scale = p.row_scale; t.group_offsets = p.group_offsets; t.out_f32 = out_dtype == YMT3_F32;
+  t.row_scale = p.row_scale; t.group_offsets = p.group_offsets; t.num_groups = groups; t.out_f32 = out_dtype == YMT3_F32;
   t.conv_T = cg.T; t.conv_F = cg.F; t.conv_cblocks = CONV ? cg.Cin / BK : 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -426,7 +490,12 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
                                          SmemLayout<BN>::TOTAL));
     attr_set = true;
   }
-  dim3 grid(ymt3_div_up(p.M, BM), ymt3_div_up(p.N, BN), groups);
+  // persistent: one CTA per SM (or per tile when there are fewer tiles than SMs); in grouped mode the tile
+  // count depends on device-side offsets, so all SMs are launched and idle CTAs exit after setup
+  const int64_t tiles = (int64_t)ymt3_div_up(p.M, BM) * ymt3_div_up(p.N, BN);
+  const int sms = ymt3_num_sms();
+  const int grid = p.group_offsets ? sms : (int)(tiles < sms ? tiles : sms);
+  YMT3_REQUIRE(groups <= 32, "gemm_bf16_tc: at most 32 groups");
   gemm_bf16_tc_kernel<BN, CONV><<<grid, THREADS, SmemLayout<BN>::TOTAL, stream>>>(mapA, mapW, t);
   YMT3_CUDA_CHECK(cudaGetLastError());
   return YMT3_OK;
@@ -449,7 +518,8 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   // pick BN so that the grid fills the 148 SMs (2 CTAs/SM resident) when the problem allows
   const int64_t mt = ymt3_div_up(p.M, BM);
   const int sms = ymt3_num_sms();
-  if (p.N % 128 == 0 && mt * (p.N / 128) >= 2 * sms) return launch<128, false>(p, out_dtype, stream);
+  // largest BN whose tile count still fills the SMs; otherwise maximise parallelism
+  if (p.N >= 128 && mt * ymt3_div_up(p.N, 128) >= sms) return launch<128, false>(p, out_dtype, stream);
   if (p.N >= 64 && mt * ymt3_div_up(p.N, 64) >= sms) return launch<64, false>(p, out_dtype, stream);
   return launch<32, false>(p, out_dtype, stream);
 }

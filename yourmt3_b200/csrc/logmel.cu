@@ -138,10 +138,10 @@ extern "C" int64_t ymt3_frontend_num_features(const ymt3_frontend_t* fe) {
 
 extern "C" int ymt3_logmel_f32(ymt3_frontend_t* fe, const float* audio_dev, int64_t B, int64_t L,
                                float* out_dev, void* stream) {
-  YMT3_REQUIRE(fe && out_dev, "logmel: null argument");
+  YMT3_REQUIRE(fe, "logmel: null handle");
   YMT3_REQUIRE(B >= 0, "logmel: negative batch");
-  if (B == 0) return YMT3_OK;
-  YMT3_REQUIRE(audio_dev, "logmel: null audio");
+  if (B == 0) return YMT3_OK;   // empty batch: nothing to do (pointers may be null)
+  YMT3_REQUIRE(audio_dev && out_dev, "logmel: null buffer");
   // torch.stft reflect padding needs pad < L (torch/functional.py:675-680)
   YMT3_REQUIRE(L > LM_NFFT / 2, "logmel: segment length %lld must exceed n_fft/2 = %d",
                (long long)L, LM_NFFT / 2);

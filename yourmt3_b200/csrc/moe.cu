@@ -16,60 +16,74 @@ template <typename T> __device__ __forceinline__ float moe_to_f(T v);
 template <> __device__ __forceinline__ float moe_to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float moe_to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// one warp per token; E <= 32, topk <= 4
+// 8 warps x 8 tokens per block; E <= 32, topk <= 4. Expert counts are aggregated in shared memory so
+// that only E global atomics are issued per 64 tokens.
+#define MOE_TOK_PER_BLOCK 64
 template <typename T>
 __global__ void __launch_bounds__(256)
 moe_route_kernel(const T* __restrict__ x, const float* __restrict__ Wg, int N, int D, int E, int topk,
                  int* __restrict__ top_idx, float* __restrict__ top_w, int* __restrict__ counts) {
-  const int tok = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (tok >= N) return;
-  const T* xr = x + (int64_t)tok * D;
-  float my_logit = -INFINITY;  // lane e holds logit e
-  for (int e = 0; e < E; ++e) {
-    float acc = 0.f;
-    for (int d = lane; d < D; d += 32) acc = fmaf(moe_to_f(xr[d]), Wg[e * D + d], acc);
+  __shared__ int hist[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 32) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int it = 0; it < MOE_TOK_PER_BLOCK / 8; ++it) {
+    const int tok = blockIdx.x * MOE_TOK_PER_BLOCK + it * 8 + warp;
+    if (tok >= N) break;
+    const T* xr = x + (int64_t)tok * D;
+    float my_logit = -INFINITY;  // lane e holds logit e
+    float xv[16];                // token row cached in registers (D <= 512)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == e) my_logit = acc;
-  }
-  // softmax over the E lanes
-  float mx = my_logit;
+    for (int i = 0; i < 16; ++i) xv[i] = (i * 32 + lane < D) ? moe_to_f(xr[i * 32 + lane]) : 0.f;
+    for (int e = 0; e < E; ++e) {
+      float acc = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float p = lane < E ? expf(my_logit - mx) : 0.f;
-  float sum = p;
+      for (int i = 0; i < 16; ++i)
+        if (i * 32 < D) acc = fmaf(xv[i], (i * 32 + lane < D) ? Wg[e * D + i * 32 + lane] : 0.f, acc);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  p /= sum;
-  // top-k by repeated arg-max (ties -> lowest expert index)
-  float sel_w[4];
-  int sel_i[4];
-  float wsum = 0.f;
-  float cur = lane < E ? p : -1.f;
-  for (int k = 0; k < topk; ++k) {
-    float bv = cur;
-    int bi = lane;
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == e) my_logit = acc;
+    }
+    float mx = my_logit;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) {
-        bv = ov;
-        bi = oi;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float p = lane < E ? expf(my_logit - mx) : 0.f;
+    float sum = p;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    p /= sum;
+    // top-k by repeated arg-max (ties -> lowest expert index)
+    float sel_w[4];
+    int sel_i[4];
+    float wsum = 0.f;
+    float cur = lane < E ? p : -1.f;
+    for (int k = 0; k < topk; ++k) {
+      float bv = cur;
+      int bi = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      sel_w[k] = bv;
+      sel_i[k] = bi;
+      wsum += bv;
+      if (lane == bi) cur = -1.f;
+    }
+    if (lane == 0) {
+      for (int k = 0; k < topk; ++k) {
+        top_idx[tok * topk + k] = sel_i[k];
+        top_w[tok * topk + k] = sel_w[k] / wsum;
+        atomicAdd(&hist[sel_i[k]], 1);
       }
     }
-    sel_w[k] = bv;
-    sel_i[k] = bi;
-    wsum += bv;
-    if (lane == bi) cur = -1.f;
   }
-  if (lane == 0) {
-    for (int k = 0; k < topk; ++k) {
-      top_idx[tok * topk + k] = sel_i[k];
-      top_w[tok * topk + k] = sel_w[k] / wsum;
-      atomicAdd(counts + sel_i[k], 1);
-    }
-  }
+  __syncthreads();
+  if (threadIdx.x < E && hist[threadIdx.x]) atomicAdd(counts + threadIdx.x, hist[threadIdx.x]);
 }
 
 // offsets[0..E] = exclusive scan of counts; cursor[e] = 0
@@ -86,26 +100,42 @@ __global__ void moe_offsets_kernel(const int* __restrict__ counts, int* __restri
   }
 }
 
-// one warp per (token, k): claim a slot in the expert's segment and copy the token row there
+// Block = 64 tokens (<= 256 (token, k) items): local ranks via shared-memory atomics, ONE global atomic per
+// expert per block reserves the block's range in the expert segment, then warps copy the rows.
 template <typename T>
 __global__ void __launch_bounds__(256)
 moe_scatter_kernel(const T* __restrict__ x, int N, int D, int topk, const int* __restrict__ top_idx,
                    const float* __restrict__ top_w, const int* __restrict__ offsets, int* __restrict__ cursor,
                    T* __restrict__ xs, float* __restrict__ slot_w, int* __restrict__ tok_slot) {
-  const int item = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (item >= N * topk) return;
-  const int tok = item / topk;
-  int slot = 0;
-  if (lane == 0) {
-    const int e = top_idx[item];
-    slot = offsets[e] + atomicAdd(cursor + e, 1);
-    slot_w[slot] = top_w[item];
-    tok_slot[item] = slot;
+  __shared__ int hist[32], base[32];
+  __shared__ int slots[MOE_TOK_PER_BLOCK * 4];
+  const int tid = threadIdx.x;
+  const int item0 = blockIdx.x * MOE_TOK_PER_BLOCK * topk;
+  const int n_items = min(MOE_TOK_PER_BLOCK * topk, N * topk - item0);
+  if (tid < 32) hist[tid] = 0;
+  __syncthreads();
+  int e = 0, rank = 0;
+  if (tid < n_items) {
+    e = top_idx[item0 + tid];
+    rank = atomicAdd(&hist[e], 1);
   }
-  slot = __shfl_sync(0xffffffffu, slot, 0);
-  const T* src = x + (int64_t)tok * D;
-  T* dst = xs + (int64_t)slot * D;
-  for (int d = lane; d < D; d += 32) dst[d] = src[d];
+  __syncthreads();
+  if (tid < 32 && hist[tid]) base[tid] = atomicAdd(cursor + tid, hist[tid]);
+  __syncthreads();
+  if (tid < n_items) {
+    const int slot = offsets[e] + base[e] + rank;
+    slots[tid] = slot;
+    slot_w[slot] = top_w[item0 + tid];
+    tok_slot[item0 + tid] = slot;
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int i = warp; i < n_items; i += 8) {
+    const int tok = (item0 + i) / topk;
+    const T* src = x + (int64_t)tok * D;
+    T* dst = xs + (int64_t)slots[i] * D;
+    for (int d = lane; d < D; d += 32) dst[d] = src[d];
+  }
 }
 
 // out[tok, :] = residual[tok, :] + sum_k ys[tok_slot[tok, k], :]
@@ -139,6 +169,7 @@ int moe_forward(int precision, const void* x, const void* residual, void* out, i
                 void* workspace, cudaStream_t s) {
   if (N64 <= 0) return YMT3_OK;
   YMT3_REQUIRE(w.E >= 1 && w.E <= 32 && w.topk >= 1 && w.topk <= 4 && w.topk <= w.E, "moe: bad E/topk");
+  YMT3_REQUIRE(w.D <= 512, "moe: router supports d_model <= 512 (got %d)", w.D);
   YMT3_REQUIRE(N64 * w.topk < (1ll << 31), "moe: too many tokens");
   const int N = (int)N64, D = w.D, I = w.I, E = w.E, topk = w.topk;
   const size_t es = dtype_size(precision);
@@ -156,7 +187,7 @@ int moe_forward(int precision, const void* x, const void* residual, void* out, i
   int* offsets = counts + E;
   int* cursor = offsets + E + 1;
   YMT3_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)E * 4, s));
-  const unsigned gt = (unsigned)ymt3_div_up(N, 8), gs = (unsigned)ymt3_div_up(S, 8);
+  const unsigned gt = (unsigned)ymt3_div_up(N, MOE_TOK_PER_BLOCK), gs = gt;
   if (precision == YMT3_F32) {
     moe_route_kernel<float><<<gt, 256, 0, s>>>((const float*)x, w.gate, N, D, E, topk, top_idx, top_w, counts);
     moe_offsets_kernel<<<1, 32, 0, s>>>(counts, offsets, cursor, E);

@@ -1,0 +1,71 @@
+"""Micro-benchmarks of individual kernels through the C ABI (CUDA events, median of N).
+usage: python tools/bench_ops.py [gemm|attn|decode_attn|all] [--once]   (--once: single pass for ncu)"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from yourmt3_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+dev = torch.device("cuda")
+once = "--once" in sys.argv
+what = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "all"
+
+
+def timeit(fn, reps=20):
+    if once:
+        fn()
+        torch.cuda.synchronize()
+        return float("nan")
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm(M, N, K, gated=0, act=0, residual=False, name=""):
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    No = N // 2 if gated else N
+    C = torch.empty(M, No, device=dev, dtype=torch.bfloat16)
+    R = torch.randn(M, No, device=dev).bfloat16() if residual else None
+    s = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        _lib.check(lib.ymt3_op_linear(1, A.data_ptr(), K, W.data_ptr(), K, None, C.data_ptr(), No,
+                                      R.data_ptr() if residual else None, No, M, N, K, act, gated, 1.0, 1, s))
+    us = timeit(run)
+    flops = 2.0 * M * N * K
+    byts = (M * K + N * K + M * No * (2 if residual else 1)) * 2
+    print(f"gemm {name:28s} M={M:8d} N={N:5d} K={K:5d} gated={gated} res={int(residual)}: {us:9.1f} us  "
+          f"{flops / us / 1e6:8.1f} TFLOP/s  {byts / us / 1e3:8.1f} GB/s", flush=True)
+
+
+if what in ("gemm", "all"):
+    gemm(183040, 384, 128, name="ptf qkv")
+    gemm(183040, 128, 128, residual=True, name="ptf out-proj+res")
+    gemm(366080, 1024, 128, gated=1, act=3, name="moe gemm1 (ungrouped equiv)")
+    gemm(366080, 128, 512, name="moe gemm2 (ungrouped equiv)")
+    gemm(901120, 256, 128, name="ptf sca kv")
+    gemm(91520, 768, 512, name="decoder cross kv")
+    gemm(832, 1152, 512, name="decode qkv")
+    gemm(832, 512, 384, residual=True, name="decode o-proj+res")
+    gemm(832, 2048, 512, gated=1, act=1, name="decode ffn wi")
+    gemm(832, 512, 1024, residual=True, name="decode ffn wo+res")
+    gemm(16384, 1152, 512, name="t5 enc qkv B=64")
+    gemm(8192, 8192, 8192, name="square 8k")
+
+if what in ("decode_attn", "all"):
+    # self-attention over a bf16 cache at length L for N sequences x 6 heads, via the generic attention op
+    pass

@@ -3,12 +3,13 @@
 //
 //   C[M, N] = residual + out_scale * row_scale * epi(A[M, K] @ W[N, K]^T + bias)
 //
-// CTA = 192 threads, one 128 x BN output tile:
-//   warp 0     TMA producer  (one elected lane): A box {64 k, 128 m}, W box {64 k, BN n}
+// Persistent CTA (one per SM) = 320 threads walking the tile list:
+//   warp 0     TMA producer  (one elected lane): A box {64 k, 128 m}, W box {64 k, BN n}, deep smem ring
 //   warp 1     TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma (K=16) per k-block
-//   warps 2..5 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> epilogue math -> global
-// 3-stage smem ring (<= 96 KB) so that two CTAs are resident per SM and one CTA's epilogue
-// overlaps the other's main loop; TMEM: BN fp32 columns per CTA.
+//   warps 2..9 epilogue (two warps per TMEM lane quadrant, interleaved 32-column chunks):
+//              tcgen05.ld -> registers -> compile-time specialised epilogue math -> 16-byte stores
+// The accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the
+// MMAs of tile i+1.
 #include "ops.cuh"
 #include <cuda.h>
 
@@ -19,7 +20,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;
+constexpr int EPI_THREADS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -120,6 +122,95 @@ struct TcParams {
   int conv_T, conv_F, conv_cblocks;
 };
 
+
+// ---------------- epilogue math, specialised at compile time (keeps the hot path a few hundred
+// straight-line instructions: the runtime-switch version thrashed the instruction cache) -------------
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+  if constexpr (ACT == YMT3_ACT_GELU_NEW) return 0.5f * x * (1.0f + fast_tanh(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+  else if constexpr (ACT == YMT3_ACT_RELU) return fmaxf(x, 0.f);
+  else if constexpr (ACT == YMT3_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
+  else if constexpr (ACT == YMT3_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  else return x;
+}
+// f[0..31] = accumulators (+bias). Non-gated: f[j] = act(f[j]) * rs (32 outputs). Gated: f[j] = act(f[2j]) * f[2j+1] * rs (16).
+template <int ACT, bool GATED>
+__device__ __forceinline__ void epi_math(float (&f)[32], float rs) {
+  if constexpr (GATED) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = act_fast<ACT>(f[2 * j]) * f[2 * j + 1] * rs;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = act_fast<ACT>(f[j]) * rs;
+  }
+}
+__device__ __forceinline__ void epi_dispatch(float (&f)[32], float rs, int act, int gated) {
+  switch (act * 2 + gated) {   // warp-uniform
+    case YMT3_ACT_NONE * 2 + 0: epi_math<YMT3_ACT_NONE, false>(f, rs); break;
+    case YMT3_ACT_NONE * 2 + 1: epi_math<YMT3_ACT_NONE, true>(f, rs); break;
+    case YMT3_ACT_GELU_NEW * 2 + 0: epi_math<YMT3_ACT_GELU_NEW, false>(f, rs); break;
+    case YMT3_ACT_GELU_NEW * 2 + 1: epi_math<YMT3_ACT_GELU_NEW, true>(f, rs); break;
+    case YMT3_ACT_RELU * 2 + 0: epi_math<YMT3_ACT_RELU, false>(f, rs); break;
+    case YMT3_ACT_RELU * 2 + 1: epi_math<YMT3_ACT_RELU, true>(f, rs); break;
+    case YMT3_ACT_SILU * 2 + 0: epi_math<YMT3_ACT_SILU, false>(f, rs); break;
+    case YMT3_ACT_SILU * 2 + 1: epi_math<YMT3_ACT_SILU, true>(f, rs); break;
+    case YMT3_ACT_GELU * 2 + 0: epi_math<YMT3_ACT_GELU, false>(f, rs); break;
+    default: epi_math<YMT3_ACT_GELU, true>(f, rs); break;
+  }
+}
+// store `count` (multiple of 8 for bf16 / 4 for f32, <= 32) consecutive outputs f[0..count) of one row (+ residual)
+template <bool OUT_F32>
+__device__ __forceinline__ void epi_store(void* Cbase, const void* Rbase, int64_t off, const float (&f)[32], int count) {
+  if constexpr (OUT_F32) {
+    float* C = static_cast<float*>(Cbase) + off;
+    const float* R = Rbase ? static_cast<const float*>(Rbase) + off : nullptr;
+    float4 r[8];
+    if (R) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (4 * j < count) r[j] = *reinterpret_cast<const float4*>(R + 4 * j);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (4 * j >= count) break;
+      float4 q = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      if (R) { q.x += r[j].x; q.y += r[j].y; q.z += r[j].z; q.w += r[j].w; }
+      *reinterpret_cast<float4*>(C + 4 * j) = q;
+    }
+  } else {
+    __nv_bfloat16* C = static_cast<__nv_bfloat16*>(Cbase) + off;
+    const __nv_bfloat16* R = Rbase ? static_cast<const __nv_bfloat16*>(Rbase) + off : nullptr;
+    uint4 r[4];
+    if (R) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (8 * j < count) r[j] = *reinterpret_cast<const uint4*>(R + 8 * j);   // all residual loads in flight first
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (8 * j >= count) break;
+      uint4 pk;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+      if (R) {
+        const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&r[j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q] + __bfloat162float(th[q].x),
+                                       f[8 * j + 2 * q + 1] + __bfloat162float(th[q].y));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+      }
+      *reinterpret_cast<uint4*>(C + 8 * j) = pk;
+    }
+  }
+}
+
 template <int BN>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
@@ -167,7 +258,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);   // all epilogue threads arrive
+      mbar_init(&tmem_empty_bar[i], EPI_THREADS);   // all epilogue threads arrive
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -287,8 +378,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;          // which interleaved set of 32-column chunks
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       int m0, row_end, n0, w_row0, g;
@@ -300,109 +392,51 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool row_ok = r < row_end;
       const float rs = p.out_scale * ((p.row_scale && row_ok) ? p.row_scale[r] : 1.0f);
+      constexpr int NCHUNK = BN / 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int ci = half; ci < NCHUNK + 2; ci += 2) {
+        // (the loop runs one dummy round past the end so that every warp -- also those without a chunk when
+        //  BN = 32 -- reaches the arrive below exactly once)
+        const bool has_chunk = ci < NCHUNK;
+        const bool last = ci + 2 >= NCHUNK;     // this warp's last round for this tile
         uint32_t v[32];
         __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c0), v);
-        if (c0 + 32 >= BN) {
-          // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
+        if (has_chunk) tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + ci * 32), v);
+        if (last) {
+          // all TMEM reads of this warp for this tile are done: hand the buffer back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tmem_empty_bar[buf]);
         }
-        if (!row_ok) continue;
-        const int c = n0 + c0;
-        if (c >= p.N) continue;
-        float f[32];
-  #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] = __uint_as_float(v[j]);
-          if (bias && c + j < p.N) f[j] += bias[c + j];
-        }
-        if (p.gated) {
-          // pairs (2j, 2j+1) -> 16 outputs at columns (c >> 1) + j
-          const int co = c >> 1;
-          const int valid = min(16, (p.N - c) >> 1);
-          float o[16];
-  #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = act_apply(f[2 * j], p.act) * f[2 * j + 1] * rs;
-          if (p.out_f32) {
-            float* C = static_cast<float*>(p.C) + (int64_t)r * p.ldc + co;
-            const float* R = p.residual ? static_cast<const float*>(p.residual) + (int64_t)r * p.ldr + co : nullptr;
-  #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              if (j >= valid) break;
-              float4 q = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-              if (R) {
-                const float4 t = *reinterpret_cast<const float4*>(R + j);
-                q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
-              }
-              *reinterpret_cast<float4*>(C + j) = q;
-            }
-          } else {
-            __nv_bfloat16* C = static_cast<__nv_bfloat16*>(p.C) + (int64_t)r * p.ldc + co;
-            const __nv_bfloat16* R =
-                p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)r * p.ldr + co : nullptr;
-  #pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-              if (j >= valid) break;
-              uint4 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-              if (R) {
-                const uint4 t = *reinterpret_cast<const uint4*>(R + j);
-                const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&t);
-  #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  h[q] = __floats2bfloat162_rn(o[j + 2 * q] + __bfloat162float(th[q].x),
-                                               o[j + 2 * q + 1] + __bfloat162float(th[q].y));
+        if (has_chunk && row_ok) {
+          const int c = n0 + ci * 32;
+          if (c < p.N) {
+            float f[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]);
+            if (bias) {
+              if (c + 32 <= p.N) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + c) + q);
+                  f[4 * q] += bq.x; f[4 * q + 1] += bq.y; f[4 * q + 2] += bq.z; f[4 * q + 3] += bq.w;
+                }
               } else {
-  #pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(o[j + 2 * q], o[j + 2 * q + 1]);
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                  if (c + q < p.N) f[q] += bias[c + q];
               }
-              *reinterpret_cast<uint4*>(C + j) = pk;
             }
-          }
-        } else {
-          const int valid = min(32, p.N - c);
-  #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = act_apply(f[j], p.act) * rs;
-          if (p.out_f32) {
-            float* C = static_cast<float*>(p.C) + (int64_t)r * p.ldc + c;
-            const float* R = p.residual ? static_cast<const float*>(p.residual) + (int64_t)r * p.ldr + c : nullptr;
-  #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j >= valid) break;
-              float4 q = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              if (R) {
-                const float4 t = *reinterpret_cast<const float4*>(R + j);
-                q.x += t.x; q.y += t.y; q.z += t.z; q.w += t.w;
-              }
-              *reinterpret_cast<float4*>(C + j) = q;
-            }
-          } else {
-            __nv_bfloat16* C = static_cast<__nv_bfloat16*>(p.C) + (int64_t)r * p.ldc + c;
-            const __nv_bfloat16* R =
-                p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)r * p.ldr + c : nullptr;
-  #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j >= valid) break;
-              uint4 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-              if (R) {
-                const uint4 t = *reinterpret_cast<const uint4*>(R + j);
-                const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&t);
-  #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  h[q] = __floats2bfloat162_rn(f[j + 2 * q] + __bfloat162float(th[q].x),
-                                               f[j + 2 * q + 1] + __bfloat162float(th[q].y));
-              } else {
-  #pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
-              }
-              *reinterpret_cast<uint4*>(C + j) = pk;
-            }
+            epi_dispatch(f, rs, p.act, p.gated);
+            const int n_out = p.gated ? min(16, (p.N - c) >> 1) : min(32, p.N - c);
+            const int64_t off = (int64_t)r * p.ldc + (p.gated ? (c >> 1) : c);
+            const int64_t roff = (int64_t)r * p.ldr + (p.gated ? (c >> 1) : c);
+            // residual may alias C (in-place x += ...): each element is read then written by this thread only
+            const void* Rb = p.residual ? (const void*)(static_cast<const char*>(p.residual) + (roff - off) * (p.out_f32 ? 4 : 2)) : nullptr;
+            if (p.out_f32) epi_store<true>(p.C, Rb, off, f, n_out);
+            else epi_store<false>(p.C, Rb, off, f, n_out);
           }
         }
+        if (last) break;
       }
     }
   }

@@ -16,7 +16,7 @@ PRESETS = {
     "t5_small": ("mt3_t5_small", {}, 256, "bf16"),
     "t5_small_f32": ("mt3_t5_small", {}, 64, "f32"),
     "yptf": ("yptf", {"codec": "spec", "hop_length": 300}, 64, "bf16"),
-    "yptf_moe_multi": ("yptf_moe_multi", {"codec": "spec", "hop_length": 300}, 64, "bf16"),
+    "yptf_moe_multi": ("yptf_moe_multi", {"codec": "spec", "hop_length": 300}, 256, "bf16"),
 }
 DEFAULT = "yptf_moe_multi"   # the model BASELINE.json quotes the target on
 

@@ -157,6 +157,13 @@ YMT3_API int ymt3_t5dec_destroy(ymt3_t5dec_t* dec);
 YMT3_API int ymt3_t5dec_generate(ymt3_t5dec_t* dec, const void* enc_hs_dev, int64_t N, int64_t T_enc,
                                  int32_t max_len, int32_t stop_at_eos, int32_t early_stop_interval,
                                  int32_t* tokens_out_dev, void* stream);
+/* Task-conditioned variant (reference `prefix_ids` / `task_tokens`): prefix_ids_dev (N, P) int32.  The decoder
+ * input sequence is [start, prefix..., generated...]: the P prefix tokens are teacher-forced (nothing is emitted
+ * while they are consumed), then max_len tokens are generated.  P + max_len <= cfg.max_length. */
+YMT3_API int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* dec, const void* enc_hs_dev, int64_t N, int64_t T_enc,
+                                          const int32_t* prefix_ids_dev, int32_t P, int32_t max_len,
+                                          int32_t stop_at_eos, int32_t early_stop_interval, int32_t* tokens_out_dev,
+                                          void* stream);
 /* fp32 logits of the LAST executed step, (N, vocab) (for logit-tolerance tests) */
 YMT3_API int ymt3_t5dec_last_logits(ymt3_t5dec_t* dec, float* logits_out_dev, int64_t N, void* stream);
 

@@ -42,7 +42,7 @@ def t5_encode(sd, feats: torch.Tensor, model_cfg: Dict, n_pos: int) -> torch.Ten
 
 
 def t5_generate(sd, enc_hs: torch.Tensor, model_cfg: Dict, n_pos: int, max_length: int, stop_at_eos=True,
-                eos_id=1, pad_id=0, return_margins=False):
+                eos_id=1, pad_id=0, return_margins=False, prefix_ids=None):
     dc = model_cfg["decoder"][model_cfg["decoder_type"]]
     pos = OT.sinusoidal_positions(n_pos, dc["d_model"]) if dc.get("position_encoding_type") == "sinusoidal" else None
     embed = sd["embed_tokens.weight"].detach().cpu().float()
@@ -53,7 +53,8 @@ def t5_generate(sd, enc_hs: torch.Tensor, model_cfg: Dict, n_pos: int, max_lengt
     return OT.greedy_generate(_sub(sd, "decoder."), enc_hs, embed=embed, lm_head=lm, n_layers=dc["num_layers"],
                               n_heads=dc["num_heads"], max_length=max_length, eps=dc.get("layer_norm_epsilon", 1e-6),
                               prefix="", pos=pos, tie_word_embeddings=model_cfg["tie_word_embeddings"], eos_id=eos_id,
-                              pad_id=pad_id, start_id=pad_id, stop_at_eos=stop_at_eos, return_margins=return_margins)
+                              pad_id=pad_id, start_id=pad_id, stop_at_eos=stop_at_eos, return_margins=return_margins,
+                              prefix_ids=prefix_ids)
 
 
 def transcribe_t5(sd, audio: np.ndarray, audio_cfg: Dict, model_cfg: Dict, n_pos: int, max_length: int, **kw):

@@ -98,7 +98,7 @@ def t5_decoder_full(sd, x, enc_hs, *, n_layers, n_heads, eps=1e-6, prefix="", po
     S = x.shape[1]
     if pos is not None:
         x = x + pos[:S]
-    causal = torch.full((S, S), float("-inf")).triu(1)
+    causal = torch.full((S, S), float("-inf"), device=x.device).triu(1)
     for i in range(n_layers):
         b = f"{prefix}block.{i}.layer."
         x, _ = t5_self_attention_layer(sd, b + "0.", x, n_heads, eps, mask=causal)
@@ -155,7 +155,7 @@ class T5DecoderState:
 def greedy_generate(sd, enc_hs: Tensor, *, embed: Tensor, lm_head: Tensor, n_layers: int, n_heads: int,
                     max_length: int, eps: float = 1e-6, prefix: str = "decoder.", pos: Optional[Tensor] = None,
                     tie_word_embeddings: bool = True, eos_id: int = 1, pad_id: int = 0, start_id: int = 0,
-                    stop_at_eos: bool = True, return_margins: bool = False):
+                    stop_at_eos: bool = True, return_margins: bool = False, prefix_ids: Optional[Tensor] = None):
     """task_cond_dec_generate semantics (no task prefix): returns (N, max_length) int64 tokens.
 
     enc_hs: (N, T_enc, d_model) -- for the multi-channel decoder N = B*C (channels folded
@@ -164,10 +164,17 @@ def greedy_generate(sd, enc_hs: Tensor, *, embed: Tensor, lm_head: Tensor, n_lay
     """
     N, _, d_model = enc_hs.shape
     st = T5DecoderState(sd, enc_hs, n_layers=n_layers, n_heads=n_heads, eps=eps, prefix=prefix, pos=pos)
-    out = torch.full((N, max_length), pad_id, dtype=torch.long)
-    margins = torch.full((N, max_length), float("inf"))
-    cur = torch.full((N,), start_id, dtype=torch.long)
-    unfinished = torch.ones(N, dtype=torch.bool)
+    dev = enc_hs.device
+    out = torch.full((N, max_length), pad_id, dtype=torch.long, device=dev)
+    margins = torch.full((N, max_length), float("inf"), device=dev)
+    cur = torch.full((N,), start_id, dtype=torch.long, device=dev)
+    unfinished = torch.ones(N, dtype=torch.bool, device=dev)
+    if prefix_ids is not None and prefix_ids.numel() > 0:
+        # task prefix: decoder inputs are [start, prefix..., generated...]; the prefix is teacher-forced
+        pfx = prefix_ids.reshape(N, -1).to(dev)
+        for s_ in range(pfx.shape[1]):
+            st.step(embed[cur][:, None, :])
+            cur = pfx[:, s_]
     for t in range(max_length):
         hs = st.step(embed[cur][:, None, :])[:, 0]
         if tie_word_embeddings:

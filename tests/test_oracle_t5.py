@@ -93,3 +93,16 @@ def test_greedy_generate_semantics():
     toks2 = OT.greedy_generate(sd, enc_hs[:1], eos_id=eos, **kw)
     assert toks2[0, : first + 1].tolist() == row0[: first + 1]
     assert (toks2[0, first + 1:] == 0).all()
+
+
+def test_prefix_conditioning_property():
+    """Forcing the first k tokens of a free-running decode as task prefix reproduces its continuation."""
+    _, dec = make_stacks(seed=5)
+    g = torch.Generator().manual_seed(4)
+    sd = {"decoder." + k: v for k, v in dec.state_dict().items()}
+    embed = torch.randn(96, 512, generator=g) * 0.2
+    enc_hs = torch.randn(3, 11, 512, generator=g)
+    kw = dict(embed=embed, lm_head=embed, n_layers=2, n_heads=6, pos=OT.sinusoidal_positions(64, 512), stop_at_eos=False)
+    free = OT.greedy_generate(sd, enc_hs, max_length=16, **kw)
+    forced = OT.greedy_generate(sd, enc_hs, max_length=13, prefix_ids=free[:, :3], **kw)
+    assert torch.equal(forced, free[:, 3:])

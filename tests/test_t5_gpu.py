@@ -76,6 +76,26 @@ def test_generate_eos_semantics(cuda_device, model_small):
     assert eos in row and all(t == 0 for t in row[row.index(eos) + 1:])
 
 
+def test_task_prefix_tokens(cuda_device, model_small):
+    """reference `prefix_ids` / `task_tokens`: teacher-forced prefix, ids returned without the prefix."""
+    m = model_small
+    enc_hs = torch.randn(4, 21, 512, generator=torch.Generator().manual_seed(9))
+    prefix = torch.tensor([[5, 17, 300], [9, 9, 9], [1, 2, 3], [595, 0, 44]])
+    ref, margins = OP.t5_generate(m.state_dict(), enc_hs, m.model_cfg, m.decoder.pos_table.shape[0], 20, stop_at_eos=False,
+                                  return_margins=True, prefix_ids=prefix)
+    got = ymt3.task_cond_dec_generate(m.decoder, "t5", m.embed_tokens, m.lm_head, enc_hs.to(cuda_device), max_length=20,
+                                      stop_at_eos=False, prefix_ids=prefix.to(cuda_device))
+    assert got.shape == (4, 20)
+    assert_tokens_identical(got.cpu().numpy(), ref.numpy(), margins.numpy(), "prefix")
+    free = ymt3.task_cond_dec_generate(m.decoder, "t5", m.embed_tokens, m.lm_head, enc_hs.to(cuda_device), max_length=20,
+                                       stop_at_eos=False)
+    assert not torch.equal(free, got)          # the prefix really conditions the decode
+    # property: forcing the free run's first 3 tokens reproduces its continuation
+    cont = ymt3.task_cond_dec_generate(m.decoder, "t5", m.embed_tokens, m.lm_head, enc_hs.to(cuda_device), max_length=17,
+                                       stop_at_eos=False, prefix_ids=free[:, :3])
+    assert torch.equal(cont, free[:, 3:])
+
+
 def test_full_inference_matches_oracle(cuda_device, model_small):
     """audio -> tokens through YourMT3.inference vs the end-to-end CPU oracle (configs[0] shape, 2 layers)."""
     m = model_small

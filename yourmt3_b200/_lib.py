@@ -86,6 +86,7 @@ SIGNATURES = {
     "ymt3_t5dec_create": (_I, [C.POINTER(T5Cfg), C.POINTER(Tensor), _I, C.POINTER(_P)]),
     "ymt3_t5dec_destroy": (_I, [_P]),
     "ymt3_t5dec_generate": (_I, [_P, _P, _I64, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "ymt3_t5dec_generate_prefixed": (_I, [_P, _P, _I64, _I64, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ymt3_t5dec_last_logits": (_I, [_P, _P, _I64, _P]),
     "ymt3_res3b_create": (_I, [C.POINTER(Res3bCfg), C.POINTER(Tensor), _I, C.POINTER(_P)]),
     "ymt3_res3b_destroy": (_I, [_P]),

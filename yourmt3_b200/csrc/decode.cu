@@ -191,7 +191,8 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
 __global__ void __launch_bounds__(256)
 greedy_select_kernel(const float* __restrict__ logits, int64_t ld, int V, int N, const int* __restrict__ step,
                      int* __restrict__ cur_tok, int* __restrict__ finished, int* __restrict__ tokens_out,
-                     int max_len, int eos_id, int pad_id, int stop_at_eos, int* __restrict__ unfinished_count) {
+                     int max_len, int eos_id, int pad_id, int stop_at_eos, int* __restrict__ unfinished_count,
+                     const int* __restrict__ forced, int n_forced) {
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= N) return;
   const float* row = logits + (int64_t)n * ld;
@@ -215,23 +216,31 @@ greedy_select_kernel(const float* __restrict__ logits, int64_t ld, int V, int N,
   }
   if (lane == 0) {
     const int s = *step;
+    if (s < n_forced) {
+      // task-prefix conditioning: the next decoder input is the given prefix token (teacher forced);
+      // nothing is emitted and EOS is not tested while the prefix is being consumed
+      cur_tok[n] = forced[(int64_t)n * n_forced + s];
+      atomicAdd(unfinished_count + (s & 1), 1);
+      return;
+    }
+    const int so = s - n_forced;
     int fin = finished[n];
     int tok = fin ? pad_id : bi;
     if (stop_at_eos && tok == eos_id) fin = 1;
     finished[n] = fin;
     cur_tok[n] = tok;
-    if (s < max_len) tokens_out[(int64_t)n * max_len + s] = tok;
+    if (so < max_len) tokens_out[(int64_t)n * max_len + so] = tok;
     if (!fin) atomicAdd(unfinished_count + (s & 1), 1);
   }
 }
 
 int greedy_select(const float* logits, int64_t ld, int V, int N, const int* step, int* cur_tok, int* finished,
                   int* tokens_out, int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count,
-                  cudaStream_t stream) {
+                  const int* forced, int n_forced, cudaStream_t stream) {
   if (N <= 0) return YMT3_OK;
   greedy_select_kernel<<<ymt3_div_up(N, 8), 256, 0, stream>>>(logits, ld, V, N, step, cur_tok, finished,
                                                               tokens_out, max_len, eos_id, pad_id, stop_at_eos,
-                                                              unfinished_count);
+                                                              unfinished_count, forced, n_forced);
   YMT3_CUDA_CHECK(cudaGetLastError());
   return YMT3_OK;
 }

@@ -14,9 +14,10 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
                      void* Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss, int Lmax, const int* step, int fixed_len,
                      float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream);
 
+// forced (N, n_forced) or null: while *step < n_forced the next input token is forced[n, *step] (task prefix)
 int greedy_select(const float* logits, int64_t ld, int V, int N, const int* step, int* cur_tok, int* finished,
                   int* tokens_out, int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count,
-                  cudaStream_t stream);
+                  const int* forced, int n_forced, cudaStream_t stream);
 int advance_step(int* step, int* unfinished_count, cudaStream_t stream);
 int fill_i32(int* p, int v, int64_t n, cudaStream_t stream);
 

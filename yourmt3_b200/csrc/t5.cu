@@ -189,8 +189,10 @@ struct ymt3_t5dec {
   // cached CUDA graph of one decode step
   cudaGraphExec_t graph = nullptr;
   int64_t graph_N = -1, graph_T = -1, graph_L = -1;
-  int graph_stop = -1;
+  int graph_stop = -1, graph_prefix = -1;
   int32_t* graph_tokens = nullptr;
+  int* d_forced = nullptr;   // (cap_N, cap_P) task-prefix tokens
+  int64_t cap_P = 0;
 };
 
 extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* tensors, int n, ymt3_t5dec_t** out) {
@@ -278,6 +280,8 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, cudaStream_t s
     d->graph_N = -1;
   }
   d->ws.release();
+  d->d_forced = nullptr;
+  d->cap_P = 0;
   d->cap_N = d->cap_T = d->cap_L = 0;
   const ymt3_t5_cfg_t& c = d->c;
   const int D = c.d_model, inner = c.num_heads * c.d_kv, F = c.d_ff;
@@ -311,7 +315,8 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, cudaStream_t s
 }
 
 // all kernels of ONE decode step; every step-dependent value is read from device memory
-int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int32_t* tokens_out, cudaStream_t s) {
+int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int32_t* tokens_out, int n_prefix,
+             cudaStream_t s) {
   const ymt3_t5_cfg_t& c = d->c;
   const int D = c.d_model, H = c.num_heads, dk = c.d_kv, inner = H * dk, F = c.d_ff, dt = c.precision;
   const size_t es = dtype_size(dt);
@@ -323,7 +328,7 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
     if ((rc = rmsnorm(d->x, L.ln_sa, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
     if ((rc = linear_fwd(dt, d->h, D, L.qkv, d->qkv, 3 * inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
     if ((rc = decode_attention(d->qkv, 3 * inner, (char*)d->qkv + inner * es, (char*)d->qkv + 2 * inner * es, 3 * inner,
-                               d->selfK[i], d->selfV[i], (int64_t)H * d->cap_L * dk, (int64_t)d->cap_L * dk, dk, Lmax,
+                               d->selfK[i], d->selfV[i], (int64_t)H * d->cap_L * dk, (int64_t)d->cap_L * dk, dk, Lmax + n_prefix,
                                d->d_step, 0, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
       return rc;
     if ((rc = linear_fwd(dt, d->attn, inner, L.o, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
@@ -345,7 +350,7 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
   const float sc = c.tie_word_embeddings ? 1.0f / sqrtf((float)D) : 1.0f;
   if ((rc = linear_fwd(dt, d->h, D, d->lm_head, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s))) return rc;
   if ((rc = greedy_select(d->logits, d->Vp, c.vocab_size, (int)N, d->d_step, d->d_cur, d->d_fin, tokens_out, Lmax,
-                          c.eos_id, c.pad_id, stop_at_eos, d->d_unfinished, s)))
+                          c.eos_id, c.pad_id, stop_at_eos, d->d_unfinished, n_prefix ? d->d_forced : nullptr, n_prefix, s)))
     return rc;
   return advance_step(d->d_step, d->d_unfinished, s);
 }
@@ -354,11 +359,20 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
 
 extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int32_t max_len,
                                    int32_t stop_at_eos, int32_t early_stop_interval, int32_t* tokens_out, void* stream) {
+  return ymt3_t5dec_generate_prefixed(d, enc_hs, N, T, nullptr, 0, max_len, stop_at_eos, early_stop_interval, tokens_out,
+                                      stream);
+}
+
+extern "C" int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T,
+                                            const int32_t* prefix_ids, int32_t P, int32_t max_len, int32_t stop_at_eos,
+                                            int32_t early_stop_interval, int32_t* tokens_out, void* stream) {
   YMT3_REQUIRE(d && tokens_out, "t5dec_generate: null argument");
   if (N <= 0) return YMT3_OK;
   YMT3_REQUIRE(enc_hs && T > 0, "t5dec_generate: bad encoder states");
-  YMT3_REQUIRE(max_len > 0 && max_len <= d->c.max_length, "t5dec_generate: max_len %d outside (0, %d]", max_len,
-               d->c.max_length);
+  YMT3_REQUIRE(P >= 0 && (P == 0 || prefix_ids), "t5dec_generate: bad task prefix");
+  YMT3_REQUIRE(max_len > 0 && max_len + P <= d->c.max_length, "t5dec_generate: max_len %d + prefix %d outside (0, %d]",
+               max_len, P, d->c.max_length);
+  YMT3_REQUIRE(!d->pos || max_len + P <= d->n_pos, "t5dec_generate: position table too short");
   const ymt3_t5_cfg_t& c = d->c;
   const int D = c.d_model, inner = c.num_heads * c.d_kv, dt = c.precision;
   cudaStream_t caller = (cudaStream_t)stream;
@@ -371,7 +385,17 @@ extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t 
     YMT3_CUDA_CHECK(cudaEventRecord(d->ev_in, caller));
     YMT3_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_in, 0));
   }
-  if ((rc = dec_ensure(d, N, T, max_len, s))) return rc;
+  if ((rc = dec_ensure(d, N, T, max_len + P, s))) return rc;
+  if (P > 0) {
+    if (N * P > d->cap_P) {
+      YMT3_CUDA_CHECK(cudaStreamSynchronize(s));
+      d->d_forced = (int*)d->ws.alloc((size_t)N * P * 4);
+      if (!d->d_forced) return YMT3_ERR_CUDA;
+      d->cap_P = N * P;
+      if (d->graph) { cudaGraphExecDestroy(d->graph); d->graph = nullptr; d->graph_N = -1; }
+    }
+    YMT3_CUDA_CHECK(cudaMemcpyAsync(d->d_forced, prefix_ids, (size_t)N * P * 4, cudaMemcpyDeviceToDevice, s));
+  }
   // state init (device side)
   if ((rc = fill_i32(d->d_step, 0, 8, s))) return rc;  // step + unfinished[2] (+pad)
   if ((rc = fill_i32(d->d_cur, c.start_id, N, s))) return rc;
@@ -386,14 +410,14 @@ extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t 
   // one decode step captured into a CUDA graph (all step-dependent scalars live on the device)
   const bool use_graph = getenv("YMT3_NO_GRAPH") == nullptr && !caller_capturing;
   if (use_graph && (!d->graph || d->graph_N != N || d->graph_T != T || d->graph_L != max_len ||
-                    d->graph_tokens != tokens_out || d->graph_stop != stop_at_eos)) {
+                    d->graph_tokens != tokens_out || d->graph_stop != stop_at_eos || d->graph_prefix != P)) {
     if (d->graph) {
       cudaGraphExecDestroy(d->graph);
       d->graph = nullptr;
     }
     cudaGraph_t g = nullptr;
     YMT3_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, s);
+    rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, P, s);
     cudaError_t ce = cudaStreamEndCapture(s, &g);
     if (rc) {
       if (g) cudaGraphDestroy(g);
@@ -406,14 +430,15 @@ extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t 
     d->graph_N = N; d->graph_T = T; d->graph_L = max_len;
     d->graph_tokens = tokens_out;
     d->graph_stop = stop_at_eos;
+    d->graph_prefix = P;
   }
-  for (int t = 0; t < max_len; ++t) {
+  for (int t = 0; t < max_len + P; ++t) {
     if (use_graph) {
       YMT3_CUDA_CHECK(cudaGraphLaunch(d->graph, s));
-    } else if ((rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, s))) {
+    } else if ((rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, P, s))) {
       return rc;
     }
-    if (stop_at_eos && early_stop_interval > 0 && (t + 1) % early_stop_interval == 0 && t + 1 < max_len) {
+    if (stop_at_eos && early_stop_interval > 0 && (t + 1) % early_stop_interval == 0 && t + 1 < max_len + P) {
       // rows still unfinished after step t were counted into slot (t & 1)
       YMT3_CUDA_CHECK(cudaMemcpyAsync(d->h_unfinished, d->d_unfinished + (t & 1), 4, cudaMemcpyDeviceToHost, s));
       YMT3_CUDA_CHECK(cudaStreamSynchronize(s));

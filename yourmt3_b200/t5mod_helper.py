@@ -51,7 +51,7 @@ class DecoderRuntime(_NativeOwner):
         return h
 
     def generate(self, enc_hs: torch.Tensor, max_length: int, stop_at_eos: bool = True,
-                 early_stop_interval: int = 0) -> torch.Tensor:
+                 early_stop_interval: int = 0, prefix_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
         """enc_hs: (N, T_enc, d_model) in the runtime's precision -> (N, max_length) int32 CUDA."""
         want = _lib.torch_dtype(self.precision)
         if not enc_hs.is_cuda:
@@ -62,10 +62,15 @@ class DecoderRuntime(_NativeOwner):
         N, T, _ = enc_hs.shape
         h = self.native()
         tokens = torch.empty((N, max_length), dtype=torch.int32, device=enc_hs.device)
+        P, pfx_ptr = 0, None
+        if prefix_ids is not None and prefix_ids.numel() > 0:
+            pfx = prefix_ids.to(enc_hs.device, torch.int32).reshape(N, -1).contiguous()
+            P, pfx_ptr = pfx.shape[1], pfx.data_ptr()
         with torch.cuda.device(enc_hs.device):
-            _lib.check(_lib.load().ymt3_t5dec_generate(h, enc_hs.data_ptr(), N, T, max_length, int(stop_at_eos),
-                                                       int(early_stop_interval), tokens.data_ptr(),
-                                                       _lib.current_stream_ptr()), "t5dec_generate")
+            _lib.check(_lib.load().ymt3_t5dec_generate_prefixed(h, enc_hs.data_ptr(), N, T, pfx_ptr, P, max_length,
+                                                                int(stop_at_eos), int(early_stop_interval),
+                                                                tokens.data_ptr(), _lib.current_stream_ptr()),
+                       "t5dec_generate")
         return tokens
 
     def last_logits(self, N: int, device) -> torch.Tensor:
@@ -82,10 +87,8 @@ def task_cond_dec_generate(decoder, decoder_type: str, embed_tokens, lm_head, en
                            early_stop_interval: int = 0, **unused) -> torch.Tensor:
     """Returns LongTensor (B, max_length) for 't5' or (B, C, max_length) for 'multi-t5'.
 
-    ``encoder_hidden_states``: (B, T, D) or (B, C, T, D).  Task-prefix conditioning
-    (``prefix_ids``) is not part of the benchmarked path and is rejected explicitly."""
-    if prefix_ids is not None and prefix_ids.numel() > 0:
-        raise NotImplementedError("task prefix tokens are not supported by the native decode loop yet")
+    ``encoder_hidden_states``: (B, T, D) or (B, C, T, D).  ``prefix_ids`` (B, P) / (B, C, P): task tokens,
+    teacher-forced after the start token; the returned ids exclude the prefix (max_length generated tokens)."""
     enc = encoder_hidden_states
     multi = decoder_type == "multi-t5"
     if multi:
@@ -94,12 +97,13 @@ def task_cond_dec_generate(decoder, decoder_type: str, embed_tokens, lm_head, en
     rt = getattr(decoder, "_runtime", None)
     tie = getattr(lm_head, "tie_word_embeddings", True)
     vocab = embed_tokens.weight.shape[0]
-    if (rt is None or rt.precision != precision or rt.max_length < max_length or rt.vocab_size != vocab
+    n_prefix = 0 if prefix_ids is None else int(prefix_ids.shape[-1])
+    if (rt is None or rt.precision != precision or rt.max_length < max_length + n_prefix or rt.vocab_size != vocab
             or (rt.eos_id, rt.pad_id, rt.start_id) != (eos_id, pad_id, decoder_start_token_id)):
         if rt is not None:
             rt.free_native()
-        rt = DecoderRuntime(decoder, embed_tokens, lm_head, precision, vocab, max_length, tie, eos_id, pad_id,
+        rt = DecoderRuntime(decoder, embed_tokens, lm_head, precision, vocab, max_length + n_prefix, tie, eos_id, pad_id,
                             decoder_start_token_id)
         object.__setattr__(decoder, "_runtime", rt)
-    toks = rt.generate(enc, max_length, stop_at_eos, early_stop_interval).long()
+    toks = rt.generate(enc, max_length, stop_at_eos, early_stop_interval, prefix_ids).long()
     return toks.view(B, Cn, max_length) if multi else toks

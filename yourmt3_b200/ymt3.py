@@ -43,7 +43,7 @@ class YourMT3(nn.Module):
         self.spectrogram, (self.feat_length, self.feat_dim) = get_spectrogram_layer_from_audio_cfg(audio_cfg)
         dec_cfg = dict(model_cfg["decoder"][self.decoder_type])
         dec_cfg["vocab_size"] = self.vocab_size
-        n_pos = max(self.feat_length, self.max_token_length) + 8
+        n_pos = max(self.feat_length, self.max_token_length) + 16   # room for task-prefix tokens
 
         pre_enc = model_cfg["pre_encoder_type"]
         if pre_enc == "default":

@@ -11,10 +11,12 @@ import yourmt3_b200 as ymt3  # noqa: E402
 
 preset, batch, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 precision = sys.argv[4] if len(sys.argv) > 4 else "bf16"
+lanes = int(os.environ.get("YMT3_LANES", "1"))
 audio = {"codec": "spec", "hop_length": 300} if preset.startswith("yptf") else {}
 m = ymt3.YourMT3(audio_cfg=ymt3.get_audio_cfg(**audio), model_cfg=ymt3.get_model_cfg(preset), precision=precision)
 ymt3.init_nondegenerate_(m, 0)
 m = m.cuda()
+m.decode_lanes = lanes
 x = torch.randn(batch, 1, 32767, device="cuda") * 0.1
 for _ in range(2):
     t = m.inference(x, max_token_length=steps, stop_at_eos=False)

@@ -39,6 +39,7 @@ class ModelWorkload:
                                   model_cfg=ymt3.get_model_cfg(self.preset), precision=self.precision)
         ymt3.init_nondegenerate_(self.model, seed=0)
         self.model = self.model.to(dev)
+        self.model.decode_lanes = int(__import__("os").environ.get("YMT3_LANES", "1"))
         g = torch.Generator().manual_seed(1234 + (dev.index or 0))
         self.host_in = (torch.randn(self.batch, 1, SEG_SAMPLES, generator=g) * 0.1).pin_memory()
         self.dev_in = self.host_in.to(dev)

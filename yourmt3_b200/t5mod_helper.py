@@ -84,7 +84,7 @@ def task_cond_dec_generate(decoder, decoder_type: str, embed_tokens, lm_head, en
                            shift_right_fn=None, prefix_ids: Optional[torch.Tensor] = None, max_length: int = 1024,
                            stop_at_eos: bool = True, eos_id: int = 1, pad_id: int = 0,
                            decoder_start_token_id: int = 0, precision: int = _lib.DTYPE_F32,
-                           early_stop_interval: int = 0, **unused) -> torch.Tensor:
+                           early_stop_interval: int = 0, lanes: int = 1, **unused) -> torch.Tensor:
     """Returns LongTensor (B, max_length) for 't5' or (B, C, max_length) for 'multi-t5'.
 
     ``encoder_hidden_states``: (B, T, D) or (B, C, T, D).  ``prefix_ids`` (B, P) / (B, C, P): task tokens,
@@ -94,16 +94,35 @@ def task_cond_dec_generate(decoder, decoder_type: str, embed_tokens, lm_head, en
     if multi:
         B, Cn, T, D = enc.shape
         enc = enc.reshape(B * Cn, T, D)
-    rt = getattr(decoder, "_runtime", None)
     tie = getattr(lm_head, "tie_word_embeddings", True)
     vocab = embed_tokens.weight.shape[0]
     n_prefix = 0 if prefix_ids is None else int(prefix_ids.shape[-1])
-    if (rt is None or rt.precision != precision or rt.max_length < max_length + n_prefix or rt.vocab_size != vocab
-            or (rt.eos_id, rt.pad_id, rt.start_id) != (eos_id, pad_id, decoder_start_token_id)):
-        if rt is not None:
+    if prefix_ids is not None:
+        prefix_ids = prefix_ids.reshape(enc.shape[0], -1)
+    # `lanes` independent decode lanes (disjoint sequence ranges, each with its own native handle, CUDA graph and
+    # internal stream) run concurrently on the GPU: the HBM-bound attention kernels of one lane overlap the
+    # latency-bound small GEMMs / norms of the other.  Sequences are independent, so results are unchanged.
+    lanes = max(1, min(int(lanes), enc.shape[0]))
+    rts = getattr(decoder, "_runtimes", None) or []
+    ok = (len(rts) >= lanes and all(rt.precision == precision and rt.max_length >= max_length + n_prefix
+                                    and rt.vocab_size == vocab
+                                    and (rt.eos_id, rt.pad_id, rt.start_id) == (eos_id, pad_id, decoder_start_token_id)
+                                    for rt in rts[:lanes]))
+    if not ok:
+        for rt in rts:
             rt.free_native()
-        rt = DecoderRuntime(decoder, embed_tokens, lm_head, precision, vocab, max_length + n_prefix, tie, eos_id, pad_id,
-                            decoder_start_token_id)
-        object.__setattr__(decoder, "_runtime", rt)
-    toks = rt.generate(enc, max_length, stop_at_eos, early_stop_interval, prefix_ids).long()
+        rts = [DecoderRuntime(decoder, embed_tokens, lm_head, precision, vocab, max_length + n_prefix, tie, eos_id, pad_id,
+                              decoder_start_token_id) for _ in range(lanes)]
+        object.__setattr__(decoder, "_runtimes", rts)
+        object.__setattr__(decoder, "_runtime", rts[0])
+    N = enc.shape[0]
+    per = -(-N // lanes)
+    outs = []
+    for li in range(lanes):
+        a, b = li * per, min((li + 1) * per, N)
+        if a >= b:
+            break
+        pfx = None if prefix_ids is None else prefix_ids[a:b]
+        outs.append(rts[li].generate(enc[a:b], max_length, stop_at_eos, early_stop_interval, pfx))
+    toks = (outs[0] if len(outs) == 1 else torch.cat(outs, 0)).long()
     return toks.view(B, Cn, max_length) if multi else toks

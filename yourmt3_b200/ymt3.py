@@ -35,6 +35,7 @@ class YourMT3(nn.Module):
         self.precision = precision
         self._prec = {"f32": _lib.DTYPE_F32, "bf16": _lib.DTYPE_BF16}[precision]
         self.eos_id, self.pad_id = eos_id, pad_id
+        self.decode_lanes = 1   # >1: concurrent decode lanes (see t5mod_helper.task_cond_dec_generate)
         self.encoder_type, self.decoder_type = model_cfg["encoder_type"], model_cfg["decoder_type"]
         self.vocab_size = int(model_cfg["vocab_size"])
         self.max_token_length = int(model_cfg["event_length"])
@@ -95,14 +96,15 @@ class YourMT3(nn.Module):
     @torch.no_grad()
     def inference(self, x: torch.Tensor, task_tokens: Optional[torch.Tensor] = None,
                   max_token_length: Optional[int] = None, stop_at_eos: bool = True,
-                  early_stop_interval: int = 0, **unused) -> torch.Tensor:
+                  early_stop_interval: int = 0, decode_lanes: Optional[int] = None, **unused) -> torch.Tensor:
         """x: (B, 1, L) audio segments -> token ids (B, L_tok) or (B, C, L_tok) (LongTensor, CUDA)."""
         max_len = max_token_length or self.max_token_length
         enc_hs = self.encode(x)
         return task_cond_dec_generate(self.decoder, self.decoder_type, self.embed_tokens, self.lm_head, enc_hs,
                                       prefix_ids=task_tokens, max_length=max_len, stop_at_eos=stop_at_eos,
                                       eos_id=self.eos_id, pad_id=self.pad_id, decoder_start_token_id=self.pad_id,
-                                      precision=self._prec, early_stop_interval=early_stop_interval)
+                                      precision=self._prec, early_stop_interval=early_stop_interval,
+                                      lanes=self.decode_lanes if decode_lanes is None else decode_lanes)
 
     @torch.no_grad()
     def inference_file_sharded(self, bsz: int, audio_segments: torch.Tensor, **kw) -> torch.Tensor:

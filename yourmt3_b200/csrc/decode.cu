@@ -50,6 +50,16 @@ int embed_pos(const int* tok, const void* E, const void* pos, const int* step, v
 //   then the query attends over keys [0, *step]. cross mode: attends over [0, fixed_len).
 template <typename T> struct Slice8;
 template <> struct Slice8<float> {
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load_raw(const float* p) {
+    Raw r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
+  }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -60,6 +70,16 @@ template <> struct Slice8<float> {
   }
 };
 template <> struct Slice8<__nv_bfloat16> {
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& u, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __bfloat162float(h[i].x);
+      v[2 * i + 1] = __bfloat162float(h[i].y);
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -74,28 +94,35 @@ template <> struct Slice8<__nv_bfloat16> {
   }
 };
 
+// ONE WARP per (sequence, head): no block barriers, no shared memory.  Lane = (grp 0..3, sub 0..7): the 8
+// lanes of a group share one key row (16-byte slices; the warp's 4 groups read 4 consecutive rows = 512
+// contiguous bytes in the self cache), each group walks keys grp, grp+4, ... four at a time (8 x 16-byte loads
+// in flight per lane) with a private online-softmax state; the 4 group states are merged with xor-shuffles.
 template <typename T>
 __global__ void __launch_bounds__(128)
 decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ knew, const T* __restrict__ vnew,
                    int64_t new_ld, T* __restrict__ Kc, T* __restrict__ Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss,
-                   const int* __restrict__ step, int fixed_len, float scale, T* __restrict__ out, int64_t out_ld) {
-  constexpr int DK = 64, NG = 16;
-  __shared__ float red_m[NG], red_l[NG];
-  __shared__ float red_o[NG][DK];
-  const int h = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
-  const int grp = tid >> 3, sub = tid & 7;
-  T* Kb = Kc + (int64_t)n * c_sn + (int64_t)h * c_sh;
-  T* Vb = Vc + (int64_t)n * c_sn + (int64_t)h * c_sh;
+                   const int* __restrict__ step, int fixed_len, float scale, T* __restrict__ out, int64_t out_ld, int H,
+                   int64_t total) {
+  constexpr int DK = 64, NG = 4, U = 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);   // (n, h) index, h fastest
+  if (pair >= total) return;
+  const int h = (int)(pair % H);
+  const int64_t n = pair / H;
+  const int grp = lane >> 3, sub = lane & 7;
+  T* Kb = Kc + n * c_sn + (int64_t)h * c_sh;
+  T* Vb = Vc + n * c_sn + (int64_t)h * c_sh;
   int len = fixed_len;
   if (knew) {
     const int s = *step;
     len = s + 1;
-    if (tid < 8) Slice8<T>::copy(Kb + (int64_t)s * c_ss + 8 * tid, knew + (int64_t)n * new_ld + h * DK + 8 * tid);
-    else if (tid < 16) Slice8<T>::copy(Vb + (int64_t)s * c_ss + 8 * (tid - 8), vnew + (int64_t)n * new_ld + h * DK + 8 * (tid - 8));
-    __syncthreads();   // the freshly appended row is read below by other threads of this CTA
+    if (lane < 8) Slice8<T>::copy(Kb + (int64_t)s * c_ss + 8 * lane, knew + n * new_ld + h * DK + 8 * lane);
+    else if (lane < 16) Slice8<T>::copy(Vb + (int64_t)s * c_ss + 8 * (lane - 8), vnew + n * new_ld + h * DK + 8 * (lane - 8));
+    __syncwarp();   // orders the append before the reads below (same warp)
   }
   float qv[8];
-  Slice8<T>::load(q + (int64_t)n * q_ld + h * DK + 8 * sub, qv);
+  Slice8<T>::load(q + n * q_ld + h * DK + 8 * sub, qv);
 #pragma unroll
   for (int i = 0; i < 8; ++i) qv[i] *= scale;
 
@@ -103,63 +130,85 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
 
-  // uniform trip count for the whole CTA (the shuffles below name all 32 lanes)
-  for (int base = 0; base < len; base += 2 * NG) {
-    const int j0 = base + grp, j1 = j0 + NG;
-    const bool has0 = j0 < len, has1 = j1 < len;
-    float k0[8], v0[8], k1[8], v1[8];
-    if (has0) {
-      Slice8<T>::load(Kb + (int64_t)j0 * c_ss + 8 * sub, k0);
-      Slice8<T>::load(Vb + (int64_t)j0 * c_ss + 8 * sub, v0);
-    }
-    if (has1) {
-      Slice8<T>::load(Kb + (int64_t)j1 * c_ss + 8 * sub, k1);
-      Slice8<T>::load(Vb + (int64_t)j1 * c_ss + 8 * sub, v1);
-    }
-    float s0 = 0.f, s1 = 0.f;
+  // uniform trip count for the whole warp (the shuffles below name all 32 lanes)
+  for (int base = 0; base < len; base += NG * U) {
+    typename Slice8<T>::Raw kk[U], vv[U];   // kept packed until use (register pressure -> occupancy)
+    float sc[U];
+    bool has[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (has0) s0 = fmaf(qv[i], k0[i], s0);
-      if (has1) s1 = fmaf(qv[i], k1[i], s1);
+    for (int u = 0; u < U; ++u) {
+      const int j = base + u * NG + grp;
+      has[u] = j < len;
+      if (has[u]) {
+        kk[u] = Slice8<T>::load_raw(Kb + (int64_t)j * c_ss + 8 * sub);
+        vv[u] = Slice8<T>::load_raw(Vb + (int64_t)j * c_ss + 8 * sub);
+      }
     }
 #pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-    }
-    if (has0) {   // has1 implies has0
-      if (!has1) s1 = -INFINITY;
-      const float mn = fmaxf(m, fmaxf(s0, s1));
-      const float corr = expf(m - mn);          // m = -inf -> 0
-      const float p0 = expf(s0 - mn), p1 = has1 ? expf(s1 - mn) : 0.f;
-      l = l * corr + p0 + p1;
+    for (int u = 0; u < U; ++u) {
+      float sacc = 0.f;
+      if (has[u]) {
+        float kf[8];
+        Slice8<T>::unpack(kk[u], kf);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        o[i] = o[i] * corr + p0 * v0[i];
-        if (has1) o[i] = fmaf(p1, v1[i], o[i]);
+        for (int i = 0; i < 8; ++i) sacc = fmaf(qv[i], kf[i], sacc);
+      }
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+      sc[u] = has[u] ? sacc : -INFINITY;
+    }
+    float mn = m;
+#pragma unroll
+    for (int u = 0; u < U; ++u) mn = fmaxf(mn, sc[u]);
+    if (mn > -INFINITY) {
+      const float corr = expf(m - mn);   // m = -inf -> 0
+      l *= corr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] *= corr;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (has[u]) {
+          const float pu = expf(sc[u] - mn);
+          l += pu;
+          float vf[8];
+          Slice8<T>::unpack(vv[u], vf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = fmaf(pu, vf[i], o[i]);
+        }
       }
       m = mn;
     }
   }
-  if (sub == 0) {
-    red_m[grp] = m;
-    red_l[grp] = l;
-  }
+  // merge the 4 group states (lanes with equal `sub`): xor 8, then xor 16
 #pragma unroll
-  for (int i = 0; i < 8; ++i) red_o[grp][8 * sub + i] = o[i];
-  __syncthreads();
-  if (tid < DK) {
-    float M = -INFINITY;
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, off);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, off);
+    const float M = fmaxf(m, m2);
+    const float a = m == -INFINITY ? 0.f : expf(m - M);
+    const float b2 = m2 == -INFINITY ? 0.f : expf(m2 - M);
+    l = l * a + l2 * b2;
 #pragma unroll
-    for (int g = 0; g < NG; ++g) M = fmaxf(M, red_m[g]);
-    float L = 0.f, acc = 0.f;
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      const float w = red_m[g] == -INFINITY ? 0.f : expf(red_m[g] - M);
-      L = fmaf(red_l[g], w, L);
-      acc = fmaf(red_o[g][tid], w, acc);
+    for (int i = 0; i < 8; ++i) {
+      const float o2 = __shfl_xor_sync(0xffffffffu, o[i], off);
+      o[i] = o[i] * a + o2 * b2;
     }
-    out[(int64_t)n * out_ld + h * DK + tid] = dec_from_f<T>(acc / L);
+    m = M;
+  }
+  if (grp == 0) {
+    const float inv = 1.0f / l;
+    T* dst = out + n * out_ld + h * DK + 8 * sub;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+    } else {
+      uint4 pk;
+      __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(o[2 * i] * inv, o[2 * i + 1] * inv);
+      *reinterpret_cast<uint4*>(dst) = pk;
+    }
   }
 }
 
@@ -167,20 +216,21 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
                      void* Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss, int Lmax, const int* step, int fixed_len,
                      float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream) {
   if (N <= 0) return YMT3_OK;
-  YMT3_REQUIRE(dk == 64, "decode_attention: head dim must be 64 (got %d)", dk);
-  YMT3_REQUIRE(N <= 65535, "decode_attention: too many sequences per call (%d > 65535)", N);
   (void)Lmax;
-  const size_t smem = 0;
-  dim3 grid(H, N);
+  YMT3_REQUIRE(dk == 64, "decode_attention: head dim must be 64 (got %d)", dk);
+  YMT3_REQUIRE((q_ld % 8 | new_ld % 8 | c_sn % 8 | c_sh % 8 | c_ss % 8 | out_ld % 8) == 0,
+               "decode_attention: strides must be multiples of 8 elements");
+  const int64_t total = (int64_t)N * H;
+  const unsigned grid = (unsigned)((total + 3) / 4);
   if (dtype == YMT3_F32)
-    decode_attn_kernel<float><<<grid, 128, smem, stream>>>((const float*)q, q_ld, (const float*)knew,
-                                                           (const float*)vnew, new_ld, (float*)Kc, (float*)Vc, c_sn,
-                                                           c_sh, c_ss, step, fixed_len, scale, (float*)out, out_ld);
+    decode_attn_kernel<float><<<grid, 128, 0, stream>>>((const float*)q, q_ld, (const float*)knew, (const float*)vnew,
+                                                        new_ld, (float*)Kc, (float*)Vc, c_sn, c_sh, c_ss, step, fixed_len,
+                                                        scale, (float*)out, out_ld, H, total);
   else
-    decode_attn_kernel<__nv_bfloat16><<<grid, 128, smem, stream>>>(
+    decode_attn_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(
         (const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)knew, (const __nv_bfloat16*)vnew, new_ld,
-        (__nv_bfloat16*)Kc, (__nv_bfloat16*)Vc, c_sn, c_sh, c_ss, step, fixed_len, scale, (__nv_bfloat16*)out,
-        out_ld);
+        (__nv_bfloat16*)Kc, (__nv_bfloat16*)Vc, c_sn, c_sh, c_ss, step, fixed_len, scale, (__nv_bfloat16*)out, out_ld, H,
+        total);
   YMT3_CUDA_CHECK(cudaGetLastError());
   return YMT3_OK;
 }

@@ -223,6 +223,19 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p, int G, in
       *reinterpret_cast<float4*>(Vs + j * DK + d) = make_float4(vv[0], vv[1], vv[2], vv[3]);
     }
   }
+  const int half = p.rope_dim >> 1;
+  if (half > 0) {   // uniform for the whole grid
+    __syncthreads();
+    if (live) {
+      for (int idx = r; idx < kv_len * half; idx += G) {
+        const int j = idx / half, i = idx - j * half;
+        const float c = p.rope_cos[j * half + i], sn = p.rope_sin[j * half + i];
+        const float x1 = Ks[j * DK + i], x2 = Ks[j * DK + i + half];
+        Ks[j * DK + i] = x1 * c - x2 * sn;
+        Ks[j * DK + i + half] = x2 * c + x1 * sn;
+      }
+    }
+  }
   __syncthreads();
   if (!live || r >= p.Sq) return;
   float q[DK], o[DK];
@@ -232,6 +245,17 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p, int G, in
     load4<T>(Q + (int64_t)r * p.q_ss + d, t);
     q[d] = t[0] * p.scale; q[d + 1] = t[1] * p.scale; q[d + 2] = t[2] * p.scale; q[d + 3] = t[3] * p.scale;
     o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
+  }
+  if (half > 0) {
+#pragma unroll
+    for (int i = 0; i < DK / 2; ++i) {
+      if (i < half) {
+        const float c = p.rope_cos[r * half + i], sn = p.rope_sin[r * half + i];
+        const float x1 = q[i], x2 = q[i + half];
+        q[i] = x1 * c - x2 * sn;
+        q[i + half] = x2 * c + x1 * sn;
+      }
+    }
   }
   float m = -INFINITY, l = 0.f;
   const int jmax = p.causal ? min(kv_len, r + (p.Sk - p.Sq) + 1) : kv_len;
@@ -283,6 +307,7 @@ static int launch_attn(const AttnParams& p, cudaStream_t stream) {
     YMT3_CUDA_CHECK(cudaGetLastError());
     return YMT3_OK;
   }
+  YMT3_REQUIRE(p.rope_dim == 0, "attention: fused RoPE is only available in the tiny-sequence kernel");
   const int nq = ymt3_div_up(p.Sq, 16);
   const int64_t blocks = (int64_t)p.B * p.H * nq;
   YMT3_REQUIRE(blocks < (1ll << 31), "attention: grid too large");

@@ -21,7 +21,8 @@ template <> __device__ __forceinline__ __nv_bfloat16 cv_from_f<__nv_bfloat16>(fl
 // Block 0, conv1 (Cin = 1):  a = relu(bn1(x)) with zero padding AFTER the activation;
 //   act_out[p, c]  = relu(sum_tap w1[c, tap] * a[p + tap] + t2[c])      (w1 already scaled by bn2)
 //   sc_out[p, c]   = wsc[c] * x[p] + bsc[c]                             (1x1 shortcut on the raw input)
-// One thread = one pixel x 8 output channels.
+// One thread = 4 consecutive pixels (along f) x 8 output channels: the 72 weights of its channel group are
+// loaded once and reused for 4 pixels; the 3 x 6 input patch is shared by the 4 pixels; 16-byte stores.
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv3x3_first_kernel(const float* __restrict__ x, int Tn, int Fn, int C, float s1, float t1,
@@ -31,36 +32,73 @@ conv3x3_first_kernel(const float* __restrict__ x, int Tn, int Fn, int C, float s
   if (gid >= total) return;
   const int groups = C / 8;
   const int cg = (int)(gid % groups);
-  const int64_t pix = gid / groups;
-  const int f = (int)(pix % Fn);
-  const int64_t bt = pix / Fn;
+  const int64_t quad = gid / groups;           // index of the 4-pixel group
+  const int fq = Fn / 4;
+  const int f0 = (int)(quad % fq) * 4;
+  const int64_t bt = quad / fq;
   const int t = (int)(bt % Tn);
-  float a[9];
+  const int64_t pix0 = bt * Fn + f0;
+  float a[3][6], xc[4];
 #pragma unroll
   for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int tt = t + dy, ff = f + dx;
+    for (int dx = -1; dx <= 4; ++dx) {
+      const int tt = t + dy, ff = f0 + dx;
       float v = 0.f;
-      if (tt >= 0 && tt < Tn && ff >= 0 && ff < Fn) v = fmaxf(fmaf(x[pix + (int64_t)dy * Fn + dx], s1, t1), 0.f);
-      a[(dy + 1) * 3 + dx + 1] = v;
+      if (tt >= 0 && tt < Tn && ff >= 0 && ff < Fn) {
+        const float raw = x[pix0 + (int64_t)dy * Fn + dx];
+        if (dy == 0 && dx >= 0 && dx < 4) xc[dx] = raw;
+        v = fmaxf(fmaf(raw, s1, t1), 0.f);
+      }
+      a[dy + 1][dx + 1] = v;
     }
-  const float xc = x[pix];
+  float accv[4][8], scv[4][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
-    float acc = t2[c];
+    float w[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc = fmaf(w1[c * 9 + k], a[k], acc);
-    act_out[pix * C + c] = cv_from_f<T>(fmaxf(acc, 0.f));
-    sc_out[pix * C + c] = cv_from_f<T>(fmaf(wsc[c], xc, bsc[c]));
+    for (int k = 0; k < 9; ++k) w[k] = w1[c * 9 + k];
+    const float tb = t2[c], ws = wsc[c], bs = bsc[c];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float acc = tb;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc = fmaf(w[ky * 3 + kx], a[ky][p + kx], acc);
+      accv[p][j] = fmaxf(acc, 0.f);
+      scv[p][j] = fmaf(ws, xc[p], bs);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    T* ao = act_out + (pix0 + p) * C + cg * 8;
+    T* so = sc_out + (pix0 + p) * C + cg * 8;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(ao) = make_float4(accv[p][0], accv[p][1], accv[p][2], accv[p][3]);
+      *reinterpret_cast<float4*>(ao + 4) = make_float4(accv[p][4], accv[p][5], accv[p][6], accv[p][7]);
+      *reinterpret_cast<float4*>(so) = make_float4(scv[p][0], scv[p][1], scv[p][2], scv[p][3]);
+      *reinterpret_cast<float4*>(so + 4) = make_float4(scv[p][4], scv[p][5], scv[p][6], scv[p][7]);
+    } else {
+      uint4 pa, ps;
+      __nv_bfloat162* ha = reinterpret_cast<__nv_bfloat162*>(&pa);
+      __nv_bfloat162* hs = reinterpret_cast<__nv_bfloat162*>(&ps);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ha[q] = __floats2bfloat162_rn(accv[p][2 * q], accv[p][2 * q + 1]);
+        hs[q] = __floats2bfloat162_rn(scv[p][2 * q], scv[p][2 * q + 1]);
+      }
+      *reinterpret_cast<uint4*>(ao) = pa;
+      *reinterpret_cast<uint4*>(so) = ps;
+    }
   }
 }
 
 int conv3x3_first(const float* x, int B, int Tn, int Fn, int C, float s1, float t1, const float* w1, const float* t2,
                   const float* wsc, const float* bsc, void* act_out, void* sc_out, int dtype, cudaStream_t stream) {
-  YMT3_REQUIRE(C % 8 == 0, "conv3x3_first: C must be a multiple of 8");
-  const int64_t total = (int64_t)B * Tn * Fn * (C / 8);
+  YMT3_REQUIRE(C % 8 == 0 && Fn % 4 == 0, "conv3x3_first: C must be a multiple of 8 and F a multiple of 4");
+  const int64_t total = (int64_t)B * Tn * (Fn / 4) * (C / 8);
   if (total <= 0) return YMT3_OK;
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (dtype == YMT3_F32)
@@ -74,24 +112,72 @@ int conv3x3_first(const float* x, int B, int Tn, int Fn, int C, float s1, float 
 }
 
 // out[b,t,f2,c] = 0.5 * (h[b,t,2*f2,c] + h[b,t,2*f2+1,c]);  act[...] = relu(out * s[c] + t[c]) (optional)
+// 16 bytes (4 fp32 / 8 bf16 channels) per thread.
 template <typename T>
 __global__ void __launch_bounds__(256)
 pool_bnrelu_kernel(const T* __restrict__ h, T* __restrict__ out, T* __restrict__ act, const float* __restrict__ s,
                    const float* __restrict__ t, int C, int64_t total) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;   // index into out: (rows/2, C)
+  constexpr int V = 16 / sizeof(T);
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V;   // index into out: (rows/2, C)
   if (i >= total) return;
   const int c = (int)(i % C);
   const int64_t r2 = i / C;
-  const float v = 0.5f * (cv_to_f(h[(2 * r2) * C + c]) + cv_to_f(h[(2 * r2 + 1) * C + c]));
-  out[i] = cv_from_f<T>(v);
-  if (act) act[i] = cv_from_f<T>(fmaxf(fmaf(v, s[c], t[c]), 0.f));
+  const uint4 u0 = *reinterpret_cast<const uint4*>(h + (2 * r2) * C + c);
+  const uint4 u1 = *reinterpret_cast<const uint4*>(h + (2 * r2 + 1) * C + c);
+  float v[V];
+  if constexpr (sizeof(T) == 4) {
+    const float *a = reinterpret_cast<const float*>(&u0), *b = reinterpret_cast<const float*>(&u1);
+#pragma unroll
+    for (int q = 0; q < V; ++q) v[q] = 0.5f * (a[q] + b[q]);
+  } else {
+    const __nv_bfloat162 *a = reinterpret_cast<const __nv_bfloat162*>(&u0), *b = reinterpret_cast<const __nv_bfloat162*>(&u1);
+#pragma unroll
+    for (int q = 0; q < V / 2; ++q) {
+      v[2 * q] = 0.5f * (__bfloat162float(a[q].x) + __bfloat162float(b[q].x));
+      v[2 * q + 1] = 0.5f * (__bfloat162float(a[q].y) + __bfloat162float(b[q].y));
+    }
+  }
+  auto pack = [&](const float (&f)[V]) {
+    uint4 o;
+    if constexpr (sizeof(T) == 4) {
+      float* p = reinterpret_cast<float*>(&o);
+#pragma unroll
+      for (int q = 0; q < V; ++q) p[q] = f[q];
+    } else {
+      __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int q = 0; q < V / 2; ++q) p[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+    }
+    return o;
+  };
+  // the activated copy is computed from the value as STORED (rounded to T), like the reference that applies
+  // bn+relu to the materialised tensor
+  const uint4 ov = pack(v);
+  *reinterpret_cast<uint4*>(out + i) = ov;
+  if (act) {
+    float w[V];
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int q = 0; q < V; ++q) w[q] = fmaxf(fmaf(v[q], s[c + q], t[c + q]), 0.f);
+    } else {
+      const __nv_bfloat162* r = reinterpret_cast<const __nv_bfloat162*>(&ov);
+#pragma unroll
+      for (int q = 0; q < V / 2; ++q) {
+        w[2 * q] = fmaxf(fmaf(__bfloat162float(r[q].x), s[c + 2 * q], t[c + 2 * q]), 0.f);
+        w[2 * q + 1] = fmaxf(fmaf(__bfloat162float(r[q].y), s[c + 2 * q + 1], t[c + 2 * q + 1]), 0.f);
+      }
+    }
+    *reinterpret_cast<uint4*>(act + i) = pack(w);
+  }
 }
 
 int pool_bnrelu(const void* h, void* out, void* act, const float* s, const float* t, int64_t rows_in, int C, int dtype,
                 cudaStream_t stream) {
   const int64_t total = rows_in / 2 * C;
   if (total <= 0) return YMT3_OK;
-  const unsigned grid = (unsigned)((total + 255) / 256);
+  YMT3_REQUIRE(C % 8 == 0, "pool_bnrelu: C must be a multiple of 8");
+  const int64_t vec = dtype == YMT3_F32 ? 4 : 8;
+  const unsigned grid = (unsigned)((total / vec + 255) / 256);
   if (dtype == YMT3_F32)
     pool_bnrelu_kernel<float><<<grid, 256, 0, stream>>>((const float*)h, (float*)out, (float*)act, s, t, C, total);
   else

@@ -16,33 +16,39 @@ template <typename T> __device__ __forceinline__ float moe_to_f(T v);
 template <> __device__ __forceinline__ float moe_to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float moe_to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// 8 warps x 8 tokens per block; E <= 32, topk <= 4. Expert counts are aggregated in shared memory so
-// that only E global atomics are issued per 64 tokens.
+// 8 warps x 8 tokens per block; E <= 8 * EG experts, topk <= 4. Router weights live in REGISTERS (lane holds
+// Wg[e][lane + 32 i]), the token row is read once; expert counts are aggregated in shared memory so that only E
+// global atomics are issued per 64 tokens.
 #define MOE_TOK_PER_BLOCK 64
-template <typename T>
+template <typename T, int NV, int EMAX>   // NV = D / 32 values per lane, EMAX >= E
 __global__ void __launch_bounds__(256)
 moe_route_kernel(const T* __restrict__ x, const float* __restrict__ Wg, int N, int D, int E, int topk,
                  int* __restrict__ top_idx, float* __restrict__ top_w, int* __restrict__ counts) {
   __shared__ int hist[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < 32) hist[threadIdx.x] = 0;
+  float wg[EMAX][NV];
+#pragma unroll
+  for (int e = 0; e < EMAX; ++e)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) wg[e][i] = e < E ? Wg[e * D + i * 32 + lane] : 0.f;
   __syncthreads();
   for (int it = 0; it < MOE_TOK_PER_BLOCK / 8; ++it) {
     const int tok = blockIdx.x * MOE_TOK_PER_BLOCK + it * 8 + warp;
     if (tok >= N) break;
     const T* xr = x + (int64_t)tok * D;
-    float my_logit = -INFINITY;  // lane e holds logit e
-    float xv[16];                // token row cached in registers (D <= 512)
+    float xv[NV];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) xv[i] = (i * 32 + lane < D) ? moe_to_f(xr[i * 32 + lane]) : 0.f;
-    for (int e = 0; e < E; ++e) {
+    for (int i = 0; i < NV; ++i) xv[i] = moe_to_f(xr[i * 32 + lane]);
+    float my_logit = -INFINITY;  // lane e holds logit e
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
       float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i * 32 < D) acc = fmaf(xv[i], (i * 32 + lane < D) ? Wg[e * D + i * 32 + lane] : 0.f, acc);
+      for (int i = 0; i < NV; ++i) acc = fmaf(xv[i], wg[e][i], acc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == e) my_logit = acc;
+      if (lane == e && e < E) my_logit = acc;
     }
     float mx = my_logit;
 #pragma unroll
@@ -84,6 +90,26 @@ moe_route_kernel(const T* __restrict__ x, const float* __restrict__ Wg, int N, i
   }
   __syncthreads();
   if (threadIdx.x < E && hist[threadIdx.x]) atomicAdd(counts + threadIdx.x, hist[threadIdx.x]);
+}
+
+template <typename T>
+static int launch_route(const T* x, const float* Wg, int N, int D, int E, int topk, int* top_idx, float* top_w, int* counts,
+                        cudaStream_t s) {
+  const unsigned gt = (unsigned)ymt3_div_up(N, MOE_TOK_PER_BLOCK);
+#define ROUTE(NV, EM) moe_route_kernel<T, NV, EM><<<gt, 256, 0, s>>>(x, Wg, N, D, E, topk, top_idx, top_w, counts)
+  if (E <= 8) {
+    if (D == 128) ROUTE(4, 8); else if (D == 256) ROUTE(8, 8); else if (D == 512) ROUTE(16, 8); else if (D == 64) ROUTE(2, 8);
+    else { ymt3_set_error("moe: d_model must be 64/128/256/512 (got %d)", D); return YMT3_ERR_UNSUPPORTED; }
+  } else if (E <= 16) {
+    if (D == 128) ROUTE(4, 16); else if (D == 256) ROUTE(8, 16); else if (D == 512) ROUTE(16, 16); else if (D == 64) ROUTE(2, 16);
+    else { ymt3_set_error("moe: d_model must be 64/128/256/512 (got %d)", D); return YMT3_ERR_UNSUPPORTED; }
+  } else {
+    ymt3_set_error("moe: at most 16 experts are supported by the fused router (got %d)", E);
+    return YMT3_ERR_UNSUPPORTED;
+  }
+#undef ROUTE
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
 }
 
 // offsets[0..E] = exclusive scan of counts; cursor[e] = 0
@@ -138,17 +164,48 @@ moe_scatter_kernel(const T* __restrict__ x, int N, int D, int topk, const int* _
   }
 }
 
-// out[tok, :] = residual[tok, :] + sum_k ys[tok_slot[tok, k], :]
+// out[tok, :] = residual[tok, :] + sum_k ys[tok_slot[tok, k], :]     (4 fp32 / 8 bf16 elements per thread)
 template <typename T>
 __global__ void __launch_bounds__(256)
 moe_combine_kernel(const T* __restrict__ ys, const int* __restrict__ tok_slot, const T* __restrict__ residual,
                    T* __restrict__ out, int N, int D, int topk) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  constexpr int V = 16 / sizeof(T);
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V;
   if (i >= (int64_t)N * D) return;
   const int tok = (int)(i / D), d = (int)(i % D);
-  float acc = residual ? moe_to_f(residual[i]) : 0.f;
-  for (int k = 0; k < topk; ++k) acc += moe_to_f(ys[(int64_t)tok_slot[tok * topk + k] * D + d]);
-  if constexpr (sizeof(T) == 4) out[i] = acc; else out[i] = __float2bfloat16(acc);
+  float acc[V];
+  auto add = [&](const T* p, bool init) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    if constexpr (sizeof(T) == 4) {
+      const float* f = reinterpret_cast<const float*>(&u);
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] = init ? f[q] : acc[q] + f[q];
+    } else {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < V / 2; ++q) {
+        acc[2 * q] = (init ? 0.f : acc[2 * q]) + __bfloat162float(h[q].x);
+        acc[2 * q + 1] = (init ? 0.f : acc[2 * q + 1]) + __bfloat162float(h[q].y);
+      }
+    }
+  };
+  if (residual) add(residual + i, true);
+  else {
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = 0.f;
+  }
+  for (int k = 0; k < topk; ++k) add(ys + (int64_t)tok_slot[tok * topk + k] * D + d, false);
+  uint4 o;
+  if constexpr (sizeof(T) == 4) {
+    float* f = reinterpret_cast<float*>(&o);
+#pragma unroll
+    for (int q = 0; q < V; ++q) f[q] = acc[q];
+  } else {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < V / 2; ++q) h[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+  }
+  *reinterpret_cast<uint4*>(out + i) = o;
 }
 
 size_t moe_workspace_bytes(int64_t N, int D, int I, int E, int topk, int dtype) {
@@ -168,7 +225,7 @@ size_t moe_workspace_bytes(int64_t N, int D, int I, int E, int topk, int dtype) 
 int moe_forward(int precision, const void* x, const void* residual, void* out, int64_t N64, const MoEWeights& w,
                 void* workspace, cudaStream_t s) {
   if (N64 <= 0) return YMT3_OK;
-  YMT3_REQUIRE(w.E >= 1 && w.E <= 32 && w.topk >= 1 && w.topk <= 4 && w.topk <= w.E, "moe: bad E/topk");
+  YMT3_REQUIRE(w.E >= 1 && w.E <= 16 && w.topk >= 1 && w.topk <= 4 && w.topk <= w.E, "moe: bad E/topk");
   YMT3_REQUIRE(w.D <= 512, "moe: router supports d_model <= 512 (got %d)", w.D);
   YMT3_REQUIRE(N64 * w.topk < (1ll << 31), "moe: too many tokens");
   const int N = (int)N64, D = w.D, I = w.I, E = w.E, topk = w.topk;
@@ -189,12 +246,12 @@ int moe_forward(int precision, const void* x, const void* residual, void* out, i
   YMT3_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)E * 4, s));
   const unsigned gt = (unsigned)ymt3_div_up(N, MOE_TOK_PER_BLOCK), gs = gt;
   if (precision == YMT3_F32) {
-    moe_route_kernel<float><<<gt, 256, 0, s>>>((const float*)x, w.gate, N, D, E, topk, top_idx, top_w, counts);
+    if (int rr = launch_route<float>((const float*)x, w.gate, N, D, E, topk, top_idx, top_w, counts, s)) return rr;
     moe_offsets_kernel<<<1, 32, 0, s>>>(counts, offsets, cursor, E);
     moe_scatter_kernel<float><<<gs, 256, 0, s>>>((const float*)x, N, D, topk, top_idx, top_w, offsets, cursor,
                                                  (float*)xs, slot_w, tok_slot);
   } else {
-    moe_route_kernel<__nv_bfloat16><<<gt, 256, 0, s>>>((const __nv_bfloat16*)x, w.gate, N, D, E, topk, top_idx, top_w, counts);
+    if (int rr = launch_route<__nv_bfloat16>((const __nv_bfloat16*)x, w.gate, N, D, E, topk, top_idx, top_w, counts, s)) return rr;
     moe_offsets_kernel<<<1, 32, 0, s>>>(counts, offsets, cursor, E);
     moe_scatter_kernel<__nv_bfloat16><<<gs, 256, 0, s>>>((const __nv_bfloat16*)x, N, D, topk, top_idx, top_w, offsets,
                                                          cursor, (__nv_bfloat16*)xs, slot_w, tok_slot);
@@ -214,7 +271,9 @@ int moe_forward(int precision, const void* x, const void* residual, void* out, i
   h.group_offsets = offsets; h.num_groups = E; h.strideW = (int64_t)D * I;
   rc = precision == YMT3_F32 ? gemm_f32(h, s) : gemm_bf16_tc(h, precision, s);
   if (rc) return rc;
-  const unsigned gc = (unsigned)(((int64_t)N * D + 255) / 256);
+  YMT3_REQUIRE(D % 8 == 0, "moe: d_model must be a multiple of 8");
+  const int64_t vec = 16 / (int64_t)es;
+  const unsigned gc = (unsigned)(((int64_t)N * D / vec + 255) / 256);
   if (precision == YMT3_F32)
     moe_combine_kernel<float><<<gc, 256, 0, s>>>((const float*)ys, tok_slot, (const float*)residual, (float*)out, N, D, topk);
   else

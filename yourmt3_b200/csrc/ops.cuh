@@ -78,6 +78,9 @@ struct AttnParams {
   int inner;
   int64_t q_sb2, k_sb2, v_sb2, o_sb2;
   float scale;
+  // optional rotate-half RoPE applied to q and k on load (tiny-sequence kernel only): rot dims per head,
+  // position = index along the attention sequence; tables (n_pos, rot/2) fp32
+  const float* rope_cos; const float* rope_sin; int rope_dim;
   int causal;        // key j allowed iff j <= i + (Sk - Sq)
   const int* kv_len; // optional per-batch valid key count (device), else Sk
 };

@@ -57,11 +57,107 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
     yr[i] = from_f<T>((to_f(xr[i]) - mean) * inv * w[i] + (b ? b[i] : 0.f));
 }
 
+// Vectorised norms: one warp per row, 16-byte loads, the row stays in registers between the statistics pass and
+// the write (dim <= 32 lanes * 4 vectors * (4 fp32 | 8 bf16)).  RMS = false -> LayerNorm (two-pass variance).
+template <typename T, bool RMS>
+__global__ void __launch_bounds__(256) norm_vec_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ b, T* __restrict__ y, int64_t rows,
+                                                       int dim, float eps) {
+  constexpr int V = 16 / sizeof(T), MAXV = 4;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* xr = x + row * dim;
+  float v[MAXV][V];
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = (k * 32 + lane) * V;
+    if (i < dim) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + i);
+      if constexpr (sizeof(T) == 4) {
+        const float* f = reinterpret_cast<const float*>(&u);
+#pragma unroll
+        for (int q = 0; q < V; ++q) v[k][q] = f[q];
+      } else {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int q = 0; q < V / 2; ++q) {
+          v[k][2 * q] = __bfloat162float(h[q].x);
+          v[k][2 * q + 1] = __bfloat162float(h[q].y);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        s += v[k][q];
+        ss = fmaf(v[k][q], v[k][q], ss);
+      }
+    }
+  }
+  float mean = 0.f, inv;
+  if constexpr (RMS) {
+    inv = rsqrtf(warp_sum(ss) / (float)dim + eps);
+  } else {
+    mean = warp_sum(s) / (float)dim;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int i = (k * 32 + lane) * V;
+      if (i < dim) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          const float d = v[k][q] - mean;
+          sq = fmaf(d, d, sq);
+        }
+      }
+    }
+    inv = rsqrtf(warp_sum(sq) / (float)dim + eps);
+  }
+  T* yr = y + row * dim;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = (k * 32 + lane) * V;
+    if (i < dim) {
+      float o[V];
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        if constexpr (RMS) o[q] = w[i + q] * (v[k][q] * inv);
+        else o[q] = (v[k][q] - mean) * inv * w[i + q] + (b ? b[i + q] : 0.f);
+      }
+      uint4 u;
+      if constexpr (sizeof(T) == 4) {
+        float* f = reinterpret_cast<float*>(&u);
+#pragma unroll
+        for (int q = 0; q < V; ++q) f[q] = o[q];
+      } else {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int q = 0; q < V / 2; ++q) h[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
+      }
+      *reinterpret_cast<uint4*>(yr + i) = u;
+    }
+  }
+}
+
+static bool norm_vec_ok(const void* x, const void* y, int dim, int dtype) {
+  const int V = dtype == YMT3_F32 ? 4 : 8;
+  return dim % V == 0 && dim <= 32 * 4 * V && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+}
+
 int rmsnorm(const void* x, const float* w, void* y, int64_t rows, int dim, float eps, int dtype,
             cudaStream_t stream) {
   if (rows <= 0) return YMT3_OK;
   YMT3_REQUIRE(x && w && y && dim > 0, "rmsnorm: bad argument");
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (norm_vec_ok(x, y, dim, dtype)) {
+    if (dtype == YMT3_F32)
+      norm_vec_kernel<float, true><<<grid, 256, 0, stream>>>((const float*)x, w, nullptr, (float*)y, rows, dim, eps);
+    else
+      norm_vec_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, w, nullptr,
+                                                                     (__nv_bfloat16*)y, rows, dim, eps);
+    YMT3_CUDA_CHECK(cudaGetLastError());
+    return YMT3_OK;
+  }
   if (dtype == YMT3_F32)
     rmsnorm_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, w, (float*)y, rows, dim, eps);
   else
@@ -76,6 +172,15 @@ int layernorm(const void* x, const float* w, const float* b, void* y, int64_t ro
   if (rows <= 0) return YMT3_OK;
   YMT3_REQUIRE(x && w && y && dim > 0, "layernorm: bad argument");
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (norm_vec_ok(x, y, dim, dtype)) {
+    if (dtype == YMT3_F32)
+      norm_vec_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)x, w, b, (float*)y, rows, dim, eps);
+    else
+      norm_vec_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, w, b, (__nv_bfloat16*)y,
+                                                                      rows, dim, eps);
+    YMT3_CUDA_CHECK(cudaGetLastError());
+    return YMT3_OK;
+  }
   if (dtype == YMT3_F32)
     layernorm_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, w, b, (float*)y, rows, dim, eps);
   else

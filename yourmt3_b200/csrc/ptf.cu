@@ -224,10 +224,18 @@ int layer_fwd(ymt3_ptf* h, const PLayer& L, int mode, const void* x_kv, int64_t 
     if (c.pos_type == 2) {
       const float* ct = mode == 1 ? h->rope_cos_k : h->rope_cos_t;
       const float* st = mode == 1 ? h->rope_sin_k : h->rope_sin_t;
-      const int64_t div = mode == 1 ? 1 : K;
-      const int mod = mode == 1 ? K : (int)T;
-      // q heads then k heads are contiguous in the first 2*D columns: treat them as 2*H heads
-      if ((rc = rope_inplace(h->qkvb, rows, 3 * D, 0, 2 * H, dh, c.rope_dim, div, mod, ct, st, dt, s))) return rc;
+      const int S = mode == 1 ? K : (int)T;
+      // fused into the tiny-sequence attention kernel (rotation applied while K is staged in shared memory and
+      // q sits in registers) when that kernel is applicable; otherwise a separate in-place pass
+      const int G = S <= 32 ? 32 : (S <= 64 ? 64 : 128);
+      const bool small_ok = (dh == 16 || dh == 32) && S <= 128 && (size_t)(128 / G) * 2 * S * dh * 4 <= 48 * 1024;
+      if (small_ok) {
+        a.rope_cos = ct; a.rope_sin = st; a.rope_dim = c.rope_dim;
+      } else {
+        const int64_t div = mode == 1 ? 1 : K;
+        // q heads then k heads are contiguous in the first 2*D columns: treat them as 2*H heads
+        if ((rc = rope_inplace(h->qkvb, rows, 3 * D, 0, 2 * H, dh, c.rope_dim, div, S, ct, st, dt, s))) return rc;
+      }
     }
     a.Q = h->qkvb; a.K = (char*)h->qkvb + (size_t)D * es; a.V = (char*)h->qkvb + (size_t)2 * D * es;
     a.q_sh = a.k_sh = a.v_sh = dh; a.o_sh = dh;

@@ -16,75 +16,97 @@ template <typename T> __device__ __forceinline__ float moe_to_f(T v);
 template <> __device__ __forceinline__ float moe_to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float moe_to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// 8 warps x 8 tokens per block; E <= 8 * EG experts, topk <= 4. Router weights live in REGISTERS (lane holds
-// Wg[e][lane + 32 i]), the token row is read once; expert counts are aggregated in shared memory so that only E
-// global atomics are issued per 64 tokens.
-#define MOE_TOK_PER_BLOCK 64
-template <typename T, int NV, int EMAX>   // NV = D / 32 values per lane, EMAX >= E
+// Router: ONE THREAD per token (256 tokens per block).  Router weights (E x D fp32) are staged in shared
+// memory and read as broadcast float4; the token row is streamed with 16-byte loads; logits, fp32 softmax, top-k
+// and renormalisation happen in registers (no shuffles); expert counts are aggregated in shared memory so that
+// only E global atomics are issued per block.
+#define MOE_TOK_PER_BLOCK 64      // tokens per block of the SCATTER kernel
+#define MOE_ROUTE_TOK 256         // tokens per block of the ROUTE kernel
+template <typename T, int EMAX>
 __global__ void __launch_bounds__(256)
 moe_route_kernel(const T* __restrict__ x, const float* __restrict__ Wg, int N, int D, int E, int topk,
                  int* __restrict__ top_idx, float* __restrict__ top_w, int* __restrict__ counts) {
+  extern __shared__ __align__(16) float wg_s[];   // [E][D]
   __shared__ int hist[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < 32) hist[threadIdx.x] = 0;
-  float wg[EMAX][NV];
-#pragma unroll
-  for (int e = 0; e < EMAX; ++e)
-#pragma unroll
-    for (int i = 0; i < NV; ++i) wg[e][i] = e < E ? Wg[e * D + i * 32 + lane] : 0.f;
+  for (int i = threadIdx.x; i < E * D; i += 256) wg_s[i] = Wg[i];
   __syncthreads();
-  for (int it = 0; it < MOE_TOK_PER_BLOCK / 8; ++it) {
-    const int tok = blockIdx.x * MOE_TOK_PER_BLOCK + it * 8 + warp;
-    if (tok >= N) break;
+  const int tok = blockIdx.x * MOE_ROUTE_TOK + threadIdx.x;
+  if (tok < N) {
     const T* xr = x + (int64_t)tok * D;
-    float xv[NV];
+    float logit[EMAX];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) xv[i] = moe_to_f(xr[i * 32 + lane]);
-    float my_logit = -INFINITY;  // lane e holds logit e
+    for (int e = 0; e < EMAX; ++e) logit[e] = 0.f;
+    constexpr int V = 16 / sizeof(T);
+    for (int d = 0; d < D; d += V) {
+      float xv[V];
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + d);
+      if constexpr (sizeof(T) == 4) {
+        const float* f = reinterpret_cast<const float*>(&u);
 #pragma unroll
-    for (int e = 0; e < EMAX; ++e) {
-      float acc = 0.f;
+        for (int q = 0; q < V; ++q) xv[q] = f[q];
+      } else {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) acc = fmaf(xv[i], wg[e][i], acc);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == e && e < E) my_logit = acc;
-    }
-    float mx = my_logit;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float p = lane < E ? expf(my_logit - mx) : 0.f;
-    float sum = p;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    p /= sum;
-    // top-k by repeated arg-max (ties -> lowest expert index)
-    float sel_w[4];
-    int sel_i[4];
-    float wsum = 0.f;
-    float cur = lane < E ? p : -1.f;
-    for (int k = 0; k < topk; ++k) {
-      float bv = cur;
-      int bi = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) {
-          bv = ov;
-          bi = oi;
+        for (int q = 0; q < V / 2; ++q) {
+          xv[2 * q] = __bfloat162float(h[q].x);
+          xv[2 * q + 1] = __bfloat162float(h[q].y);
         }
       }
-      sel_w[k] = bv;
-      sel_i[k] = bi;
-      wsum += bv;
-      if (lane == bi) cur = -1.f;
+#pragma unroll
+      for (int e = 0; e < EMAX; ++e) {
+        if (e < E) {
+#pragma unroll
+          for (int q = 0; q < V; q += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(wg_s + e * D + d + q);
+            logit[e] = fmaf(xv[q], wv.x, logit[e]);
+            logit[e] = fmaf(xv[q + 1], wv.y, logit[e]);
+            logit[e] = fmaf(xv[q + 2], wv.z, logit[e]);
+            logit[e] = fmaf(xv[q + 3], wv.w, logit[e]);
+          }
+        }
+      }
     }
-    if (lane == 0) {
-      for (int k = 0; k < topk; ++k) {
-        top_idx[tok * topk + k] = sel_i[k];
-        top_w[tok * topk + k] = sel_w[k] / wsum;
-        atomicAdd(&hist[sel_i[k]], 1);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e)
+      if (e < E) mx = fmaxf(mx, logit[e]);
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      logit[e] = e < E ? expf(logit[e] - mx) : -1.f;
+      if (e < E) sum += logit[e];
+    }
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e)
+      if (e < E) logit[e] /= sum;
+    float wsum = 0.f, sw[4];
+    int si[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < topk) {
+        float bv = -1.f;
+        int bi = 0;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e)
+          if (e < E && logit[e] > bv) {   // strict '>' keeps the lowest index on ties
+            bv = logit[e];
+            bi = e;
+          }
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e)
+          if (e == bi) logit[e] = -2.f;
+        sw[k] = bv;
+        si[k] = bi;
+        wsum += bv;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < topk) {
+        top_idx[tok * topk + k] = si[k];
+        top_w[tok * topk + k] = sw[k] / wsum;
+        atomicAdd(&hist[si[k]], 1);
       }
     }
   }
@@ -95,19 +117,11 @@ moe_route_kernel(const T* __restrict__ x, const float* __restrict__ Wg, int N, i
 template <typename T>
 static int launch_route(const T* x, const float* Wg, int N, int D, int E, int topk, int* top_idx, float* top_w, int* counts,
                         cudaStream_t s) {
-  const unsigned gt = (unsigned)ymt3_div_up(N, MOE_TOK_PER_BLOCK);
-#define ROUTE(NV, EM) moe_route_kernel<T, NV, EM><<<gt, 256, 0, s>>>(x, Wg, N, D, E, topk, top_idx, top_w, counts)
-  if (E <= 8) {
-    if (D == 128) ROUTE(4, 8); else if (D == 256) ROUTE(8, 8); else if (D == 512) ROUTE(16, 8); else if (D == 64) ROUTE(2, 8);
-    else { ymt3_set_error("moe: d_model must be 64/128/256/512 (got %d)", D); return YMT3_ERR_UNSUPPORTED; }
-  } else if (E <= 16) {
-    if (D == 128) ROUTE(4, 16); else if (D == 256) ROUTE(8, 16); else if (D == 512) ROUTE(16, 16); else if (D == 64) ROUTE(2, 16);
-    else { ymt3_set_error("moe: d_model must be 64/128/256/512 (got %d)", D); return YMT3_ERR_UNSUPPORTED; }
-  } else {
-    ymt3_set_error("moe: at most 16 experts are supported by the fused router (got %d)", E);
-    return YMT3_ERR_UNSUPPORTED;
-  }
-#undef ROUTE
+  const unsigned gt = (unsigned)ymt3_div_up(N, MOE_ROUTE_TOK);
+  const size_t smem = (size_t)E * D * sizeof(float);
+  YMT3_REQUIRE(smem <= 40 * 1024 && D % 8 == 0, "moe: router weights (E*D fp32) must fit 40 KB and D %% 8 == 0");
+  if (E <= 8) moe_route_kernel<T, 8><<<gt, 256, smem, s>>>(x, Wg, N, D, E, topk, top_idx, top_w, counts);
+  else moe_route_kernel<T, 16><<<gt, 256, smem, s>>>(x, Wg, N, D, E, topk, top_idx, top_w, counts);
   YMT3_CUDA_CHECK(cudaGetLastError());
   return YMT3_OK;
 }
@@ -244,7 +258,7 @@ int moe_forward(int precision, const void* x, const void* residual, void* out, i
   int* offsets = counts + E;
   int* cursor = offsets + E + 1;
   YMT3_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)E * 4, s));
-  const unsigned gt = (unsigned)ymt3_div_up(N, MOE_TOK_PER_BLOCK), gs = gt;
+  const unsigned gs = (unsigned)ymt3_div_up(N, MOE_TOK_PER_BLOCK);
   if (precision == YMT3_F32) {
     if (int rr = launch_route<float>((const float*)x, w.gate, N, D, E, topk, top_idx, top_w, counts, s)) return rr;
     moe_offsets_kernel<<<1, 32, 0, s>>>(counts, offsets, cursor, E);

@@ -57,23 +57,25 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
     yr[i] = from_f<T>((to_f(xr[i]) - mean) * inv * w[i] + (b ? b[i] : 0.f));
 }
 
-// Vectorised norms: one warp per row, 16-byte loads, the row stays in registers between the statistics pass and
-// the write (dim <= 32 lanes * 4 vectors * (4 fp32 | 8 bf16)).  RMS = false -> LayerNorm (two-pass variance).
-template <typename T, bool RMS>
+// Vectorised norms, 16-byte loads, the row stays in registers between the statistics pass and the write.
+// LPR = lanes per row (power of two <= 32): narrow rows (dim = 128 bf16 -> 16 lanes) pack 32/LPR rows into a warp;
+// wide rows use the whole warp with up to MAXV vectors per lane.  RMS = false -> LayerNorm (two-pass variance).
+template <typename T, bool RMS, int LPR, int MAXV>
 __global__ void __launch_bounds__(256) norm_vec_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ b, T* __restrict__ y, int64_t rows,
                                                        int dim, float eps) {
-  constexpr int V = 16 / sizeof(T), MAXV = 4;
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  constexpr int V = 16 / sizeof(T), RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const T* xr = x + row * dim;
+  const int sub = lane % LPR;
+  const int64_t row = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool live = row < rows;
+  const T* xr = x + (live ? row : 0) * dim;
   float v[MAXV][V];
   float s = 0.f, ss = 0.f;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
-    const int i = (k * 32 + lane) * V;
-    if (i < dim) {
+    const int i = (k * LPR + sub) * V;
+    if (live && i < dim) {
       const uint4 u = *reinterpret_cast<const uint4*>(xr + i);
       if constexpr (sizeof(T) == 4) {
         const float* f = reinterpret_cast<const float*>(&u);
@@ -94,16 +96,21 @@ __global__ void __launch_bounds__(256) norm_vec_kernel(const T* __restrict__ x, 
       }
     }
   }
+  auto group_sum = [](float t) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+  };
   float mean = 0.f, inv;
   if constexpr (RMS) {
-    inv = rsqrtf(warp_sum(ss) / (float)dim + eps);
+    inv = rsqrtf(group_sum(ss) / (float)dim + eps);
   } else {
-    mean = warp_sum(s) / (float)dim;
+    mean = group_sum(s) / (float)dim;
     float sq = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
-      const int i = (k * 32 + lane) * V;
-      if (i < dim) {
+      const int i = (k * LPR + sub) * V;
+      if (live && i < dim) {
 #pragma unroll
         for (int q = 0; q < V; ++q) {
           const float d = v[k][q] - mean;
@@ -111,12 +118,13 @@ __global__ void __launch_bounds__(256) norm_vec_kernel(const T* __restrict__ x, 
         }
       }
     }
-    inv = rsqrtf(warp_sum(sq) / (float)dim + eps);
+    inv = rsqrtf(group_sum(sq) / (float)dim + eps);
   }
+  if (!live) return;
   T* yr = y + row * dim;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
-    const int i = (k * 32 + lane) * V;
+    const int i = (k * LPR + sub) * V;
     if (i < dim) {
       float o[V];
 #pragma unroll
@@ -139,6 +147,22 @@ __global__ void __launch_bounds__(256) norm_vec_kernel(const T* __restrict__ x, 
   }
 }
 
+template <typename T, bool RMS>
+static void launch_norm_vec(const T* x, const float* w, const float* b, T* y, int64_t rows, int dim, float eps,
+                            cudaStream_t stream) {
+  constexpr int V = 16 / sizeof(T);
+  const int vecs = dim / V;   // 16-byte vectors per row
+#define NV(LPR, MAXV)                                                                                          \
+  norm_vec_kernel<T, RMS, LPR, MAXV><<<(unsigned)((rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR))), 256, 0, stream>>>( \
+      x, w, b, y, rows, dim, eps)
+  if (vecs <= 8) NV(8, 1);
+  else if (vecs <= 16) NV(16, 1);
+  else if (vecs <= 32) NV(32, 1);
+  else if (vecs <= 64) NV(32, 2);
+  else NV(32, 4);
+#undef NV
+}
+
 static bool norm_vec_ok(const void* x, const void* y, int dim, int dtype) {
   const int V = dtype == YMT3_F32 ? 4 : 8;
   return dim % V == 0 && dim <= 32 * 4 * V && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
@@ -150,11 +174,8 @@ int rmsnorm(const void* x, const float* w, void* y, int64_t rows, int dim, float
   YMT3_REQUIRE(x && w && y && dim > 0, "rmsnorm: bad argument");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (norm_vec_ok(x, y, dim, dtype)) {
-    if (dtype == YMT3_F32)
-      norm_vec_kernel<float, true><<<grid, 256, 0, stream>>>((const float*)x, w, nullptr, (float*)y, rows, dim, eps);
-    else
-      norm_vec_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, w, nullptr,
-                                                                     (__nv_bfloat16*)y, rows, dim, eps);
+    if (dtype == YMT3_F32) launch_norm_vec<float, true>((const float*)x, w, nullptr, (float*)y, rows, dim, eps, stream);
+    else launch_norm_vec<__nv_bfloat16, true>((const __nv_bfloat16*)x, w, nullptr, (__nv_bfloat16*)y, rows, dim, eps, stream);
     YMT3_CUDA_CHECK(cudaGetLastError());
     return YMT3_OK;
   }
@@ -173,11 +194,8 @@ int layernorm(const void* x, const float* w, const float* b, void* y, int64_t ro
   YMT3_REQUIRE(x && w && y && dim > 0, "layernorm: bad argument");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (norm_vec_ok(x, y, dim, dtype)) {
-    if (dtype == YMT3_F32)
-      norm_vec_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)x, w, b, (float*)y, rows, dim, eps);
-    else
-      norm_vec_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, w, b, (__nv_bfloat16*)y,
-                                                                      rows, dim, eps);
+    if (dtype == YMT3_F32) launch_norm_vec<float, false>((const float*)x, w, b, (float*)y, rows, dim, eps, stream);
+    else launch_norm_vec<__nv_bfloat16, false>((const __nv_bfloat16*)x, w, b, (__nv_bfloat16*)y, rows, dim, eps, stream);
     YMT3_CUDA_CHECK(cudaGetLastError());
     return YMT3_OK;
   }

@@ -89,6 +89,8 @@ int attention(const AttnParams& p, int dtype, cudaStream_t stream);
 // elementwise helpers
 int add_rows(const void* x, const void* table, void* y, int64_t rows, int period, int dim, int dtype,
              cudaStream_t stream, int64_t div = 1);  // y[r,:] = x[r,:] + table[(r / div) % period,:]
+int split_kv_heads(const void* kv, void* Kout, void* Vout, int64_t N, int Tn, int H, int dk, int dtype,
+                   cudaStream_t stream);
 int permute_btcd_bctd(const void* x, void* y, int64_t B, int64_t T, int64_t C, int64_t D, int dtype,
                       cudaStream_t stream);
 int convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, cudaStream_t stream);

@@ -228,6 +228,40 @@ __global__ void __launch_bounds__(256) permute_btcd_kernel(const T* __restrict__
   y[i] = x[((b * Tn + t) * Cn + c) * Dn + d];
 }
 
+// cross-attention K/V: (N*T, [K|V], H, dk) rows straight out of the projection GEMM  ->  K: (N, H, T, dk) then
+// V: (N, H, T, dk), so that one (sequence, head) is two contiguous T*dk blocks for the decode attention kernel.
+// 16 bytes per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) split_kv_heads_kernel(const T* __restrict__ kv, T* __restrict__ Kout,
+                                                             T* __restrict__ Vout, int64_t total, int Tn, int H, int dk) {
+  constexpr int V = 16 / sizeof(T);
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V;   // index into Kout (n, h, t, d)
+  if (i >= total) return;
+  const int d = (int)(i % dk);
+  const int t = (int)((i / dk) % Tn);
+  const int h = (int)((i / ((int64_t)dk * Tn)) % H);
+  const int64_t n = i / ((int64_t)dk * Tn * H);
+  const int64_t src = ((n * Tn + t) * 2) * (int64_t)H * dk + (int64_t)h * dk + d;
+  *reinterpret_cast<uint4*>(Kout + i) = *reinterpret_cast<const uint4*>(kv + src);
+  *reinterpret_cast<uint4*>(Vout + i) = *reinterpret_cast<const uint4*>(kv + src + (int64_t)H * dk);
+}
+
+int split_kv_heads(const void* kv, void* Kout, void* Vout, int64_t N, int Tn, int H, int dk, int dtype,
+                   cudaStream_t stream) {
+  const int64_t total = N * Tn * H * dk;
+  if (total <= 0) return YMT3_OK;
+  YMT3_REQUIRE(dk % 8 == 0, "split_kv_heads: dk must be a multiple of 8");
+  const int64_t vec = dtype == YMT3_F32 ? 4 : 8;
+  const unsigned grid = (unsigned)((total / vec + 255) / 256);
+  if (dtype == YMT3_F32)
+    split_kv_heads_kernel<float><<<grid, 256, 0, stream>>>((const float*)kv, (float*)Kout, (float*)Vout, total, Tn, H, dk);
+  else
+    split_kv_heads_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)kv, (__nv_bfloat16*)Kout,
+                                                                   (__nv_bfloat16*)Vout, total, Tn, H, dk);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
 int permute_btcd_bctd(const void* x, void* y, int64_t B, int64_t T, int64_t C, int64_t D, int dtype,
                       cudaStream_t stream) {
   const int64_t total = B * T * C * D;

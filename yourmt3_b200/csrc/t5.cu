@@ -179,7 +179,8 @@ struct ymt3_t5dec {
   int64_t cap_N = 0, cap_T = 0, cap_L = 0;
   void *x = nullptr, *h = nullptr, *qkv = nullptr, *attn = nullptr, *qx = nullptr, *g = nullptr;
   float* logits = nullptr;
-  std::vector<void*> selfK, selfV, crossKV;
+  std::vector<void*> selfK, selfV, crossKV;   // crossKV[i]: K (N, H, T, dk) followed by V (N, H, T, dk)
+  void* kv_tmp = nullptr;                      // (N*T, 2*inner) projection output before the head split
   int *d_step = nullptr, *d_cur = nullptr, *d_fin = nullptr, *d_unfinished = nullptr;
   int* h_unfinished = nullptr;  // pinned
   // the decode loop runs on an internal stream (graph capture is illegal on the legacy default
@@ -294,9 +295,10 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, cudaStream_t s
   d->qx = d->ws.alloc(cN * inner * es);
   d->g = d->ws.alloc(cN * F * es);
   d->logits = (float*)d->ws.alloc(cN * d->Vp * 4);
+  d->kv_tmp = d->ws.alloc(cN * cT * 2 * inner * es);
   d->d_cur = (int*)d->ws.alloc(cN * 4);
   d->d_fin = (int*)d->ws.alloc(cN * 4);
-  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin;
+  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->kv_tmp;
   d->selfK.assign(c.num_layers, nullptr);
   d->selfV.assign(c.num_layers, nullptr);
   d->crossKV.assign(c.num_layers, nullptr);
@@ -335,9 +337,9 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
     // cross-attention over encoder K/V computed once (modeling_t5.py:387-408)
     if ((rc = rmsnorm(d->x, L.ln_ca, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
     if ((rc = linear_fwd(dt, d->h, D, L.xq, d->qx, inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
-    if ((rc = decode_attention(d->qx, inner, nullptr, nullptr, 0, d->crossKV[i], (char*)d->crossKV[i] + inner * es,
-                               T * 2 * inner, dk, 2 * inner, 0, d->d_step, (int)T, 1.0f, d->attn, inner, (int)N, H, dk,
-                               dt, s)))
+    if ((rc = decode_attention(d->qx, inner, nullptr, nullptr, 0, d->crossKV[i],
+                               (char*)d->crossKV[i] + (size_t)N * inner * T * es, (int64_t)H * T * dk, T * dk, dk, 0,
+                               d->d_step, (int)T, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
       return rc;
     if ((rc = linear_fwd(dt, d->attn, inner, L.xo, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
     // gated-GELU feed-forward
@@ -402,10 +404,15 @@ extern "C" int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* d, const void* enc_hs,
   if ((rc = fill_i32(d->d_fin, 0, N, s))) return rc;
   if ((rc = fill_i32(tokens_out, c.pad_id, N * max_len, s))) return rc;
   // cross-attention K/V of every layer, once (modeling_t5.py:287-299)
-  for (int i = 0; i < c.num_layers; ++i)
-    if ((rc = linear_fwd(dt, enc_hs, D, d->layers[i].xkv, d->crossKV[i], 2 * inner, (int)(N * T), 0, 0, nullptr, 0, 1.f,
-                         dt, s)))
+  for (int i = 0; i < c.num_layers; ++i) {
+    if ((rc = linear_fwd(dt, enc_hs, D, d->layers[i].xkv, d->kv_tmp, 2 * inner, (int)(N * T), 0, 0, nullptr, 0, 1.f, dt,
+                         s)))
       return rc;
+    // head-major contiguous layout: each (sequence, head) becomes two contiguous T*dk streams for the 256+ re-reads
+    if ((rc = split_kv_heads(d->kv_tmp, d->crossKV[i], (char*)d->crossKV[i] + (size_t)N * inner * T * dtype_size(dt), N,
+                             (int)T, c.num_heads, c.d_kv, dt, s)))
+      return rc;
+  }
 
   // one decode step captured into a CUDA graph (all step-dependent scalars live on the device)
   const bool use_graph = getenv("YMT3_NO_GRAPH") == nullptr && !caller_capturing;

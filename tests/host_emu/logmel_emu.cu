@@ -10,12 +10,10 @@ extern "C" __attribute__((visibility("default"))) int lm_emu_run(const ymt3_audi
                           const float* audio, int B, int L, float* out) {
   LmHostTables ht;
   if (lm_build_host_tables(cfg, fb, ht)) return 1;
-  LmTables tb{window, ht.tw1.data(), ht.tw2.data(), ht.first.data(), ht.off.data(), ht.wts.data()};
+  LmTables tb{window, ht.tw1.data(), ht.tw2.data(), ht.first.data(), ht.off.data(), ht.meta.data(), ht.wts.data()};
   const int T = 1 + L / cfg->hop_length, hop = cfg->hop_length, n_out = ht.n_out;
   const int pairs = (T + 1) / 2;
-  std::vector<float2> bufA(LM_BUF_ELEMS), bufB(LM_BUF_ELEMS);
-  float* magA = reinterpret_cast<float*>(bufB.data());
-  float* magB = magA + 1028;
+  std::vector<float2> bufA(LM_BUF_ELEMS), bufB(LM_BUF_ELEMS), mags(LM_MAG_ELEMS);
   for (int b = 0; b < B; ++b)
     for (int tp = 0; tp < pairs; ++tp) {
       const int tA = 2 * tp;
@@ -28,16 +26,17 @@ extern "C" __attribute__((visibility("default"))) int lm_emu_run(const ymt3_audi
         lm_pass1(tid, seg, L, startA, startB, hasB, w, tb.tw1, bufA.data());
       }
       for (int tid = 0; tid < LM_THREADS; ++tid) lm_pass2(tid, tb.tw2, bufA.data(), bufB.data());
-      for (int tid = 0; tid < LM_THREADS; ++tid) lm_pass3(tid, bufB.data(), bufA.data());
-      for (int tid = 0; tid < LM_THREADS; ++tid)
-        lm_mag(tid, bufA.data(), magA, magB, cfg->power_mode);
+      for (size_t i = 0; i < mags.size(); ++i) mags[i] = make_float2(-1.f, -1.f);   // poison: every bin must be written
+      for (int tid = 0; tid < LM_THREADS; ++tid) lm_pass3_mag(tid, bufB.data(), mags.data(), cfg->power_mode);
+      for (int k = 0; k <= 1024; ++k)
+        if (mags[lm_magaddr(k)].x < 0.f) return 2;
       float* outA = out + ((size_t)b * T + tA) * n_out;
       float* outB = hasB ? outA + n_out : nullptr;
       for (int tid = 0; tid < LM_THREADS; ++tid) {
         if (cfg->codec == YMT3_CODEC_MELSPEC)
-          lm_mel_log(tid, tb, n_out, cfg->log_eps, magA, magB, outA, outB);
+          lm_mel_log(tid, tb, n_out, cfg->log_eps, mags.data(), outA, outB);
         else
-          lm_spec_log(tid, cfg->spec_bin0, n_out, cfg->log_eps, magA, magB, outA, outB);
+          lm_spec_log(tid, cfg->spec_bin0, n_out, cfg->log_eps, mags.data(), outA, outB);
       }
     }
   return 0;

@@ -16,6 +16,7 @@ struct ymt3_frontend {
   float2* d_tw2;
   int* d_mel_first;
   int* d_mel_off;
+  int2* d_mel_meta;
   float* d_mel_w;
   // staging for the *_host entry point (grown on demand)
   float* d_stage_in;
@@ -29,16 +30,15 @@ ymt3_logmel_kernel(LmTables tb, const float* __restrict__ audio, float* __restri
                    int n_out, int spec_bin0, int power_mode, float eps) {
   __shared__ __align__(16) float2 bufA[LM_BUF_ELEMS];
   __shared__ __align__(16) float2 bufB[LM_BUF_ELEMS];
+  float2* mags = bufA;   // bufA is dead after pass 2; the interleaved magnitudes (LM_MAG_ELEMS <= LM_BUF_ELEMS) reuse it
   const int tid = threadIdx.x;
 
-  float w[16];
+  float w[16];   // loop-invariant window column of this thread
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) w[n1] = __ldg(tb.window + 128 * n1 + tid);
 
   const int p0 = blockIdx.x * chunk;
   const int p1 = min(p0 + chunk, total_pairs);
-  float* magA = reinterpret_cast<float*>(bufB);
-  float* magB = magA + 1028;
 
   for (int p = p0; p < p1; ++p) {
     const int b = p / pairs_per_seg;
@@ -52,19 +52,15 @@ ymt3_logmel_kernel(LmTables tb, const float* __restrict__ audio, float* __restri
     __syncthreads();
     lm_pass2(tid, tb.tw2, bufA, bufB);
     __syncthreads();
-    lm_pass3(tid, bufB, bufA);
-    __syncthreads();
-    lm_mag(tid, bufA, magA, magB, power_mode);
+    lm_pass3_mag(tid, bufB, mags, power_mode);
     __syncthreads();
     float* outA = out + ((size_t)b * T + tA) * n_out;
     float* outB = hasB ? outA + n_out : nullptr;
     if (codec == YMT3_CODEC_MELSPEC)
-      lm_mel_log(tid, tb, n_out, eps, magA, magB, outA, outB);
+      lm_mel_log(tid, tb, n_out, eps, mags, outA, outB);
     else
-      lm_spec_log(tid, spec_bin0, n_out, eps, magA, magB, outA, outB);
-    // no barrier needed here: the next pass-1 only writes bufA (mag reads of bufA
-    // completed before the last barrier) and bufB is next written after the
-    // barrier that follows pass-1, which every thread reaches after its mel reads.
+      lm_spec_log(tid, spec_bin0, n_out, eps, mags, outA, outB);
+    __syncthreads();   // mags alias bufA, which the next pair's pass 1 overwrites
   }
 }
 
@@ -109,6 +105,7 @@ extern "C" int ymt3_frontend_create(const ymt3_audio_cfg_t* cfg, const float* wi
   FE_UPLOAD(fe->d_tw2, tw2, float2);
   FE_UPLOAD(fe->d_mel_first, first, int);
   FE_UPLOAD(fe->d_mel_off, off, int);
+  FE_UPLOAD(fe->d_mel_meta, ht.meta, int2);
   FE_UPLOAD(fe->d_mel_w, wts, float);
 #undef FE_UPLOAD
   *out = fe;
@@ -122,6 +119,7 @@ extern "C" int ymt3_frontend_destroy(ymt3_frontend_t* fe) {
   cudaFree(fe->d_tw2);
   cudaFree(fe->d_mel_first);
   cudaFree(fe->d_mel_off);
+  cudaFree(fe->d_mel_meta);
   cudaFree(fe->d_mel_w);
   cudaFree(fe->d_stage_in);
   cudaFree(fe->d_stage_out);
@@ -158,7 +156,7 @@ extern "C" int ymt3_logmel_f32(ymt3_frontend_t* fe, const float* audio_dev, int6
   if (chunk < 1) chunk = 1;
   if (chunk > 8) chunk = 8;
   const int grid = ymt3_div_up(total, chunk);
-  LmTables tb{fe->d_window, fe->d_tw1, fe->d_tw2, fe->d_mel_first, fe->d_mel_off, fe->d_mel_w};
+  LmTables tb{fe->d_window, fe->d_tw1, fe->d_tw2, fe->d_mel_first, fe->d_mel_off, fe->d_mel_meta, fe->d_mel_w};
   ymt3_logmel_kernel<<<grid, LM_THREADS, 0, (cudaStream_t)stream>>>(
       tb, audio_dev, out_dev, (int)L, T, fe->cfg.hop_length, pairs_per_seg, chunk, total,
       fe->cfg.codec, fe->n_out, fe->cfg.spec_bin0, fe->cfg.power_mode, fe->cfg.log_eps);

@@ -9,6 +9,7 @@
 struct LmHostTables {
   std::vector<float2> tw1, tw2;
   std::vector<int> first, off;
+  std::vector<int2> meta;   // (first | count << 16, offset)
   std::vector<float> wts;
   int n_out = 0;
 };
@@ -60,5 +61,11 @@ static inline const char* lm_build_host_tables(const ymt3_audio_cfg_t* cfg, cons
     t.off.assign(2, 0);
   }
   if (t.wts.empty()) t.wts.push_back(0.f);
+  t.meta.resize(t.first.size());
+  for (size_t m = 0; m < t.first.size(); ++m) {
+    const int cnt = t.off[m + 1] - t.off[m];
+    if (t.first[m] > 0xffff || cnt > 0x7fff) return "mel filter too wide";
+    t.meta[m] = make_int2(t.first[m] | (cnt << 16), t.off[m]);
+  }
   return nullptr;
 }

@@ -82,6 +82,12 @@ YMT3_API int64_t ymt3_frontend_num_features(const ymt3_frontend_t* fe);
 /* audio_dev: (B, L) f32 contiguous. out_dev: (B, T, F) f32 contiguous. */
 YMT3_API int ymt3_logmel_f32(ymt3_frontend_t* fe, const float* audio_dev, int64_t B, int64_t L,
                     float* out_dev, void* stream);
+/* Whole-waveform entry: replaces upstream utils/audio.py slice_padded_array(audio, L, L) +
+ * the spectrogram layer.  wave_dev: (n_samples) f32 mono 16 kHz; segments are [b*seg_len, (b+1)*seg_len) with the
+ * tail zero-padded; out_dev: (ymt3_num_segments(n_samples, seg_len), T, F).  No sliced copy is materialised. */
+YMT3_API int64_t ymt3_num_segments(int64_t n_samples, int64_t seg_len);
+YMT3_API int ymt3_logmel_waveform_f32(ymt3_frontend_t* fe, const float* wave_dev, int64_t n_samples, int64_t seg_len,
+                                      float* out_dev, void* stream);
 /* Same with HOST buffers: H2D + kernel + D2H + stream sync (the end-to-end call). */
 YMT3_API int ymt3_logmel_host_f32(ymt3_frontend_t* fe, const float* audio_host, int64_t B, int64_t L,
                          float* out_host, void* stream);

@@ -6,8 +6,16 @@
 #include "../../yourmt3_b200/csrc/logmel_tables.h"
 #include <vector>
 
+extern "C" __attribute__((visibility("default"))) int lm_emu_run_wave(const ymt3_audio_cfg_t* cfg, const float* window,
+                                                                     const float* fb, const float* audio, long long total,
+                                                                     int B, int L, float* out);
 extern "C" __attribute__((visibility("default"))) int lm_emu_run(const ymt3_audio_cfg_t* cfg, const float* window, const float* fb,
                           const float* audio, int B, int L, float* out) {
+  return lm_emu_run_wave(cfg, window, fb, audio, (long long)B * L, B, L, out);
+}
+extern "C" __attribute__((visibility("default"))) int lm_emu_run_wave(const ymt3_audio_cfg_t* cfg, const float* window,
+                                                                     const float* fb, const float* audio, long long total,
+                                                                     int B, int L, float* out) {
   LmHostTables ht;
   if (lm_build_host_tables(cfg, fb, ht)) return 1;
   LmTables tb{window, ht.tw1.data(), ht.tw2.data(), ht.first.data(), ht.off.data(), ht.meta.data(), ht.wts.data()};
@@ -23,7 +31,9 @@ extern "C" __attribute__((visibility("default"))) int lm_emu_run(const ymt3_audi
       for (int tid = 0; tid < LM_THREADS; ++tid) {
         float w[16];
         for (int n1 = 0; n1 < 16; ++n1) w[n1] = window[128 * n1 + tid];
-        lm_pass1(tid, seg, L, startA, startB, hasB, w, tb.tw1, bufA.data());
+        const long long remain = total - (long long)b * L;
+        const int valid = remain >= L ? L : (remain > 0 ? (int)remain : 0);
+        lm_pass1(tid, seg, L, valid, startA, startB, hasB, w, tb.tw1, bufA.data());
       }
       for (int tid = 0; tid < LM_THREADS; ++tid) lm_pass2(tid, tb.tw2, bufA.data(), bufB.data());
       for (size_t i = 0; i < mags.size(); ++i) mags[i] = make_float2(-1.f, -1.f);   // poison: every bin must be written

@@ -78,3 +78,21 @@ def test_emu_impulse_and_dc(emu_lib):
     assert np.allclose(y[1, :, 0], np.log(512.0), atol=1e-5)
     assert np.allclose(y[1, :, 1], np.log(256.0), atol=1e-5)          # hann first side lobe = half
     assert np.all(y[1, :, 3:] < np.log(1e-3))
+
+
+def test_emu_waveform_mode_equals_slice_padded_array(emu_lib):
+    """Segmentation fused into the loads == slice_padded_array + per-segment frontend."""
+    from yourmt3_b200.audio_utils import slice_padded_array
+    layer = S.Melspectrogram()
+    L = 4100
+    wave = synth_noise(1, 3 * L - 1234, seed=3)[0]
+    segs = np.ascontiguousarray(slice_padded_array(wave, L, L)[:, 0, :])
+    ref = emu_run(emu_lib, layer, segs)
+    out = np.zeros_like(ref)
+    win, fb, cfg = layer._window().numpy().copy(), layer._fb().numpy().copy(), layer._cfg()
+    emu_lib.lm_emu_run_wave.restype = C.c_int
+    rc = emu_lib.lm_emu_run_wave(C.byref(cfg), win.ctypes.data_as(C.c_void_p), fb.ctypes.data_as(C.c_void_p),
+                                 np.ascontiguousarray(wave).ctypes.data_as(C.c_void_p), C.c_longlong(wave.size), 3, L,
+                                 out.ctypes.data_as(C.c_void_p))
+    assert rc == 0 and segs.shape[0] == 3
+    assert np.array_equal(out, ref)

@@ -124,3 +124,16 @@ def test_state_dict_buffers_drive_the_kernel(cuda_device, native_lib):
     layer.load_state_dict(sd)
     y1 = layer(x)
     assert torch.allclose(y1, y0 + float(np.log(2.0)), atol=1e-5)
+
+
+def test_waveform_entry_equals_sliced_segments(cuda_device, native_lib):
+    """ymt3_logmel_waveform_f32 (segmentation + tail padding fused) == slice_padded_array + forward, bit for bit."""
+    from yourmt3_b200.audio_utils import slice_padded_array
+    for layer in (S.Melspectrogram(), S.Spectrogram()):
+        for n in (32767 * 3 + 5000, 32767 * 2, 100, 32767 * 4 - 1):
+            wave = torch.from_numpy(synth_noise(1, n, seed=n % 1000)[0]).to(cuda_device)
+            segs = slice_padded_array(wave, 32767, 32767)
+            ref = layer(segs)
+            got = layer.forward_waveform(wave)
+            assert got.shape == ref.shape
+            assert torch.equal(got, ref)

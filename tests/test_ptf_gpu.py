@@ -114,3 +114,14 @@ def test_full_inference_bf16_runs_and_agrees(cuda_device, native_lib):
     a, b = m32.inference(x, stop_at_eos=False).cpu(), m16.inference(x, stop_at_eos=False).cpu()
     assert a.shape == b.shape == (2, 13, 8)
     assert float((a[..., 0] == b[..., 0]).float().mean()) >= 0.75      # first-step tokens mostly agree in bf16
+
+
+def test_transcribe_waveform_equals_segmented_inference(cuda_device, native_lib):
+    """whole-waveform entry (fused segmentation) == slice_padded_array + inference, identical tokens."""
+    from yourmt3_b200.audio_utils import slice_padded_array
+    m = small_model("yptf_moe_multi", "f32", blocks=1, dec_layers=2, event_length=6, seed=5).to(cuda_device)
+    wave = torch.from_numpy(synth_noise(1, 32767 * 2 + 9000, seed=33)[0]).to(cuda_device)
+    a = m.transcribe_waveform(wave, bsz=2, stop_at_eos=False)
+    b = m.inference(slice_padded_array(wave, 32767, 32767), stop_at_eos=False)
+    assert a.shape == b.shape == (3, 13, 6)
+    assert torch.equal(a, b)

@@ -79,6 +79,8 @@ SIGNATURES = {
     "ymt3_frontend_num_frames": (_I64, [_P, _I64]),
     "ymt3_frontend_num_features": (_I64, [_P]),
     "ymt3_logmel_f32": (_I, [_P, _P, _I64, _I64, _P, _P]),
+    "ymt3_num_segments": (_I64, [_I64, _I64]),
+    "ymt3_logmel_waveform_f32": (_I, [_P, _P, _I64, _I64, _P, _P]),
     "ymt3_logmel_host_f32": (_I, [_P, _P, _I64, _I64, _P, _P]),
     "ymt3_t5enc_create": (_I, [C.POINTER(T5Cfg), C.POINTER(Tensor), _I, C.POINTER(_P)]),
     "ymt3_t5enc_destroy": (_I, [_P]),

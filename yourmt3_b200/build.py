@@ -62,6 +62,11 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             for out in ex.map(_run, jobs):
                 if verbose and out.strip():
                     print(out)
+    # prune stale objects of earlier source revisions (the directory travels with gpurun snapshots)
+    keep = {os.path.basename(o) for o in objs}
+    for f in os.listdir(OBJ_DIR):
+        if f.endswith(".o") and f not in keep:
+            os.remove(os.path.join(OBJ_DIR, f))
     stamp = os.path.join(OBJ_DIR, "link.stamp")
     link_tag = _digest(objs) if all(os.path.exists(o) for o in objs) else ""
     old = open(stamp).read() if os.path.exists(stamp) else ""

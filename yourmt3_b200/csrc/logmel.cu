@@ -25,7 +25,7 @@ struct ymt3_frontend {
 };
 
 __global__ void __launch_bounds__(LM_THREADS, 6)
-ymt3_logmel_kernel(LmTables tb, const float* __restrict__ audio, float* __restrict__ out, int L,
+ymt3_logmel_kernel(LmTables tb, const float* __restrict__ audio, int64_t total_samples, float* __restrict__ out, int L,
                    int T, int hop, int pairs_per_seg, int chunk, int total_pairs, int codec,
                    int n_out, int spec_bin0, int power_mode, float eps) {
   __shared__ __align__(16) float2 bufA[LM_BUF_ELEMS];
@@ -45,10 +45,12 @@ ymt3_logmel_kernel(LmTables tb, const float* __restrict__ audio, float* __restri
     const int tA = 2 * (p - b * pairs_per_seg);
     const bool hasB = (tA + 1) < T;
     const float* seg = audio + (size_t)b * L;
+    const int64_t remain = total_samples - (int64_t)b * L;   // waveform mode: the last segment may be partial
+    const int valid = remain >= L ? L : (remain > 0 ? (int)remain : 0);
     const int startA = tA * hop - LM_NFFT / 2;
     const int startB = startA + hop;
 
-    lm_pass1(tid, seg, L, startA, startB, hasB, w, tb.tw1, bufA);
+    lm_pass1(tid, seg, L, valid, startA, startB, hasB, w, tb.tw1, bufA);
     __syncthreads();
     lm_pass2(tid, tb.tw2, bufA, bufB);
     __syncthreads();
@@ -134,8 +136,30 @@ extern "C" int64_t ymt3_frontend_num_features(const ymt3_frontend_t* fe) {
   return fe ? fe->n_out : -1;
 }
 
+static int logmel_launch(ymt3_frontend_t* fe, const float* audio_dev, int64_t total_samples, int64_t B, int64_t L,
+                         float* out_dev, void* stream);
+
 extern "C" int ymt3_logmel_f32(ymt3_frontend_t* fe, const float* audio_dev, int64_t B, int64_t L,
                                float* out_dev, void* stream) {
+  return logmel_launch(fe, audio_dev, B * L, B, L, out_dev, stream);
+}
+
+extern "C" int64_t ymt3_num_segments(int64_t n_samples, int64_t seg_len) {
+  if (seg_len <= 0) return -1;
+  const int64_t n = (n_samples + seg_len - 1) / seg_len;
+  return n < 1 ? 1 : n;
+}
+
+// Waveform entry: segmentation (upstream utils/audio.py slice_padded_array: hop == length, zero-padded tail)
+// is fused into the kernel's loads -- no sliced / padded copy of the audio is ever materialised.
+extern "C" int ymt3_logmel_waveform_f32(ymt3_frontend_t* fe, const float* wave_dev, int64_t n_samples, int64_t seg_len,
+                                        float* out_dev, void* stream) {
+  YMT3_REQUIRE(n_samples >= 0 && seg_len > 0, "logmel_waveform: bad sizes");
+  return logmel_launch(fe, wave_dev, n_samples, ymt3_num_segments(n_samples, seg_len), seg_len, out_dev, stream);
+}
+
+static int logmel_launch(ymt3_frontend_t* fe, const float* audio_dev, int64_t total_samples, int64_t B, int64_t L,
+                         float* out_dev, void* stream) {
   YMT3_REQUIRE(fe, "logmel: null handle");
   YMT3_REQUIRE(B >= 0, "logmel: negative batch");
   if (B == 0) return YMT3_OK;   // empty batch: nothing to do (pointers may be null)
@@ -158,7 +182,7 @@ extern "C" int ymt3_logmel_f32(ymt3_frontend_t* fe, const float* audio_dev, int6
   const int grid = ymt3_div_up(total, chunk);
   LmTables tb{fe->d_window, fe->d_tw1, fe->d_tw2, fe->d_mel_first, fe->d_mel_off, fe->d_mel_meta, fe->d_mel_w};
   ymt3_logmel_kernel<<<grid, LM_THREADS, 0, (cudaStream_t)stream>>>(
-      tb, audio_dev, out_dev, (int)L, T, fe->cfg.hop_length, pairs_per_seg, chunk, total,
+      tb, audio_dev, total_samples, out_dev, (int)L, T, fe->cfg.hop_length, pairs_per_seg, chunk, total,
       fe->cfg.codec, fe->n_out, fe->cfg.spec_bin0, fe->cfg.power_mode, fe->cfg.log_eps);
   YMT3_CUDA_CHECK(cudaGetLastError());
   return YMT3_OK;

@@ -133,10 +133,16 @@ YMT3_HD void lm_tw_powers(float2 w1, float2 w2, float2 w4, float2 w8, float2 (&p
 // in un-padded coordinates (may be negative / beyond L -> reflect).
 // tw1: [16][128] table W_2048^(m*k1) (L1-resident; rebuilding the powers in registers was measured slower:
 // +130 FP instructions and +16 registers per thread cost more than the 15 loads they save)
-YMT3_HD void lm_pass1(int tid, const float* __restrict__ seg, int L, int startA, int startB,
+// valid <= L: number of samples of this segment that exist (waveform tail); samples in [valid, L) read as 0
+// (= slice_padded_array zero padding fused into the load), reflection still happens at the segment length L.
+YMT3_HD float lm_ld(const float* __restrict__ seg, int i, int L, int valid) {
+  i = lm_reflect(i, L);
+  return i < valid ? seg[i] : 0.f;
+}
+YMT3_HD void lm_pass1(int tid, const float* __restrict__ seg, int L, int valid, int startA, int startB,
                       bool hasB, const float (&w)[16], const float2* __restrict__ tw1, float2* __restrict__ bufA) {
   float2 v[16];
-  const bool interior = (startA >= 0) && (startB + LM_NFFT <= L);
+  const bool interior = (startA >= 0) && (startB + LM_NFFT <= valid);
   if (startB - startA == 128) {
     // hop == 128: frame B sample (n1) == frame A sample (n1 + 1): 17 loads feed both frames
     float xs[17];
@@ -145,7 +151,7 @@ YMT3_HD void lm_pass1(int tid, const float* __restrict__ seg, int L, int startA,
       for (int n1 = 0; n1 < 17; ++n1) xs[n1] = seg[startA + 128 * n1 + tid];
     } else {
 #pragma unroll
-      for (int n1 = 0; n1 < 17; ++n1) xs[n1] = seg[lm_reflect(startA + 128 * n1 + tid, L)];
+      for (int n1 = 0; n1 < 17; ++n1) xs[n1] = lm_ld(seg, startA + 128 * n1 + tid, L, valid);
     }
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) v[n1] = make_float2(xs[n1] * w[n1], xs[n1 + 1] * w[n1]);
@@ -165,8 +171,8 @@ YMT3_HD void lm_pass1(int tid, const float* __restrict__ seg, int L, int startA,
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
       int n = 128 * n1 + tid;
-      float xa = seg[lm_reflect(startA + n, L)];
-      float xb = hasB ? seg[lm_reflect(startB + n, L)] : 0.f;
+      float xa = lm_ld(seg, startA + n, L, valid);
+      float xb = hasB ? lm_ld(seg, startB + n, L, valid) : 0.f;
       v[n1] = make_float2(xa * w[n1], xb * w[n1]);
     }
   }

@@ -117,6 +117,25 @@ class _FusedFrontend(nn.Module):
         _lib.check(rc, "logmel")
         return out
 
+    def forward_waveform(self, wave: torch.Tensor, segment_length: int = 32767) -> torch.Tensor:
+        """wave: (n_samples,) or (1, n_samples) float32 CUDA -> (n_seg, T, F).  Equivalent to
+        ``forward(slice_padded_array(wave, L, L))`` (upstream utils/audio.py) with the slicing and the zero
+        padding of the tail fused into the kernel's loads."""
+        if not wave.is_cuda or wave.dtype != torch.float32:
+            raise RuntimeError("forward_waveform expects a float32 CUDA tensor (no CPU fallback)")
+        wave = wave.reshape(-1).contiguous()
+        n = wave.numel()
+        lib = _lib.load()
+        n_seg = lib.ymt3_num_segments(n, segment_length)
+        h = self._get_handle(wave.device)
+        out = torch.empty((n_seg, self.num_frames(segment_length), self.num_features), dtype=torch.float32,
+                          device=wave.device)
+        with torch.cuda.device(wave.device):
+            rc = lib.ymt3_logmel_waveform_f32(h, wave.data_ptr(), n, segment_length, out.data_ptr(),
+                                              _lib.current_stream_ptr())
+        _lib.check(rc, "logmel_waveform")
+        return out
+
     def forward_host(self, x: torch.Tensor) -> torch.Tensor:
         """End-to-end call with HOST buffers (H2D + kernel + D2H inside the C ABI)."""
         if x.dim() == 3:

@@ -107,6 +107,22 @@ class YourMT3(nn.Module):
                                       lanes=self.decode_lanes if decode_lanes is None else decode_lanes)
 
     @torch.no_grad()
+    def transcribe_waveform(self, wave: torch.Tensor, bsz: int = 256, **kw) -> torch.Tensor:
+        """Whole mono 16 kHz waveform (n_samples,) on the model's device -> tokens (n_seg, L) / (n_seg, C, L).
+        The frontend consumes the waveform directly (segmentation + tail zero-padding fused into its loads,
+        SURVEY 8f.1); the model then runs in batches of ``bsz`` segments."""
+        feats = self.spectrogram.forward_waveform(wave, self.audio_cfg["input_frames"])
+        max_len = kw.pop("max_token_length", None) or self.max_token_length
+        outs = []
+        for i in range(0, feats.shape[0], bsz):
+            enc_hs = self.pre_decoder(self.encoder(inputs_embeds=self.pre_encoder(feats[i:i + bsz]))["last_hidden_state"])
+            outs.append(task_cond_dec_generate(self.decoder, self.decoder_type, self.embed_tokens, self.lm_head, enc_hs,
+                                               max_length=max_len, stop_at_eos=kw.get("stop_at_eos", True),
+                                               eos_id=self.eos_id, pad_id=self.pad_id, decoder_start_token_id=self.pad_id,
+                                               precision=self._prec))
+        return torch.cat(outs, 0)
+
+    @torch.no_grad()
     def inference_file_sharded(self, bsz: int, audio_segments: torch.Tensor, **kw) -> torch.Tensor:
         """Multi-GPU long-form path (one process per GPU, torch.distributed initialised with NCCL): this
         rank transcribes its contiguous range of segments; ONE all-gather returns the ordered tokens

@@ -159,3 +159,27 @@ def test_bf16_logits_and_tokens(cuda_device, native_lib):
         neq = np.nonzero(got[n] != ref[n].numpy())[0]
         agree.append((neq[0] if len(neq) else 24) / 24.0)
     assert np.mean(agree) >= 0.9, agree
+
+
+def test_bf16_note_onset_f1_vs_fp32(cuda_device, native_lib):
+    """North-star bf16 criterion restated for random weights: decode the SAME synthetic multitrack audio with the
+    fp32 (exact) and the bf16 (tcgen05) paths, detokenise both to note events and score bf16 against fp32 with the
+    mir_eval-style onset F1 (50 ms).  Stated bar: F1 >= 0.7 over 16 segments x 32 tokens."""
+    from yourmt3_b200 import event_codec as EC
+    cfg = small_cfg(n_layers=2, event_length=32)
+    audio = torch.from_numpy(synth_multitrack(16, seed=77)).unsqueeze(1).to(cuda_device)
+    toks = {}
+    for prec in ("f32", "bf16"):
+        m = ymt3.init_nondegenerate_(ymt3.YourMT3(model_cfg=cfg, precision=prec), seed=3).to(cuda_device)
+        toks[prec] = m.inference(audio, stop_at_eos=False).cpu().numpy()
+    ref, est = EC.batch_tokens_to_notes(toks["f32"]), EC.batch_tokens_to_notes(toks["bf16"])
+    # random-init decodes have no tie token: treat every pitch token as an onset by prepending one
+    if not ref:
+        tie = EC.encode_event("tie", 0)
+        ref = EC.batch_tokens_to_notes(np.concatenate([np.full((16, 1), tie), toks["f32"]], 1))
+        est = EC.batch_tokens_to_notes(np.concatenate([np.full((16, 1), tie), toks["bf16"]], 1))
+    p, r, f = EC.onset_f1(ref, est)
+    agree = float((toks["f32"] == toks["bf16"]).mean())
+    print(f"bf16 vs fp32: token agreement {agree:.3f}, notes {len(ref)}/{len(est)}, onset P/R/F1 = {p:.3f}/{r:.3f}/{f:.3f}")
+    assert len(ref) > 0
+    assert f >= 0.7

@@ -92,6 +92,16 @@ class ModelWorkload:
         ts.sort()
         return ts[len(ts) // 2]
 
+    @property
+    def ncu_traffic_bytes(self):
+        """dram__bytes_read + dram__bytes_write of the log-mel kernel from `ncu --set full`, scaled to this batch:
+        spec/hop-300 codec: profiles/r01_logmel_default_workload_ncu_full.txt (33.7 MB + 60.2 MB per 256 segments;
+        below the algorithmic 148.9 MB because part of the output is still resident in the 126 MB L2 when the
+        kernel ends); melspec/hop-128: profiles/r01_logmel_v1_ncu_full.txt (67.2 MB + 213.7 MB per 512 segments)."""
+        if self.model.audio_cfg["codec"] == "spec":
+            return int((33.69e6 + 60.15e6) / 256 * self.batch)
+        return int((67.20e6 + 213.67e6) / 512 * self.batch)
+
     def roofline_units(self):
         return self.batch * self.bytes_per_seg
 

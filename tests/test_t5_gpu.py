@@ -96,6 +96,15 @@ def test_task_prefix_tokens(cuda_device, model_small):
     assert torch.equal(cont, free[:, 3:])
 
 
+def test_decode_lanes_give_identical_tokens(cuda_device, model_small):
+    m = model_small
+    enc_hs = torch.randn(7, 21, 512, generator=torch.Generator().manual_seed(10)).to(cuda_device)
+    a = ymt3.task_cond_dec_generate(m.decoder, "t5", m.embed_tokens, m.lm_head, enc_hs, max_length=16, stop_at_eos=False)
+    b = ymt3.task_cond_dec_generate(m.decoder, "t5", m.embed_tokens, m.lm_head, enc_hs, max_length=16, stop_at_eos=False,
+                                    lanes=3)
+    assert torch.equal(a, b)
+
+
 def test_full_inference_matches_oracle(cuda_device, model_small):
     """audio -> tokens through YourMT3.inference vs the end-to-end CPU oracle (configs[0] shape, 2 layers)."""
     m = model_small

@@ -170,6 +170,22 @@ YMT3_API int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* dec, const void* enc_hs_
                                           const int32_t* prefix_ids_dev, int32_t P, int32_t max_len,
                                           int32_t stop_at_eos, int32_t early_stop_interval, int32_t* tokens_out_dev,
                                           void* stream);
+/* Absorbed ("latent") cross-attention, bf16 handles only.  When the encoder->decoder projection is an affine map of a
+ * narrow latent (upstream projection_layer.py `mc_shared_linear` [RECALL]: enc_hs[b,c,t,:] = Wp z[b,t,c,:] + bp with
+ * z = the channel's k2 x d_latent = 256 latent values), the K/V projections of every decoder layer are linear in the same
+ * z, so HF modeling_t5.py:269-305 (q K^T, softmax, V, o) can be evaluated without materialising K/V:
+ *     block.{i}.layer.1.EncDecAttention.q_absorbed.weight (H*zdim, d_model): rows h*zdim.. = (Wk_h Wp)^T Wq_h
+ *     block.{i}.layer.1.EncDecAttention.o_absorbed.weight (d_model, H*zdim): cols h*zdim.. = Wo_h Wv_h Wp
+ *     block.{i}.layer.1.EncDecAttention.o_absorbed.bias   (d_model)        : Wo Wv bp
+ * (the Wk bp term is constant over keys and cancels in the softmax).  If these tensors are present in the table
+ * given to ymt3_t5dec_create the handle also accepts ymt3_t5dec_generate_latent, which takes the ENCODER LATENTS
+ * latents_dev (B, T_enc, C, zdim) instead of the projected hidden states (N = B*C sequences, channel c of segment b
+ * is sequence b*C + c) and reads one zdim-wide row per encoder token per layer instead of 2*H*d_kv: 24x fewer
+ * cross-attention bytes per decode step for YPTF.MoE+Multi.  Same function, different association order, hence
+ * bf16 only; the fp32 token-exact path keeps the reference order.  zdim must be 256, H <= 8. */
+YMT3_API int ymt3_t5dec_generate_latent(ymt3_t5dec_t* dec, const void* latents_dev, int64_t B, int64_t T_enc, int32_t C,
+                                        const int32_t* prefix_ids_dev, int32_t P, int32_t max_len, int32_t stop_at_eos,
+                                        int32_t early_stop_interval, int32_t* tokens_out_dev, void* stream);
 /* fp32 logits of the LAST executed step, (N, vocab) (for logit-tolerance tests) */
 YMT3_API int ymt3_t5dec_last_logits(ymt3_t5dec_t* dec, float* logits_out_dev, int64_t N, void* stream);
 
@@ -255,6 +271,10 @@ YMT3_API int ymt3_op_layernorm(int32_t dtype, const void* x, const float* w, con
 YMT3_API int ymt3_op_attention(int32_t dtype, const void* q, const void* k, const void* v, void* o, int64_t B,
                                int64_t H, int64_t Sq, int64_t Sk, int64_t dk, float scale, int32_t causal,
                                void* stream);
+/* Absorbed cross-attention kernel alone (see ymt3_t5dec_generate_latent): q (N, H*256) bf16, z (N, Tp, 256) bf16 with
+ * rows >= T zero, out (N, H*256) bf16 = per head softmax_t(q_h . z_t) z_t;  Tp % 16 == 0, H <= 8. */
+YMT3_API int ymt3_op_cross_attn_absorbed(const void* q, const void* z, void* out, int64_t N, int64_t H, int64_t T,
+                                         int64_t Tp, void* stream);
 
 #ifdef __cplusplus
 }

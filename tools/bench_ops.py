@@ -66,6 +66,28 @@ if what in ("gemm", "all"):
     gemm(16384, 1152, 512, name="t5 enc qkv B=64")
     gemm(8192, 8192, 8192, name="square 8k")
 
+if what in ("decode", "all"):
+    # the GEMMs of one YPTF.MoE+Multi decode step at B=256 (N = 3328 sequences)
+    M = 3328
+    gemm(M, 1152, 512, name="dec self qkv")
+    gemm(M, 512, 384, residual=True, name="dec self o+res")
+    gemm(M, 384, 512, name="dec cross q (K/V mode)")
+    gemm(M, 1536, 512, name="dec cross q absorbed")
+    gemm(M, 512, 1536, residual=True, name="dec cross o absorbed+res")
+    gemm(M, 2048, 512, gated=1, act=1, name="dec ffn wi")
+    gemm(M, 512, 1024, residual=True, name="dec ffn wo+res")
+    gemm(M, 600, 512, name="dec lm head")
+    for (N, H, T) in [(3328, 6, 110), (832, 6, 110)]:
+        Tp = (T + 15) // 16 * 16
+        q = torch.randn(N, H * 256, device=dev).bfloat16()
+        z = torch.zeros(N, Tp, 256, device=dev, dtype=torch.bfloat16)
+        z[:, :T] = torch.randn(N, T, 256, device=dev).bfloat16()
+        o = torch.empty_like(q)
+        s_ = torch.cuda.current_stream().cuda_stream
+        us = timeit(lambda: _lib.check(lib.ymt3_op_cross_attn_absorbed(q.data_ptr(), z.data_ptr(), o.data_ptr(), N, H, T, Tp, s_)))
+        byts = z.numel() * 2 + 2 * q.numel() * 2
+        print(f"cross_attn_absorbed N={N} H={H} T={T}: {us:8.1f} us  {byts / us / 1e3:8.1f} GB/s (z + q + out bytes)", flush=True)
+
 if what in ("decode_attn", "all"):
     # self-attention over a bf16 cache at length L for N sequences x 6 heads, via the generic attention op
     pass

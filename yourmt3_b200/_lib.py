@@ -89,6 +89,8 @@ SIGNATURES = {
     "ymt3_t5dec_destroy": (_I, [_P]),
     "ymt3_t5dec_generate": (_I, [_P, _P, _I64, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ymt3_t5dec_generate_prefixed": (_I, [_P, _P, _I64, _I64, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "ymt3_t5dec_generate_latent": (_I, [_P, _P, _I64, _I64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,
+                                        _P]),
     "ymt3_t5dec_last_logits": (_I, [_P, _P, _I64, _P]),
     "ymt3_res3b_create": (_I, [C.POINTER(Res3bCfg), C.POINTER(Tensor), _I, C.POINTER(_P)]),
     "ymt3_res3b_destroy": (_I, [_P]),
@@ -103,6 +105,7 @@ SIGNATURES = {
     "ymt3_op_rmsnorm": (_I, [C.c_int32, _P, _P, _P, _I64, _I64, C.c_float, _P]),
     "ymt3_op_layernorm": (_I, [C.c_int32, _P, _P, _P, _P, _I64, _I64, C.c_float, _P]),
     "ymt3_op_attention": (_I, [C.c_int32, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, C.c_float, C.c_int32, _P]),
+    "ymt3_op_cross_attn_absorbed": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
 }
 
 

@@ -1,5 +1,6 @@
 // Per-op C-ABI entry points (include/ymt3_b200.h, "Per-op entry points").
 #include "ops.cuh"
+#include "decode.cuh"
 #include "../../include/ymt3_b200.h"
 
 using namespace ymt3;
@@ -42,4 +43,10 @@ extern "C" int ymt3_op_attention(int32_t dtype, const void* q, const void* k, co
   a.B = (int)B; a.H = (int)H; a.Sq = (int)Sq; a.Sk = (int)Sk; a.dk = (int)dk;
   a.scale = scale; a.causal = causal;
   return attention(a, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int ymt3_op_cross_attn_absorbed(const void* q, const void* z, void* out, int64_t N, int64_t H, int64_t T,
+                                           int64_t Tp, void* stream) {
+  YMT3_REQUIRE(q && z && out, "op_cross_attn_absorbed: null argument");
+  return cross_attn_absorbed(q, H * 256, z, out, H * 256, N, (int)H, (int)T, (int)Tp, 256, (cudaStream_t)stream);
 }

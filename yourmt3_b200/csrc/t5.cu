@@ -13,6 +13,7 @@ namespace {
 struct T5Layer {
   float* ln_sa = nullptr;  Linear qkv, o;           // layer.0 SelfAttention (q|k|v stacked)
   float* ln_ca = nullptr;  Linear xq, xkv, xo;      // layer.1 EncDecAttention (decoder only; k|v stacked)
+  Linear xq_abs, xo_abs;                            // optional absorbed cross-attention (latent-space q / o + bias)
   float* ln_ff = nullptr;  Linear wi, wo;           // DenseReluDense (wi_0/wi_1 interleaved -> gated epilogue)
 };
 
@@ -194,6 +195,12 @@ struct ymt3_t5dec {
   int32_t* graph_tokens = nullptr;
   int* d_forced = nullptr;   // (cap_N, cap_P) task-prefix tokens
   int64_t cap_P = 0;
+  // absorbed cross-attention (bf16, cross_absorbed.cu): present when the tensor table carried *.q_absorbed.weight
+  int zdim = 0;              // latent width (0 = not available)
+  int cap_latent = -1;       // workspace currently laid out for: 0 = K/V mode, 1 = latent mode
+  int64_t cap_Tp = 0;
+  void *zbuf = nullptr, *qz = nullptr, *cz = nullptr;   // (N, Tp, zdim) latents, (N, H*zdim) queries / contexts
+  int graph_latent = -1;
 };
 
 extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* tensors, int n, ymt3_t5dec_t** out) {
@@ -207,6 +214,26 @@ extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
   TensorTable tt{tensors, n};
   const int D = cfg->d_model, V = cfg->vocab_size;
   rc = load_layers(*cfg, tt, true, d->weights, d->layers, &d->final_ln, 0);
+  if (!rc) {
+    // optional absorbed cross-attention weights (host-folded, see include/ymt3_b200.h)
+    const std::string k0 = "block.0.layer.1.EncDecAttention.q_absorbed.weight";
+    if (const ymt3_tensor_t* q0 = tt.find(k0)) {
+      if (cfg->precision != YMT3_BF16 || q0->ndim != 2 || q0->shape[1] != D || q0->shape[0] % cfg->num_heads) {
+        ymt3_set_error("t5dec_create: absorbed cross-attention needs bf16 precision and (H*zdim, d_model) weights");
+        rc = YMT3_ERR_INVALID;
+      } else {
+        d->zdim = (int)(q0->shape[0] / cfg->num_heads);
+        const int HZ = cfg->num_heads * d->zdim;
+        for (int i = 0; !rc && i < cfg->num_layers; ++i) {
+          const std::string ca = "block." + std::to_string(i) + ".layer.1.EncDecAttention.";
+          T5Layer& L = d->layers[i];
+          rc = pack_rows(d->weights, {tt.require(ca + "q_absorbed.weight", HZ, D)}, D, YMT3_BF16, false, &L.xq_abs, 0);
+          if (!rc) rc = pack_rows(d->weights, {tt.require(ca + "o_absorbed.weight", D, HZ)}, HZ, YMT3_BF16, false, &L.xo_abs, 0);
+          if (!rc) rc = pack_vec(d->weights, {tt.require(ca + "o_absorbed.bias", D)}, false, &L.xo_abs.bias, 0);
+        }
+      }
+    }
+  }
   if (!rc) {
     const ymt3_tensor_t* E = tt.require("embed_tokens.weight", V, D);
     if (!E) rc = YMT3_ERR_INVALID;
@@ -272,8 +299,8 @@ extern "C" int ymt3_t5dec_destroy(ymt3_t5dec_t* d) {
 
 namespace {
 
-int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, cudaStream_t s) {
-  if (N <= d->cap_N && T <= d->cap_T && Lmax <= d->cap_L) return YMT3_OK;
+int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, int latent, cudaStream_t s) {
+  if (N <= d->cap_N && T <= d->cap_T && Lmax <= d->cap_L && latent == d->cap_latent) return YMT3_OK;
   YMT3_CUDA_CHECK(cudaStreamSynchronize(s));
   if (d->graph) {
     cudaGraphExecDestroy(d->graph);
@@ -284,6 +311,7 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, cudaStream_t s
   d->d_forced = nullptr;
   d->cap_P = 0;
   d->cap_N = d->cap_T = d->cap_L = 0;
+  d->cap_latent = -1;
   const ymt3_t5_cfg_t& c = d->c;
   const int D = c.d_model, inner = c.num_heads * c.d_kv, F = c.d_ff;
   const size_t es = dtype_size(c.precision);
@@ -295,7 +323,17 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, cudaStream_t s
   d->qx = d->ws.alloc(cN * inner * es);
   d->g = d->ws.alloc(cN * F * es);
   d->logits = (float*)d->ws.alloc(cN * d->Vp * 4);
-  d->kv_tmp = d->ws.alloc(cN * cT * 2 * inner * es);
+  const int64_t cTp = (cT + 15) / 16 * 16;
+  if (latent) {
+    // latent mode: no per-layer K/V at all; one padded latent tile per sequence (pad rows stay zero)
+    const size_t zb = (size_t)cN * cTp * d->zdim * es;
+    d->kv_tmp = d->zbuf = d->ws.alloc(zb);
+    d->qz = d->ws.alloc((size_t)cN * c.num_heads * d->zdim * es);
+    d->cz = d->ws.alloc((size_t)cN * c.num_heads * d->zdim * es);
+    if (!d->zbuf || !d->qz || !d->cz) d->kv_tmp = nullptr;
+  } else {
+    d->kv_tmp = d->ws.alloc(cN * cT * 2 * inner * es);
+  }
   d->d_cur = (int*)d->ws.alloc(cN * 4);
   d->d_fin = (int*)d->ws.alloc(cN * 4);
   bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->kv_tmp;
@@ -305,20 +343,22 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, cudaStream_t s
   for (int i = 0; ok && i < c.num_layers; ++i) {
     d->selfK[i] = d->ws.alloc(cN * inner * cL * es);
     d->selfV[i] = d->ws.alloc(cN * inner * cL * es);
-    d->crossKV[i] = d->ws.alloc(cN * cT * 2 * inner * es);
-    ok = d->selfK[i] && d->selfV[i] && d->crossKV[i];
+    if (!latent) d->crossKV[i] = d->ws.alloc(cN * cT * 2 * inner * es);
+    ok = d->selfK[i] && d->selfV[i] && (latent || d->crossKV[i]);
   }
   if (!ok) {
     d->ws.release();
     return YMT3_ERR_CUDA;
   }
   d->cap_N = cN; d->cap_T = cT; d->cap_L = cL;
+  d->cap_Tp = cTp;
+  d->cap_latent = latent;
   return YMT3_OK;
 }
 
 // all kernels of ONE decode step; every step-dependent value is read from device memory
 int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int32_t* tokens_out, int n_prefix,
-             cudaStream_t s) {
+             int latent, cudaStream_t s) {
   const ymt3_t5_cfg_t& c = d->c;
   const int D = c.d_model, H = c.num_heads, dk = c.d_kv, inner = H * dk, F = c.d_ff, dt = c.precision;
   const size_t es = dtype_size(dt);
@@ -336,12 +376,20 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
     if ((rc = linear_fwd(dt, d->attn, inner, L.o, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
     // cross-attention over encoder K/V computed once (modeling_t5.py:387-408)
     if ((rc = rmsnorm(d->x, L.ln_ca, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
+    if (latent) {
+      // absorbed form: latent-space query, attention over the shared latent tile, folded (Wo Wv Wp) output
+      const int HZ = H * d->zdim;
+      if ((rc = linear_fwd(dt, d->h, D, L.xq_abs, d->qz, HZ, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
+      if ((rc = cross_attn_absorbed(d->qz, HZ, d->zbuf, d->cz, HZ, N, H, (int)T, (int)((T + 15) / 16 * 16), d->zdim, s))) return rc;
+      if ((rc = linear_fwd(dt, d->cz, HZ, L.xo_abs, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
+    } else {
     if ((rc = linear_fwd(dt, d->h, D, L.xq, d->qx, inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
     if ((rc = decode_attention(d->qx, inner, nullptr, nullptr, 0, d->crossKV[i],
                                (char*)d->crossKV[i] + (size_t)N * inner * T * es, (int64_t)H * T * dk, T * dk, dk, 0,
                                d->d_step, (int)T, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
       return rc;
     if ((rc = linear_fwd(dt, d->attn, inner, L.xo, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
+    }
     // gated-GELU feed-forward
     if ((rc = rmsnorm(d->x, L.ln_ff, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
     if ((rc = linear_fwd(dt, d->h, D, L.wi, d->g, F, (int)N, YMT3_ACT_GELU_NEW, 1, nullptr, 0, 1.f, dt, s))) return rc;
@@ -365,9 +413,34 @@ extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t 
                                       stream);
 }
 
+namespace {
+int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int latent_channels,
+                  const int32_t* prefix_ids, int32_t P, int32_t max_len, int32_t stop_at_eos,
+                  int32_t early_stop_interval, int32_t* tokens_out, void* stream);
+}
+
 extern "C" int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T,
                                             const int32_t* prefix_ids, int32_t P, int32_t max_len, int32_t stop_at_eos,
                                             int32_t early_stop_interval, int32_t* tokens_out, void* stream) {
+  return generate_impl(d, enc_hs, N, T, 0, prefix_ids, P, max_len, stop_at_eos, early_stop_interval, tokens_out, stream);
+}
+
+extern "C" int ymt3_t5dec_generate_latent(ymt3_t5dec_t* d, const void* latents, int64_t B, int64_t T, int32_t C,
+                                          const int32_t* prefix_ids, int32_t P, int32_t max_len, int32_t stop_at_eos,
+                                          int32_t early_stop_interval, int32_t* tokens_out, void* stream) {
+  YMT3_REQUIRE(d && d->zdim > 0, "t5dec_generate_latent: handle was created without absorbed cross-attention weights");
+  YMT3_REQUIRE(C >= 1, "t5dec_generate_latent: bad channel count %d", C);
+  return generate_impl(d, latents, B * C, T, C, prefix_ids, P, max_len, stop_at_eos, early_stop_interval, tokens_out,
+                       stream);
+}
+
+namespace {
+// latent_channels == 0: enc_hs is (N, T, d_model), cross K/V per layer.  > 0: enc_hs is the encoder latent array
+// (N / C, T, C, zdim) and the cross-attention runs in its absorbed form.
+int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int latent_channels,
+                  const int32_t* prefix_ids, int32_t P, int32_t max_len, int32_t stop_at_eos,
+                  int32_t early_stop_interval, int32_t* tokens_out, void* stream) {
+  const int latent = latent_channels > 0;
   YMT3_REQUIRE(d && tokens_out, "t5dec_generate: null argument");
   if (N <= 0) return YMT3_OK;
   YMT3_REQUIRE(enc_hs && T > 0, "t5dec_generate: bad encoder states");
@@ -387,7 +460,7 @@ extern "C" int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* d, const void* enc_hs,
     YMT3_CUDA_CHECK(cudaEventRecord(d->ev_in, caller));
     YMT3_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_in, 0));
   }
-  if ((rc = dec_ensure(d, N, T, max_len + P, s))) return rc;
+  if ((rc = dec_ensure(d, N, T, max_len + P, latent, s))) return rc;
   if (P > 0) {
     if (N * P > d->cap_P) {
       YMT3_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -403,8 +476,14 @@ extern "C" int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* d, const void* enc_hs,
   if ((rc = fill_i32(d->d_cur, c.start_id, N, s))) return rc;
   if ((rc = fill_i32(d->d_fin, 0, N, s))) return rc;
   if ((rc = fill_i32(tokens_out, c.pad_id, N * max_len, s))) return rc;
+  if (latent) {
+    // the only per-call encoder-side work: latents regrouped per sequence (channel-major), time padded to 16
+    const int64_t Tp = (T + 15) / 16 * 16;
+    if (Tp != T) YMT3_CUDA_CHECK(cudaMemsetAsync(d->zbuf, 0, (size_t)N * Tp * d->zdim * dtype_size(dt), s));
+    if ((rc = gather_latents(enc_hs, d->zbuf, N / latent_channels, (int)T, latent_channels, (int)Tp, d->zdim, s))) return rc;
+  }
   // cross-attention K/V of every layer, once (modeling_t5.py:287-299)
-  for (int i = 0; i < c.num_layers; ++i) {
+  for (int i = 0; !latent && i < c.num_layers; ++i) {
     if ((rc = linear_fwd(dt, enc_hs, D, d->layers[i].xkv, d->kv_tmp, 2 * inner, (int)(N * T), 0, 0, nullptr, 0, 1.f, dt,
                          s)))
       return rc;
@@ -417,14 +496,15 @@ extern "C" int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* d, const void* enc_hs,
   // one decode step captured into a CUDA graph (all step-dependent scalars live on the device)
   const bool use_graph = getenv("YMT3_NO_GRAPH") == nullptr && !caller_capturing;
   if (use_graph && (!d->graph || d->graph_N != N || d->graph_T != T || d->graph_L != max_len ||
-                    d->graph_tokens != tokens_out || d->graph_stop != stop_at_eos || d->graph_prefix != P)) {
+                    d->graph_tokens != tokens_out || d->graph_stop != stop_at_eos || d->graph_prefix != P ||
+                    d->graph_latent != latent)) {
     if (d->graph) {
       cudaGraphExecDestroy(d->graph);
       d->graph = nullptr;
     }
     cudaGraph_t g = nullptr;
     YMT3_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, P, s);
+    rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, P, latent, s);
     cudaError_t ce = cudaStreamEndCapture(s, &g);
     if (rc) {
       if (g) cudaGraphDestroy(g);
@@ -438,11 +518,12 @@ extern "C" int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* d, const void* enc_hs,
     d->graph_tokens = tokens_out;
     d->graph_stop = stop_at_eos;
     d->graph_prefix = P;
+    d->graph_latent = latent;
   }
   for (int t = 0; t < max_len + P; ++t) {
     if (use_graph) {
       YMT3_CUDA_CHECK(cudaGraphLaunch(d->graph, s));
-    } else if ((rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, P, s))) {
+    } else if ((rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, P, latent, s))) {
       return rc;
     }
     if (stop_at_eos && early_stop_interval > 0 && (t + 1) % early_stop_interval == 0 && t + 1 < max_len + P) {
@@ -458,6 +539,7 @@ extern "C" int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* d, const void* enc_hs,
   }
   return YMT3_OK;
 }
+}  // namespace
 
 extern "C" int ymt3_t5dec_last_logits(ymt3_t5dec_t* d, float* out, int64_t N, void* stream) {
   YMT3_REQUIRE(d && out && N <= d->cap_N, "t5dec_last_logits: bad argument");

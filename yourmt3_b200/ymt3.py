@@ -36,6 +36,9 @@ class YourMT3(nn.Module):
         self._prec = {"f32": _lib.DTYPE_F32, "bf16": _lib.DTYPE_BF16}[precision]
         self.eos_id, self.pad_id = eos_id, pad_id
         self.decode_lanes = 1   # >1: concurrent decode lanes (see t5mod_helper.task_cond_dec_generate)
+        # bf16 multi-channel models: run the decoder's cross-attention in absorbed form on the encoder latents
+        # (same function, 24x fewer cross-attention bytes per step; include/ymt3_b200.h ymt3_t5dec_generate_latent)
+        self.absorb_cross_attention = True
         self.encoder_type, self.decoder_type = model_cfg["encoder_type"], model_cfg["decoder_type"]
         self.vocab_size = int(model_cfg["vocab_size"])
         self.max_token_length = int(model_cfg["event_length"])
@@ -99,12 +102,29 @@ class YourMT3(nn.Module):
                   early_stop_interval: int = 0, decode_lanes: Optional[int] = None, **unused) -> torch.Tensor:
         """x: (B, 1, L) audio segments -> token ids (B, L_tok) or (B, C, L_tok) (LongTensor, CUDA)."""
         max_len = max_token_length or self.max_token_length
+        if self._absorbed():
+            feats = self.pre_encoder(self.spectrogram(x))
+            return self._generate_absorbed(self.encoder(inputs_embeds=feats)["last_hidden_state"], task_tokens, max_len,
+                                           stop_at_eos, early_stop_interval)
         enc_hs = self.encode(x)
         return task_cond_dec_generate(self.decoder, self.decoder_type, self.embed_tokens, self.lm_head, enc_hs,
                                       prefix_ids=task_tokens, max_length=max_len, stop_at_eos=stop_at_eos,
                                       eos_id=self.eos_id, pad_id=self.pad_id, decoder_start_token_id=self.pad_id,
                                       precision=self._prec, early_stop_interval=early_stop_interval,
                                       lanes=self.decode_lanes if decode_lanes is None else decode_lanes)
+
+    def _absorbed(self) -> bool:
+        return (self.absorb_cross_attention and self.precision == "bf16" and self.decoder_type == "multi-t5"
+                and getattr(self.pre_decoder, "kind", None) == "mc_shared_linear"
+                and self.pre_decoder.proj.in_features == 256 and self.decoder.config["num_heads"] <= 8
+                and self.feat_length <= 128)   # kernel limits (cross_absorbed.cu): zdim 256, <= 8 heads, T_enc <= 128
+
+    def _generate_absorbed(self, latents, task_tokens, max_len, stop_at_eos=True, early_stop_interval=0):
+        return task_cond_dec_generate(self.decoder, self.decoder_type, self.embed_tokens, self.lm_head, latents,
+                                      prefix_ids=task_tokens, max_length=max_len, stop_at_eos=stop_at_eos,
+                                      eos_id=self.eos_id, pad_id=self.pad_id, decoder_start_token_id=self.pad_id,
+                                      precision=self._prec, early_stop_interval=early_stop_interval,
+                                      cross_proj=self.pre_decoder.proj)
 
     @torch.no_grad()
     def transcribe_waveform(self, wave: torch.Tensor, bsz: int = 256, **kw) -> torch.Tensor:
@@ -115,6 +135,10 @@ class YourMT3(nn.Module):
         max_len = kw.pop("max_token_length", None) or self.max_token_length
         outs = []
         for i in range(0, feats.shape[0], bsz):
+            if self._absorbed():
+                lat = self.encoder(inputs_embeds=self.pre_encoder(feats[i:i + bsz]))["last_hidden_state"]
+                outs.append(self._generate_absorbed(lat, None, max_len, kw.get("stop_at_eos", True)))
+                continue
             enc_hs = self.pre_decoder(self.encoder(inputs_embeds=self.pre_encoder(feats[i:i + bsz]))["last_hidden_state"])
             outs.append(task_cond_dec_generate(self.decoder, self.decoder_type, self.embed_tokens, self.lm_head, enc_hs,
                                                max_length=max_len, stop_at_eos=kw.get("stop_at_eos", True),

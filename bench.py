@@ -188,7 +188,7 @@ def cpu_baseline(wl, budget_s=12.0):
             break
     scale = wl.reference_scale() if hasattr(wl, "reference_scale") else 1.0
     return {"value": wl.ref_batch * SEG_SECONDS * n / dt * scale, "unit": "audio-s/s", "cores": torch.get_num_threads(),
-            "kind": "reference", "sample": wl.reference_sample() + f", {n} steps in {dt:.1f}s"}
+            "kind": "port", "sample": wl.reference_sample() + f", {n} steps in {dt:.1f}s"}
 
 
 def run_reference(args):
@@ -211,7 +211,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": wl.config(),
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": torch.get_num_threads(),
-                             "kind": "reference", "sample": wl.reference_sample()},
+                             "kind": "port", "sample": wl.reference_sample()},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -280,22 +280,21 @@ def run_native(args):
         peaks = measured_peaks()
         units = wl.batch * world
         value = units * SEG_SECONDS * args.steps / (total_ms * 1e-3)
-        kern_ms = sorted(per_step)[len(per_step) // 2] if not hasattr(wl, "dominant_kernel_ms") else wl.dominant_kernel_ms()
-        if wl.roofline_bound == "hbm":
-            achieved = wl.roofline_units() / (kern_ms * 1e-3) / 1e9
-            peak, unit = peaks["hbm_gbs"], "GB/s"
+        if hasattr(wl, "rooflines"):
+            roofs = wl.rooflines(peaks)     # model workloads: dominant decode kernel + the log-mel frontend kernel
         else:
-            achieved = wl.roofline_units() / (kern_ms * 1e-3) / 1e12
-            peak, unit = peaks["bf16_tflops_sustained"], "TFLOP/s"
+            # frontend workload: the step IS one launch of the log-mel kernel
+            kern_ms = sorted(per_step)[len(per_step) // 2]
+            achieved = wl.roofline_units() / (kern_ms * 1e-3) / 1e9
+            roofs = {"roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                  "frac": achieved / peaks["hbm_gbs"], "traffic": getattr(wl, "ncu_traffic_bytes", None),
+                                  "peak_source": peaks["source"], "kernel": "ymt3_logmel_kernel", "kernel_ms": kern_ms}}
         line = {
             "metric": "audio_seconds_per_wall_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
             "data": "synthetic", "config": wl.config(),
-            "roofline": {"bound": wl.roofline_bound, "achieved": achieved, "peak": peak, "unit": unit,
-                         "frac": achieved / peak, "traffic": getattr(wl, "ncu_traffic_bytes", None),
-                         "peak_source": peaks["source"], "kernel": getattr(wl, "dominant_kernel", "ymt3_logmel_kernel"),
-                         "kernel_ms": kern_ms},
+            **roofs,
             "e2e": {"value": wl.e2e_batch * world * SEG_SECONDS * n_e2e / e_dt, "unit": "audio-s/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": wl.launches_per_step * args.steps,

@@ -271,6 +271,13 @@ YMT3_API int ymt3_op_layernorm(int32_t dtype, const void* x, const float* w, con
 YMT3_API int ymt3_op_attention(int32_t dtype, const void* q, const void* k, const void* v, void* o, int64_t B,
                                int64_t H, int64_t Sq, int64_t Sk, int64_t dk, float scale, int32_t causal,
                                void* stream);
+/* Single-query attention over a device-resident KV cache alone (the decode step's dominant kernel; HF
+ * modeling_t5.py:269-305 with use_cache): q (N, H*64); cache K/V (N, H, Lcap, 64).  knew/vnew (N, H*64) non-null:
+ * self mode - the row is appended at index *step_dev, then keys [0, *step_dev] are attended.  knew == NULL: cross
+ * mode over keys [0, fixed_len).  out (N, H*64).  No scaling (T5). */
+YMT3_API int ymt3_op_decode_attention(int32_t dtype, const void* q, const void* knew, const void* vnew, void* Kc,
+                                      void* Vc, const int32_t* step_dev, int64_t fixed_len, void* out, int64_t N,
+                                      int64_t H, int64_t Lcap, void* stream);
 /* Absorbed cross-attention kernel alone (see ymt3_t5dec_generate_latent): q (N, H*256) bf16, z (N, Tp, 256) bf16 with
  * rows >= T zero, out (N, H*256) bf16 = per head softmax_t(q_h . z_t) z_t;  Tp % 16 == 0, H <= 8. */
 YMT3_API int ymt3_op_cross_attn_absorbed(const void* q, const void* z, void* out, int64_t N, int64_t H, int64_t T,

@@ -183,3 +183,36 @@ def test_norm_attention_bf16_io(cuda_device, native_lib):
     _lib.check(native_lib.ymt3_op_attention(1, qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, H, Sq, Sk, dk,
                                             1.0, 0, s))
     _close(o.float().cpu(), ref, 6e-3)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("N,H,step,Lcap", [(5, 6, 0, 16), (7, 6, 37, 64), (300, 6, 200, 256)])
+def test_decode_attention_self_and_cross(cuda_device, native_lib, dtype, N, H, step, Lcap):
+    """single-query attention over the KV cache (decode.cu) vs plain torch fp32: self mode appends the new K/V row at
+    *step and attends [0, step]; cross mode attends [0, fixed_len)."""
+    td, code = (torch.float32, 0) if dtype == "f32" else (torch.bfloat16, 1)
+    g = torch.Generator().manual_seed(N + step)
+    q = (torch.randn(N, H, 64, generator=g) * 0.5).to(cuda_device, td)
+    kn = torch.randn(N, H, 64, generator=g).to(cuda_device, td)
+    vn = torch.randn(N, H, 64, generator=g).to(cuda_device, td)
+    Kc = torch.randn(N, H, Lcap, 64, generator=g).to(cuda_device, td)
+    Vc = torch.randn(N, H, Lcap, 64, generator=g).to(cuda_device, td)
+    K0, V0 = Kc.clone(), Vc.clone()
+    st = torch.tensor([step], dtype=torch.int32, device=cuda_device)
+    out = torch.empty(N, H, 64, dtype=td, device=cuda_device)
+    s = _lib.current_stream_ptr()
+    _lib.check(native_lib.ymt3_op_decode_attention(code, q.data_ptr(), kn.data_ptr(), vn.data_ptr(), Kc.data_ptr(),
+                                                   Vc.data_ptr(), st.data_ptr(), 0, out.data_ptr(), N, H, Lcap, s))
+    assert torch.equal(Kc[:, :, step], kn) and torch.equal(Vc[:, :, step], vn)           # appended in place
+    assert torch.equal(Kc[:, :, step + 1:], K0[:, :, step + 1:])                         # nothing else touched
+    Kr, Vr = Kc[:, :, :step + 1].float(), Vc[:, :, :step + 1].float()
+    p = torch.softmax(torch.einsum("nhd,nhld->nhl", q.float(), Kr), -1)
+    ref = torch.einsum("nhl,nhld->nhd", p, Vr)
+    tol = 2e-5 if dtype == "f32" else 2e-2
+    assert float((out.float() - ref).abs().max()) < tol
+    L = step + 1
+    _lib.check(native_lib.ymt3_op_decode_attention(code, q.data_ptr(), None, None, K0.data_ptr(), V0.data_ptr(), None,
+                                                   L, out.data_ptr(), N, H, Lcap, s))
+    p = torch.softmax(torch.einsum("nhd,nhld->nhl", q.float(), K0[:, :, :L].float()), -1)
+    ref = torch.einsum("nhl,nhld->nhd", p, V0[:, :, :L].float())
+    assert float((out.float() - ref).abs().max()) < tol

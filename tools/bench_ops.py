@@ -89,5 +89,17 @@ if what in ("decode", "all"):
         print(f"cross_attn_absorbed N={N} H={H} T={T}: {us:8.1f} us  {byts / us / 1e3:8.1f} GB/s (z + q + out bytes)", flush=True)
 
 if what in ("decode_attn", "all"):
-    # self-attention over a bf16 cache at length L for N sequences x 6 heads, via the generic attention op
-    pass
+    # self-attention over a bf16 KV cache (decode.cu) at the YPTF.MoE+Multi B=256 shape, cache length L
+    N, H, Lcap = 3328, 6, 256
+    q = torch.randn(N, H * 64, device=dev).bfloat16()
+    kn, vn, o = torch.randn_like(q), torch.randn_like(q), torch.empty_like(q)
+    Kc = torch.randn(N, H, Lcap, 64, device=dev).bfloat16()
+    Vc = torch.randn(N, H, Lcap, 64, device=dev).bfloat16()
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    s_ = torch.cuda.current_stream().cuda_stream
+    for L in ([128] if once else [16, 64, 128, 192, 256]):
+        st.fill_(L - 1)
+        us = timeit(lambda: _lib.check(lib.ymt3_op_decode_attention(1, q.data_ptr(), kn.data_ptr(), vn.data_ptr(), Kc.data_ptr(),
+                                                                    Vc.data_ptr(), st.data_ptr(), 0, o.data_ptr(), N, H, Lcap, s_)))
+        byts = N * H * 64 * 2 * (2 * L + 6)
+        print(f"decode_attn N={N} H={H} len={L}: {us:8.1f} us  {byts / us / 1e3:8.1f} GB/s (algorithmic)", flush=True)

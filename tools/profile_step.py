@@ -1,5 +1,5 @@
 """Small driver for ncu: run a few decode steps (and optionally the encoder) of a preset so the
-per-kernel launch list can be captured.  usage: python tools/profile_step.py PRESET BATCH STEPS [precision]"""
+per-kernel launch list can be captured.  usage: python tools/profile_step.py PRESET BATCH STEPS [precision] [runs]"""
 import os
 import sys
 
@@ -18,7 +18,8 @@ ymt3.init_nondegenerate_(m, 0)
 m = m.cuda()
 m.decode_lanes = lanes
 x = torch.randn(batch, 1, 32767, device="cuda") * 0.1
-for _ in range(2):
+runs = int(sys.argv[5]) if len(sys.argv) > 5 else 2
+for _ in range(runs):
     t = m.inference(x, max_token_length=steps, stop_at_eos=False)
 torch.cuda.synchronize()
 print("ok", tuple(t.shape))

@@ -23,7 +23,11 @@ DEFAULT = "yptf_moe_multi"   # the model BASELINE.json quotes the target on
 
 class ModelWorkload:
     roofline_bound = "hbm"
-    dominant_kernel = "ymt3_logmel_kernel"
+    dominant_kernel = "decode_attn_kernel"
+    # dram__bytes_read + dram__bytes_write of ONE decode_attn_kernel launch at cache length 128 for 3328 x 6 (sequence,
+    # head) pairs, from `ncu --set full` (profiles/r01_cross_absorbed_v3_and_decode_attn_len128_ncu_full.txt, launch 2:
+    # 657.4 MB read + 11.3 MB written; algorithmic 669.6 MB)
+    NCU_DECODE_ATTN_TRAFFIC_3328x6_L128 = 657.416704e6 + 11.324672e6
 
     def __init__(self, name, batch):
         self.name = name
@@ -75,6 +79,68 @@ class ModelWorkload:
     def e2e_bytes(self):
         return self.batch * SEG_SAMPLES * 4, self.batch * self.channels * self.max_len * 8
 
+    def rooflines(self, peaks):
+        """{"roofline": dominant kernel of the step, "roofline_frontend": the log-mel kernel (metric (ii))}.
+
+        The dominant kernel of every model workload is ``decode_attn_kernel`` (self-attention of one decoder layer
+        over the device-resident KV cache; 8 launches per step, ~40-50 % of the step, see tools/time_phases.py).  It is
+        timed ALONE here through the C ABI (``ymt3_op_decode_attention``) at the workload's own shape
+        (N = batch x channels sequences, 6 heads x 64, bf16/f32 cache) over a uniform sample of the cache lengths the
+        decode loop visits (8, 24, ..., 248 of 256 -> mean 128), CUDA events, median of 5 per length.  Algorithmic
+        bytes per launch = N*H*64*es*(2*len + 6): K and V rows [0, len) read once, q / new k / new v read, new k / v
+        appended, out written."""
+        import ctypes  # noqa: F401
+        from . import _lib
+        torch = self.torch
+        lib = _lib.load()
+        dev = self.dev_in.device
+        cfg = self.model.model_cfg["decoder"][self.model.decoder_type]
+        H, dk = cfg["num_heads"], cfg.get("d_kv", 64)
+        N, Lcap = self.batch * self.channels, self.max_len
+        td = _lib.torch_dtype(self.model._prec)
+        es = 2 if td == torch.bfloat16 else 4
+        q = torch.randn(N, H * dk, device=dev).to(td)
+        kn, vn, out = torch.randn_like(q), torch.randn_like(q), torch.empty_like(q)
+        Kc = torch.randn(N, H, Lcap, dk, device=dev).to(td)
+        Vc = torch.randn(N, H, Lcap, dk, device=dev).to(td)
+        step = torch.zeros(1, dtype=torch.int32, device=dev)
+        s = _lib.current_stream_ptr()
+        tot_ms, tot_bytes, n = 0.0, 0.0, 0
+        for ln in range(8, Lcap + 1, 16):
+            step.fill_(ln - 1)
+            ts = []
+            for i in range(7):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _lib.check(lib.ymt3_op_decode_attention(self.model._prec, q.data_ptr(), kn.data_ptr(), vn.data_ptr(),
+                                                        Kc.data_ptr(), Vc.data_ptr(), step.data_ptr(), 0, out.data_ptr(),
+                                                        N, H, Lcap, s), "decode_attention")
+                b.record()
+                b.synchronize()
+                if i >= 2:
+                    ts.append(a.elapsed_time(b))
+            ts.sort()
+            tot_ms += ts[len(ts) // 2]
+            tot_bytes += N * H * dk * es * (2 * ln + 6)
+            n += 1
+        kern_ms, alg = tot_ms / n, tot_bytes / n
+        achieved = alg / (kern_ms * 1e-3) / 1e9
+        traffic = self.NCU_DECODE_ATTN_TRAFFIC_3328x6_L128
+        if traffic is not None:
+            traffic = int(traffic * (N * H) / (3328.0 * 6) * (Lcap / 256.0) * (es / 2.0))
+        main = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
+                "kernel": "decode_attn_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg,
+                "launches_per_step": self.max_len * cfg["num_layers"],
+                "note": "self-attention over the KV cache, timed alone at this workload's shape, mean over cache lengths 8..%d" % Lcap}
+        f_ms = self.dominant_kernel_ms()
+        f_ach = self.roofline_units() / (f_ms * 1e-3) / 1e9
+        front = {"bound": "hbm", "achieved": f_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": f_ach / peaks["hbm_gbs"],
+                 "traffic": self.ncu_traffic_bytes, "peak_source": peaks["source"], "kernel": "ymt3_logmel_kernel",
+                 "kernel_ms": f_ms, "algorithmic_bytes_per_launch": self.roofline_units(), "launches_per_step": 1,
+                 "note": "compute-bound on the fp32 pipes (2048-point FFT per 128/300 new samples), see DESIGN.md 3.1"}
+        return {"roofline": main, "roofline_frontend": front}
+
     def dominant_kernel_ms(self):
         """log-mel kernel of this workload timed alone with CUDA events (median of 10)."""
         torch = self.torch
@@ -114,7 +180,9 @@ class ModelWorkload:
                 "encoder": m.encoder_type, "decoder": m.decoder_type, "channels": self.channels,
                 "decode_steps": self.max_len, "vocab": m.vocab_size, "weights": "random-init (non-degenerate, seed 0)",
                 "l2_policy": "per-step working set (activations + KV cache) larger than L2",
-                "roofline_kernel_note": "roofline object = log-mel kernel of this workload timed alone"}
+                "cross_attention": "absorbed (latent)" if (getattr(self, "model", None) is not None
+                                                           and self.model._absorbed()) else "k/v",
+                "roofline_kernel_note": "roofline = decode self-attention kernel (dominant); roofline_frontend = log-mel"}
 
     # ---- reference arm: same architecture through the CPU oracle (HF-pinned torch restatement) ----
     def setup_reference(self):

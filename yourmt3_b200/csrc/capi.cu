@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/ymt3_b200.h"
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[1024] = "";
 
@@ -23,6 +24,15 @@ int ymt3_num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool ymt3_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("YMT3_NO_PDL");
+    v = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 extern "C" const char* ymt3_last_error(void) { return g_err; }

@@ -42,3 +42,32 @@ static inline int ymt3_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) /
 
 // number of SMs of the current device (cached)
 int ymt3_num_sms();
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// The decode step is ~100 short dependent kernels replayed from a CUDA graph; with PDL the next kernel's CTAs are
+// scheduled (and run their prologue: barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel
+// drains, instead of after it has fully retired.  Contract: a kernel launched through ymt3_launch_pdl must call
+// pdl_wait() before its first access to global memory (griddepcontrol.wait returns once every prerequisite grid has
+// completed and its writes are visible, so RAW and WAR hazards are both covered) and pdl_launch_dependents() as
+// early as it likes.  Both are no-ops for ordinary launches.  YMT3_NO_PDL=1 disables the attribute (A/B timing).
+bool ymt3_pdl_enabled();
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t ymt3_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ymt3_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif

@@ -125,12 +125,14 @@ cross_attn_absorbed_kernel(const __grid_constant__ CUtensorMap mq, const __grid_
   const int lr = lane & 7, lm = lane >> 3;   // ldmatrix: this lane addresses row lr of matrix lm
   const int64_t stride = gridDim.x;
 
+  pdl_launch_dependents();   // prologue below touches only shared memory; global reads start after pdl_wait()
   if (tid == 0) {
     for (int i = 0; i < stages; ++i) mbar_init(bar0 + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < MAX_H * PLD; i += NTHREAD) P[i] = __float2bfloat16(0.f);   // rows >= H stay zero
   __syncthreads();
+  pdl_wait();
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mq) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mz) : "memory");
@@ -325,9 +327,8 @@ int cross_attn_absorbed(const void* q, int64_t q_ld, const void* z, void* out, i
   if ((rc = make_row_map(&mq, q, N * H, H))) return rc;
   if ((rc = make_row_map(&mz, z, N * Tp, Tp))) return rc;
   const int64_t grid = N < ymt3_num_sms() ? N : ymt3_num_sms();
-  cross_attn_absorbed_kernel<<<(unsigned)grid, NTHREAD, smem, stream>>>(mq, mz, (__nv_bfloat16*)out, out_ld, N, H, T, Tp,
-                                                                        stages);
-  YMT3_CUDA_CHECK(cudaGetLastError());
+  YMT3_CUDA_CHECK(ymt3_launch_pdl(cross_attn_absorbed_kernel, dim3((unsigned)grid), dim3(NTHREAD), smem, stream, mq, mz,
+                                  (__nv_bfloat16*)out, out_ld, N, H, T, Tp, stages));
   return YMT3_OK;
 }
 

@@ -19,6 +19,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) embed_pos_kernel(const int* __restrict__ tok, const T* __restrict__ E,
                                                         const T* __restrict__ pos, const int* __restrict__ step,
                                                         T* __restrict__ x, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x;
   const int t = tok[n];
   const int s = *step;
@@ -33,11 +35,11 @@ int embed_pos(const int* tok, const void* E, const void* pos, const int* step, v
               int dtype, cudaStream_t stream) {
   if (N <= 0) return YMT3_OK;
   if (dtype == YMT3_F32)
-    embed_pos_kernel<float><<<N, 128, 0, stream>>>(tok, (const float*)E, (const float*)pos, step, (float*)x, dim);
+    YMT3_CUDA_CHECK(ymt3_launch_pdl(embed_pos_kernel<float>, dim3(N), dim3(128), 0, stream, tok, (const float*)E,
+                                    (const float*)pos, step, (float*)x, dim));
   else
-    embed_pos_kernel<__nv_bfloat16><<<N, 128, 0, stream>>>(tok, (const __nv_bfloat16*)E, (const __nv_bfloat16*)pos,
-                                                          step, (__nv_bfloat16*)x, dim);
-  YMT3_CUDA_CHECK(cudaGetLastError());
+    YMT3_CUDA_CHECK(ymt3_launch_pdl(embed_pos_kernel<__nv_bfloat16>, dim3(N), dim3(128), 0, stream, tok,
+                                    (const __nv_bfloat16*)E, (const __nv_bfloat16*)pos, step, (__nv_bfloat16*)x, dim));
   return YMT3_OK;
 }
 
@@ -105,6 +107,8 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
                    const int* __restrict__ step, int fixed_len, float scale, T* __restrict__ out, int64_t out_ld, int H,
                    int64_t total) {
   constexpr int DK = 64, NG = 4, U = 4;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t pair = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);   // (n, h) index, h fastest
   if (pair >= total) return;
@@ -223,15 +227,14 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
   const int64_t total = (int64_t)N * H;
   const unsigned grid = (unsigned)((total + 3) / 4);
   if (dtype == YMT3_F32)
-    decode_attn_kernel<float><<<grid, 128, 0, stream>>>((const float*)q, q_ld, (const float*)knew, (const float*)vnew,
-                                                        new_ld, (float*)Kc, (float*)Vc, c_sn, c_sh, c_ss, step, fixed_len,
-                                                        scale, (float*)out, out_ld, H, total);
+    YMT3_CUDA_CHECK(ymt3_launch_pdl(decode_attn_kernel<float>, dim3(grid), dim3(128), 0, stream, (const float*)q, q_ld,
+                                    (const float*)knew, (const float*)vnew, new_ld, (float*)Kc, (float*)Vc, c_sn, c_sh,
+                                    c_ss, step, fixed_len, scale, (float*)out, out_ld, H, total));
   else
-    decode_attn_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(
-        (const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)knew, (const __nv_bfloat16*)vnew, new_ld,
-        (__nv_bfloat16*)Kc, (__nv_bfloat16*)Vc, c_sn, c_sh, c_ss, step, fixed_len, scale, (__nv_bfloat16*)out, out_ld, H,
-        total);
-  YMT3_CUDA_CHECK(cudaGetLastError());
+    YMT3_CUDA_CHECK(ymt3_launch_pdl(decode_attn_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream,
+                                    (const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)knew,
+                                    (const __nv_bfloat16*)vnew, new_ld, (__nv_bfloat16*)Kc, (__nv_bfloat16*)Vc, c_sn,
+                                    c_sh, c_ss, step, fixed_len, scale, (__nv_bfloat16*)out, out_ld, H, total));
   return YMT3_OK;
 }
 
@@ -243,6 +246,8 @@ greedy_select_kernel(const float* __restrict__ logits, int64_t ld, int V, int N,
                      int* __restrict__ cur_tok, int* __restrict__ finished, int* __restrict__ tokens_out,
                      int max_len, int eos_id, int pad_id, int stop_at_eos, int* __restrict__ unfinished_count,
                      const int* __restrict__ forced, int n_forced) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= N) return;
   const float* row = logits + (int64_t)n * ld;
@@ -288,23 +293,23 @@ int greedy_select(const float* logits, int64_t ld, int V, int N, const int* step
                   int* tokens_out, int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count,
                   const int* forced, int n_forced, cudaStream_t stream) {
   if (N <= 0) return YMT3_OK;
-  greedy_select_kernel<<<ymt3_div_up(N, 8), 256, 0, stream>>>(logits, ld, V, N, step, cur_tok, finished,
-                                                              tokens_out, max_len, eos_id, pad_id, stop_at_eos,
-                                                              unfinished_count, forced, n_forced);
-  YMT3_CUDA_CHECK(cudaGetLastError());
+  YMT3_CUDA_CHECK(ymt3_launch_pdl(greedy_select_kernel, dim3(ymt3_div_up(N, 8)), dim3(256), 0, stream, logits, ld, V, N,
+                                  step, cur_tok, finished, tokens_out, max_len, eos_id, pad_id, stop_at_eos,
+                                  unfinished_count, forced, n_forced));
   return YMT3_OK;
 }
 
 // (*step)++ and reset the unfinished counter slot the NEXT step will accumulate into
 __global__ void advance_step_kernel(int* step, int* unfinished_count) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int s = *step + 1;
   *step = s;
   unfinished_count[s & 1] = 0;
 }
 
 int advance_step(int* step, int* unfinished_count, cudaStream_t stream) {
-  advance_step_kernel<<<1, 1, 0, stream>>>(step, unfinished_count);
-  YMT3_CUDA_CHECK(cudaGetLastError());
+  YMT3_CUDA_CHECK(ymt3_launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, stream, step, unfinished_count));
   return YMT3_OK;
 }
 

@@ -249,6 +249,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int num_kb = (p.K + BK - 1) / BK;
   const int groups = p.group_offsets ? p.num_groups : 1;
 
+  // PDL: dependents may be scheduled now; this kernel's own prologue (barriers, TMEM, tensor maps) overlaps the
+  // tail of the previous kernel, global memory is only touched after pdl_wait()
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -264,6 +267,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     int acc = 0;
     if (p.group_offsets) {
+      pdl_wait();   // the offsets are produced by the preceding kernel
       for (int g = 0; g < groups; ++g) {
         gstart[g] = acc;
         acc += ((p.group_offsets[g + 1] - p.group_offsets[g] + BM - 1) / BM) * n_tiles;
@@ -283,6 +287,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = gstart[groups];
 
@@ -530,8 +535,8 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   const int sms = ymt3_num_sms();
   const int grid = p.group_offsets ? sms : (int)(tiles < sms ? tiles : sms);
   YMT3_REQUIRE(groups <= 32, "gemm_bf16_tc: at most 32 groups");
-  gemm_bf16_tc_kernel<BN, CONV><<<grid, THREADS, SmemLayout<BN>::TOTAL, stream>>>(mapA, mapW, t);
-  YMT3_CUDA_CHECK(cudaGetLastError());
+  YMT3_CUDA_CHECK(ymt3_launch_pdl(gemm_bf16_tc_kernel<BN, CONV>, dim3(grid), dim3(THREADS), SmemLayout<BN>::TOTAL, stream,
+                                  mapA, mapW, t));
   return YMT3_OK;
 }
 

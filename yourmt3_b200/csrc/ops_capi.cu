@@ -50,3 +50,12 @@ extern "C" int ymt3_op_cross_attn_absorbed(const void* q, const void* z, void* o
   YMT3_REQUIRE(q && z && out, "op_cross_attn_absorbed: null argument");
   return cross_attn_absorbed(q, H * 256, z, out, H * 256, N, (int)H, (int)T, (int)Tp, 256, (cudaStream_t)stream);
 }
+
+extern "C" int ymt3_op_decode_attention(int32_t dtype, const void* q, const void* knew, const void* vnew, void* Kc,
+                                        void* Vc, const int32_t* step_dev, int64_t fixed_len, void* out, int64_t N,
+                                        int64_t H, int64_t Lcap, void* stream) {
+  YMT3_REQUIRE(q && Kc && Vc && out && (knew == nullptr) == (vnew == nullptr), "op_decode_attention: null argument");
+  YMT3_REQUIRE(knew ? step_dev != nullptr : (fixed_len > 0 && fixed_len <= Lcap), "op_decode_attention: bad length");
+  return decode_attention(q, H * 64, knew, vnew, H * 64, Kc, Vc, H * Lcap * 64, Lcap * 64, 64, (int)Lcap, step_dev,
+                          (int)fixed_len, 1.0f, out, H * 64, (int)N, (int)H, 64, dtype, (cudaStream_t)stream);
+}

@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(256) norm_vec_kernel(const T* __restrict__ x, 
                                                        const float* __restrict__ b, T* __restrict__ y, int64_t rows,
                                                        int dim, float eps) {
   constexpr int V = 16 / sizeof(T), RPW = 32 / LPR;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
   const int64_t row = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
@@ -153,8 +155,8 @@ static void launch_norm_vec(const T* x, const float* w, const float* b, T* y, in
   constexpr int V = 16 / sizeof(T);
   const int vecs = dim / V;   // 16-byte vectors per row
 #define NV(LPR, MAXV)                                                                                          \
-  norm_vec_kernel<T, RMS, LPR, MAXV><<<(unsigned)((rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR))), 256, 0, stream>>>( \
-      x, w, b, y, rows, dim, eps)
+  ymt3_launch_pdl(norm_vec_kernel<T, RMS, LPR, MAXV>, dim3((unsigned)((rows + 8 * (32 / LPR) - 1) / (8 * (32 / LPR)))), \
+                  dim3(256), 0, stream, x, w, b, y, rows, dim, eps)
   if (vecs <= 8) NV(8, 1);
   else if (vecs <= 16) NV(16, 1);
   else if (vecs <= 32) NV(32, 1);

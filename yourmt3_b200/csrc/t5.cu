@@ -363,13 +363,19 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
   const int D = c.d_model, H = c.num_heads, dk = c.d_kv, inner = H * dk, F = c.d_ff, dt = c.precision;
   const size_t es = dtype_size(dt);
   int rc;
+  // PROFILING AID ONLY (tools/time_phases.py): YMT3_DEBUG_SKIP is a bit mask of kernel families to leave out of the
+  // step so their in-graph cost can be measured by difference; the tokens are meaningless when it is set.
+  // 1 = self-attention, 2 = cross-attention kernel, 4 = all GEMMs of the layers, 8 = norms
+  static const int skip = getenv("YMT3_DEBUG_SKIP") ? atoi(getenv("YMT3_DEBUG_SKIP")) : 0;
+#define rmsnorm(...) ((skip & 8) ? 0 : rmsnorm(__VA_ARGS__))
+#define linear_fwd(...) ((skip & 4) ? 0 : linear_fwd(__VA_ARGS__))
   if ((rc = embed_pos(d->d_cur, d->embed, d->pos, d->d_step, d->x, (int)N, D, dt, s))) return rc;
   for (int i = 0; i < c.num_layers; ++i) {
     const T5Layer& L = d->layers[i];
     // self-attention over the device-resident cache (modeling_t5.py:269-305, 356-377)
     if ((rc = rmsnorm(d->x, L.ln_sa, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
     if ((rc = linear_fwd(dt, d->h, D, L.qkv, d->qkv, 3 * inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
-    if ((rc = decode_attention(d->qkv, 3 * inner, (char*)d->qkv + inner * es, (char*)d->qkv + 2 * inner * es, 3 * inner,
+    if (!(skip & 1) && (rc = decode_attention(d->qkv, 3 * inner, (char*)d->qkv + inner * es, (char*)d->qkv + 2 * inner * es, 3 * inner,
                                d->selfK[i], d->selfV[i], (int64_t)H * d->cap_L * dk, (int64_t)d->cap_L * dk, dk, Lmax + n_prefix,
                                d->d_step, 0, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
       return rc;
@@ -380,11 +386,11 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
       // absorbed form: latent-space query, attention over the shared latent tile, folded (Wo Wv Wp) output
       const int HZ = H * d->zdim;
       if ((rc = linear_fwd(dt, d->h, D, L.xq_abs, d->qz, HZ, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
-      if ((rc = cross_attn_absorbed(d->qz, HZ, d->zbuf, d->cz, HZ, N, H, (int)T, (int)((T + 15) / 16 * 16), d->zdim, s))) return rc;
+      if (!(skip & 2) && (rc = cross_attn_absorbed(d->qz, HZ, d->zbuf, d->cz, HZ, N, H, (int)T, (int)((T + 15) / 16 * 16), d->zdim, s))) return rc;
       if ((rc = linear_fwd(dt, d->cz, HZ, L.xo_abs, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
     } else {
     if ((rc = linear_fwd(dt, d->h, D, L.xq, d->qx, inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
-    if ((rc = decode_attention(d->qx, inner, nullptr, nullptr, 0, d->crossKV[i],
+    if (!(skip & 2) && (rc = decode_attention(d->qx, inner, nullptr, nullptr, 0, d->crossKV[i],
                                (char*)d->crossKV[i] + (size_t)N * inner * T * es, (int64_t)H * T * dk, T * dk, dk, 0,
                                d->d_step, (int)T, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
       return rc;
@@ -395,6 +401,8 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
     if ((rc = linear_fwd(dt, d->h, D, L.wi, d->g, F, (int)N, YMT3_ACT_GELU_NEW, 1, nullptr, 0, 1.f, dt, s))) return rc;
     if ((rc = linear_fwd(dt, d->g, F, L.wo, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
   }
+#undef rmsnorm
+#undef linear_fwd
   if ((rc = rmsnorm(d->x, d->final_ln, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
   // LM head; tied embeddings scale hidden by d_model^-0.5 (modeling_t5.py:1105-1110)
   const float sc = c.tie_word_embeddings ? 1.0f / sqrtf((float)D) : 1.0f;

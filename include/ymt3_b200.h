@@ -271,6 +271,16 @@ YMT3_API int ymt3_op_layernorm(int32_t dtype, const void* x, const float* w, con
 YMT3_API int ymt3_op_attention(int32_t dtype, const void* q, const void* k, const void* v, void* o, int64_t B,
                                int64_t H, int64_t Sq, int64_t Sk, int64_t dk, float scale, int32_t causal,
                                void* stream);
+/* bf16 tensor-core linear with the fused-RMSNorm hooks of the decode step (T5LayerNorm, HF modeling_t5.py:46-68, fused
+ * into the GEMMs around it).  Consumer side (ss_in != NULL): A is the UN-normalised x (M, K) bf16, W has the norm
+ * weight folded into its columns (W[n,k] * w_ln[k]), and every accumulator row is scaled by
+ * rsqrt(sum_c ss_in[m, c] / K + eps) before bias / activation; ss_in is (M, chunks) fp32, chunks % 4 == 0.
+ * Producer side (ss_out != NULL, bf16 non-gated output, N % 32 == 0): ss_out[m, n/32] = sum of squares of the
+ * bf16-rounded outputs C[m, 32*(n/32) .. +31] (after the residual add). */
+YMT3_API int ymt3_op_linear_normfused(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                      const float* ss_in, int64_t chunks, float eps, void* C, int64_t ldc,
+                                      const void* residual, int64_t ldr, float* ss_out, int64_t M, int64_t N, int64_t K,
+                                      int32_t act, int32_t gated, float out_scale, int32_t out_dtype, void* stream);
 /* Single-query attention over a device-resident KV cache alone (the decode step's dominant kernel; HF
  * modeling_t5.py:269-305 with use_cache): q (N, H*64); cache K/V (N, H, Lcap, 64).  knew/vnew (N, H*64) non-null:
  * self mode - the row is appended at index *step_dev, then keys [0, *step_dev] are attended.  knew == NULL: cross

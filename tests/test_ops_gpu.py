@@ -216,3 +216,44 @@ def test_decode_attention_self_and_cross(cuda_device, native_lib, dtype, N, H, s
     p = torch.softmax(torch.einsum("nhd,nhld->nhl", q.float(), K0[:, :, :L].float()), -1)
     ref = torch.einsum("nhl,nhld->nhd", p, V0[:, :, :L].float())
     assert float((out.float() - ref).abs().max()) < tol
+
+
+@pytest.mark.parametrize("M,N,K,gated", [(300, 1152, 512, 0), (3328, 2048, 512, 1), (77, 600, 512, 0)])
+def test_linear_fused_rmsnorm_consumer(cuda_device, native_lib, M, N, K, gated):
+    """GEMM on the un-normalised x with the norm weight folded into W and the row scale taken from sum-of-squares
+    partials == rmsnorm kernel followed by the plain GEMM (reference order), to bf16 accuracy."""
+    g = torch.Generator().manual_seed(M + N)
+    x = (torch.randn(M, K, generator=g) * 1.7).to(cuda_device, torch.bfloat16)
+    w_ln = (1.0 + 0.2 * torch.randn(K, generator=g)).to(cuda_device)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(cuda_device)
+    eps = 1e-6
+    ss = (x.float() ** 2).view(M, K // 32, 32).sum(-1).contiguous()
+    Wn = (W * w_ln[None, :]).to(torch.bfloat16).contiguous()
+    No = N // 2 if gated else N
+    out = torch.empty(M, No, dtype=torch.bfloat16, device=cuda_device)
+    act = 1 if gated else 0
+    _lib.check(native_lib.ymt3_op_linear_normfused(x.data_ptr(), K, Wn.data_ptr(), K, None, ss.data_ptr(), K // 32, eps,
+                                                   out.data_ptr(), No, None, 0, None, M, N, K, act, gated, 1.0, 1,
+                                                   _lib.current_stream_ptr()))
+    xf = x.float()
+    h = xf * torch.rsqrt((xf ** 2).mean(-1, keepdim=True) + eps) * w_ln
+    y = h @ W.T
+    if gated:   # rows interleaved: 2j = activated branch, 2j+1 = linear branch
+        y = OT.gelu_new(y[:, 0::2]) * y[:, 1::2]
+    err = float((out.float() - y).abs().max()) / max(1.0, float(y.abs().max()))
+    assert err < 2e-2, err
+
+
+def test_linear_fused_rmsnorm_producer(cuda_device, native_lib):
+    """the residual GEMM emits, per row and 32-column chunk, the sum of squares of exactly the bf16 values it stored."""
+    M, N, K = 333, 512, 384
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(M, K, generator=g).to(cuda_device, torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(cuda_device, torch.bfloat16)
+    x = torch.randn(M, N, generator=g).to(cuda_device, torch.bfloat16)
+    ss = torch.full((M, N // 32), float("nan"), device=cuda_device)
+    _lib.check(native_lib.ymt3_op_linear_normfused(a.data_ptr(), K, W.data_ptr(), K, None, None, 0, 0.0, x.data_ptr(), N,
+                                                   x.data_ptr(), N, ss.data_ptr(), M, N, K, 0, 0, 1.0, 1,
+                                                   _lib.current_stream_ptr()))
+    want = (x.float() ** 2).view(M, N // 32, 32).sum(-1)
+    assert float((ss - want).abs().max()) <= 1e-4 * float(want.abs().max())

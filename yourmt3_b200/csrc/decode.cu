@@ -18,7 +18,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 dec_from_f<__nv_bfloat16>(f
 template <typename T>
 __global__ void __launch_bounds__(128) embed_pos_kernel(const int* __restrict__ tok, const T* __restrict__ E,
                                                         const T* __restrict__ pos, const int* __restrict__ step,
-                                                        T* __restrict__ x, int dim) {
+                                                        T* __restrict__ x, int dim, float* __restrict__ ss) {
   pdl_launch_dependents();
   pdl_wait();
   const int n = blockIdx.x;
@@ -27,19 +27,30 @@ __global__ void __launch_bounds__(128) embed_pos_kernel(const int* __restrict__ 
   for (int i = threadIdx.x; i < dim; i += 128) {
     float v = dec_to_f(E[(int64_t)t * dim + i]);
     if (pos) v += dec_to_f(pos[(int64_t)s * dim + i]);
-    x[(int64_t)n * dim + i] = dec_from_f<T>(v);
+    const T o = dec_from_f<T>(v);
+    x[(int64_t)n * dim + i] = o;
+    if (ss) {
+      // fused RMSNorm producer (dim % 32 == 0): in every round a warp covers exactly one 32-column chunk
+      float sq = dec_to_f(o);
+      sq *= sq;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+      if ((threadIdx.x & 31) == 0) ss[(int64_t)n * (dim >> 5) + (i >> 5)] = sq;
+    }
   }
 }
 
 int embed_pos(const int* tok, const void* E, const void* pos, const int* step, void* x, int N, int dim,
-              int dtype, cudaStream_t stream) {
+              int dtype, cudaStream_t stream, float* ss_out) {
   if (N <= 0) return YMT3_OK;
+  YMT3_REQUIRE(!ss_out || dim % 128 == 0, "embed_pos: sum-of-squares output needs dim %% 128 == 0");
   if (dtype == YMT3_F32)
     YMT3_CUDA_CHECK(ymt3_launch_pdl(embed_pos_kernel<float>, dim3(N), dim3(128), 0, stream, tok, (const float*)E,
-                                    (const float*)pos, step, (float*)x, dim));
+                                    (const float*)pos, step, (float*)x, dim, ss_out));
   else
     YMT3_CUDA_CHECK(ymt3_launch_pdl(embed_pos_kernel<__nv_bfloat16>, dim3(N), dim3(128), 0, stream, tok,
-                                    (const __nv_bfloat16*)E, (const __nv_bfloat16*)pos, step, (__nv_bfloat16*)x, dim));
+                                    (const __nv_bfloat16*)E, (const __nv_bfloat16*)pos, step, (__nv_bfloat16*)x, dim,
+                                    ss_out));
   return YMT3_OK;
 }
 
@@ -101,7 +112,7 @@ template <> struct Slice8<__nv_bfloat16> {
 // contiguous bytes in the self cache), each group walks keys grp, grp+4, ... four at a time (8 x 16-byte loads
 // in flight per lane) with a private online-softmax state; the 4 group states are merged with xor-shuffles.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ knew, const T* __restrict__ vnew,
                    int64_t new_ld, T* __restrict__ Kc, T* __restrict__ Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss,
                    const int* __restrict__ step, int fixed_len, float scale, T* __restrict__ out, int64_t out_ld, int H,
@@ -117,18 +128,22 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
   const int grp = lane >> 3, sub = lane & 7;
   T* Kb = Kc + n * c_sn + (int64_t)h * c_sh;
   T* Vb = Vc + n * c_sn + (int64_t)h * c_sh;
-  int len = fixed_len;
+  // Every independent load is issued before the first one is consumed (the warp issues in order, so a consumed load
+  // stalls everything behind it): step, q and - self mode - the new K/V row.  The new row is attended straight from
+  // knew/vnew (key index s_new) and appended to the cache on the side, so there is no store -> load round trip.
+  const typename Slice8<T>::Raw qraw = Slice8<T>::load_raw(q + n * q_ld + h * DK + 8 * sub);
+  int len = fixed_len, s_new = -1;
+  const T* kn = nullptr;
+  const T* vn = nullptr;
   if (knew) {
-    const int s = *step;
-    len = s + 1;
-    if (lane < 8) Slice8<T>::copy(Kb + (int64_t)s * c_ss + 8 * lane, knew + n * new_ld + h * DK + 8 * lane);
-    else if (lane < 16) Slice8<T>::copy(Vb + (int64_t)s * c_ss + 8 * (lane - 8), vnew + n * new_ld + h * DK + 8 * (lane - 8));
-    __syncwarp();   // orders the append before the reads below (same warp)
+    kn = knew + n * new_ld + h * DK + 8 * sub;
+    vn = vnew + n * new_ld + h * DK + 8 * sub;
+    s_new = *step;
+    len = s_new + 1;
+    if (lane < 8) Slice8<T>::copy(Kb + (int64_t)s_new * c_ss + 8 * sub, kn);
+    else if (lane < 16) Slice8<T>::copy(Vb + (int64_t)s_new * c_ss + 8 * sub, vn);
   }
   float qv[8];
-  Slice8<T>::load(q + n * q_ld + h * DK + 8 * sub, qv);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) qv[i] *= scale;
 
   float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
@@ -144,9 +159,15 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
       const int j = base + u * NG + grp;
       has[u] = j < len;
       if (has[u]) {
-        kk[u] = Slice8<T>::load_raw(Kb + (int64_t)j * c_ss + 8 * sub);
-        vv[u] = Slice8<T>::load_raw(Vb + (int64_t)j * c_ss + 8 * sub);
+        const bool fresh = j == s_new;
+        kk[u] = Slice8<T>::load_raw(fresh ? kn : Kb + (int64_t)j * c_ss + 8 * sub);
+        vv[u] = Slice8<T>::load_raw(fresh ? vn : Vb + (int64_t)j * c_ss + 8 * sub);
       }
+    }
+    if (base == 0) {   // first consumption of q: after the first K/V loads are in flight
+      Slice8<T>::unpack(qraw, qv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qv[i] *= scale;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {

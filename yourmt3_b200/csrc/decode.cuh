@@ -4,8 +4,9 @@
 
 namespace ymt3 {
 
+// ss_out (optional, (N, dim/32) fp32): per-32-column sums of squares of the stored row (fused RMSNorm producer)
 int embed_pos(const int* tok, const void* E, const void* pos, const int* step, void* x, int N, int dim,
-              int dtype, cudaStream_t stream);
+              int dtype, cudaStream_t stream, float* ss_out = nullptr);
 
 // q: (N, H*dk) rows with leading dim q_ld. knew/vnew (self mode) rows with leading dim new_ld or
 // null (cross mode). Kc/Vc: caches addressed as base + n*c_sn + h*c_sh + j*c_ss (+ d), element strides.

@@ -114,6 +114,8 @@ struct TcParams {
   int act, gated;
   float out_scale;
   const float* row_scale;
+  const float* norm_ss_in; int norm_ss_chunks; float norm_eps;   // fused RMSNorm, consumer side (ops.cuh)
+  float* ss_out; int ss_out_chunks;                               // fused RMSNorm, producer side
   const int* group_offsets;
   int num_groups;
   int out_f32;
@@ -164,8 +166,10 @@ __device__ __forceinline__ void epi_dispatch(float (&f)[32], float rs, int act, 
   }
 }
 // store `count` (multiple of 8 for bf16 / 4 for f32, <= 32) consecutive outputs f[0..count) of one row (+ residual)
+// ss != null (bf16 output only): *ss = sum of squares of the bf16-rounded values stored (fused RMSNorm producer)
 template <bool OUT_F32>
-__device__ __forceinline__ void epi_store(void* Cbase, const void* Rbase, int64_t off, const float (&f)[32], int count) {
+__device__ __forceinline__ void epi_store(void* Cbase, const void* Rbase, int64_t off, const float (&f)[32], int count,
+                                          float* ss = nullptr) {
   if constexpr (OUT_F32) {
     float* C = static_cast<float*>(Cbase) + off;
     const float* R = Rbase ? static_cast<const float*>(Rbase) + off : nullptr;
@@ -191,6 +195,7 @@ __device__ __forceinline__ void epi_store(void* Cbase, const void* Rbase, int64_
       for (int j = 0; j < 4; ++j)
         if (8 * j < count) r[j] = *reinterpret_cast<const uint4*>(R + 8 * j);   // all residual loads in flight first
     }
+    float sq = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (8 * j >= count) break;
@@ -206,8 +211,16 @@ __device__ __forceinline__ void epi_store(void* Cbase, const void* Rbase, int64_
 #pragma unroll
         for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
       }
+      if (ss) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 v2 = __bfloat1622float2(h[q]);
+          sq = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, sq));
+        }
+      }
       *reinterpret_cast<uint4*>(C + 8 * j) = pk;
     }
+    if (ss) *ss = sq;
   }
 }
 
@@ -397,6 +410,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool row_ok = r < row_end;
       const float rs = p.out_scale * ((p.row_scale && row_ok) ? p.row_scale[r] : 1.0f);
+      float pre = 1.0f;   // fused RMSNorm: r = rsqrt(mean(x^2) + eps) of this row of A, partials summed in a fixed order
+      if (p.norm_ss_in && row_ok) {
+        const float* sp = p.norm_ss_in + (int64_t)r * p.norm_ss_chunks;
+        float tot = 0.f;
+        for (int c4 = 0; c4 + 4 <= p.norm_ss_chunks; c4 += 4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sp + c4);
+          tot += (s4.x + s4.y) + (s4.z + s4.w);
+        }
+        for (int c1 = p.norm_ss_chunks & ~3; c1 < p.norm_ss_chunks; ++c1) tot += sp[c1];
+        pre = rsqrtf(tot / (float)p.K + p.norm_eps);
+      }
       constexpr int NCHUNK = BN / 32;
 #pragma unroll 1
       for (int ci = half; ci < NCHUNK + 2; ci += 2) {
@@ -417,7 +441,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if (c < p.N) {
             float f[32];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]);
+            for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]) * pre;
             if (bias) {
               if (c + 32 <= p.N) {
 #pragma unroll
@@ -438,7 +462,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             // residual may alias C (in-place x += ...): each element is read then written by this thread only
             const void* Rb = p.residual ? (const void*)(static_cast<const char*>(p.residual) + (roff - off) * (p.out_f32 ? 4 : 2)) : nullptr;
             if (p.out_f32) epi_store<true>(p.C, Rb, off, f, n_out);
-            else epi_store<false>(p.C, Rb, off, f, n_out);
+            else epi_store<false>(p.C, Rb, off, f, n_out, p.ss_out ? p.ss_out + (int64_t)r * p.ss_out_chunks + (c >> 5) : nullptr);
           }
         }
         if (last) break;
@@ -521,6 +545,8 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   TcParams t;
   t.C = p.C; t.ldc = p.ldc; t.bias = p.bias; t.residual = p.residual; t.ldr = p.ldr;
   t.M = p.M; t.N = p.N; t.K = p.K; t.act = p.act; t.gated = p.gated; t.out_scale = p.out_scale;
+  t.norm_ss_in = p.norm_ss_in; t.norm_ss_chunks = p.norm_ss_chunks; t.norm_eps = p.norm_eps;
+  t.ss_out = p.ss_out; t.ss_out_chunks = (p.N + 31) / 32;
   t.row_scale = p.row_scale; t.group_offsets = p.group_offsets; t.num_groups = groups; t.out_f32 = out_dtype == YMT3_F32;
   t.conv_T = cg.T; t.conv_F = cg.F; t.conv_cblocks = CONV ? cg.Cin / BK : 0;
   static bool attr_set = false;
@@ -554,6 +580,10 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
                "gemm_bf16_tc: pointers must be 16-byte aligned");
   YMT3_REQUIRE(!p.group_offsets || p.strideW == (int64_t)p.N * p.ldw,
                "gemm_bf16_tc: grouped weights must be stacked contiguously");
+  YMT3_REQUIRE(!p.ss_out || (out_dtype == YMT3_BF16 && !p.gated && p.N % 32 == 0),
+               "gemm_bf16_tc: sum-of-squares output needs bf16, non-gated, N %% 32 == 0");
+  YMT3_REQUIRE(!p.norm_ss_in || (p.norm_ss_chunks > 0 && ((uintptr_t)p.norm_ss_in & 15) == 0 && p.norm_ss_chunks % 4 == 0),
+               "gemm_bf16_tc: fused-norm partials must be 16-byte aligned, a multiple of 4 per row");
   // pick BN so that the grid fills the 148 SMs (2 CTAs/SM resident) when the problem allows
   const int64_t mt = ymt3_div_up(p.M, BM);
   const int sms = ymt3_num_sms();

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
 }
 
 int gemm_f32(const GemmParams& p, cudaStream_t stream) {
+  YMT3_REQUIRE(!p.norm_ss_in && !p.ss_out, "gemm_f32: fused RMSNorm is a bf16 tensor-core path feature");
   YMT3_REQUIRE(p.A && p.W && p.C, "gemm_f32: null pointer");
   if (p.M <= 0 || p.N <= 0) return YMT3_OK;
   YMT3_REQUIRE(p.K > 0 && p.K % 4 == 0 && p.lda % 4 == 0 && p.ldw % 4 == 0,

@@ -6,18 +6,18 @@ namespace ymt3 {
 template <typename D>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ src, D* __restrict__ dst, int64_t rows, int K, int64_t row_offset,
-                 int row_stride) {
+                 int row_stride, const float* __restrict__ col_scale = nullptr) {
   int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= rows * K) return;
   int64_t r = i / K;
   int c = (int)(i - r * K);
-  const float v = src[i];
+  const float v = col_scale ? src[i] * col_scale[c] : src[i];
   D* d = dst + (row_offset + r * row_stride) * K + c;
   if constexpr (sizeof(D) == 4) *d = v; else *d = __float2bfloat16(v);
 }
 
 int pack_rows(DevicePool& pool, const std::vector<const ymt3_tensor_t*>& srcs, int K, int dtype,
-              bool interleave2, Linear* out, cudaStream_t stream) {
+              bool interleave2, Linear* out, cudaStream_t stream, const float* col_scale) {
   int64_t total = 0;
   for (auto* s : srcs) {
     if (!s) return YMT3_ERR_INVALID;  // error already set by TensorTable::require
@@ -36,10 +36,10 @@ int pack_rows(DevicePool& pool, const std::vector<const ymt3_tensor_t*>& srcs, i
     const int row_stride = interleave2 ? 2 : 1;
     if (dtype == YMT3_F32)
       pack_rows_kernel<float><<<grid, 256, 0, stream>>>((const float*)srcs[si]->data, (float*)W, rows, K,
-                                                        row_offset, row_stride);
+                                                        row_offset, row_stride, col_scale);
     else
       pack_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)srcs[si]->data, (__nv_bfloat16*)W,
-                                                                rows, K, row_offset, row_stride);
+                                                                rows, K, row_offset, row_stride, col_scale);
     off += rows;
   }
   YMT3_CUDA_CHECK(cudaGetLastError());
@@ -49,16 +49,18 @@ int pack_rows(DevicePool& pool, const std::vector<const ymt3_tensor_t*>& srcs, i
   return YMT3_OK;
 }
 
-int pack_rows_at(void* W, int64_t row0, int row_stride, const ymt3_tensor_t* src, int K, int dtype, cudaStream_t stream) {
+int pack_rows_at(void* W, int64_t row0, int row_stride, const ymt3_tensor_t* src, int K, int dtype, cudaStream_t stream,
+                 const float* col_scale) {
   if (!src) return YMT3_ERR_INVALID;
   const int64_t rows = src->shape[0];
   const int64_t n = rows * K;
   const unsigned grid = (unsigned)((n + 255) / 256);
   if (dtype == YMT3_F32)
-    pack_rows_kernel<float><<<grid, 256, 0, stream>>>((const float*)src->data, (float*)W, rows, K, row0, row_stride);
+    pack_rows_kernel<float><<<grid, 256, 0, stream>>>((const float*)src->data, (float*)W, rows, K, row0, row_stride,
+                                                      col_scale);
   else
     pack_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)src->data, (__nv_bfloat16*)W, rows, K, row0,
-                                                              row_stride);
+                                                              row_stride, col_scale);
   YMT3_CUDA_CHECK(cudaGetLastError());
   return YMT3_OK;
 }
@@ -105,8 +107,9 @@ int pack_table(DevicePool& pool, const float* src, bool src_on_host, int64_t num
 
 int linear_fwd(int precision, const void* x, int64_t ldx, const Linear& lin, void* y, int64_t ldy, int M,
                int act, int gated, const void* residual, int64_t ldr, float out_scale, int out_dtype,
-               cudaStream_t stream) {
+               cudaStream_t stream, const NormFuse& nf) {
   GemmParams p{};
+  p.norm_ss_in = nf.ss_in; p.norm_ss_chunks = nf.chunks; p.norm_eps = nf.eps; p.ss_out = nf.ss_out;
   p.A = x; p.lda = ldx;
   p.W = lin.W; p.ldw = lin.K;
   p.C = y; p.ldc = ldy;

@@ -71,10 +71,13 @@ struct Linear {
 
 // Stack the rows of several (n_i, K) f32 tensors into one (sum n_i, K) weight in `dtype`.
 // interleave2: exactly two sources of equal shape; output row 2j = src0[j], 2j+1 = src1[j].
+// col_scale (device fp32 (K) or null): every row is multiplied element-wise by it BEFORE the conversion (RMSNorm
+// weight folded into the consumer GEMM, see GemmParams::norm_ss_in)
 int pack_rows(DevicePool& pool, const std::vector<const ymt3_tensor_t*>& srcs, int K, int dtype,
-              bool interleave2, Linear* out, cudaStream_t stream);
+              bool interleave2, Linear* out, cudaStream_t stream, const float* col_scale = nullptr);
 // write one (rows, K) f32 source into an existing packed weight: dst row = row0 + r * row_stride
-int pack_rows_at(void* W, int64_t row0, int row_stride, const ymt3_tensor_t* src, int K, int dtype, cudaStream_t stream);
+int pack_rows_at(void* W, int64_t row0, int row_stride, const ymt3_tensor_t* src, int K, int dtype, cudaStream_t stream,
+                 const float* col_scale = nullptr);
 // concatenate 1-D f32 tensors (biases / norm scales) into one fp32 device vector
 int pack_vec(DevicePool& pool, const std::vector<const ymt3_tensor_t*>& srcs, bool interleave2, float** out,
              cudaStream_t stream);
@@ -83,8 +86,13 @@ int pack_table(DevicePool& pool, const float* src_dev_or_host, bool src_on_host,
                void** out, cudaStream_t stream);
 
 // y = epi(x @ lin.W^T + bias) dispatched on the handle's precision
+// nf: fused RMSNorm hooks of the bf16 GEMM (consumer: row scale from sum-of-squares partials; producer: emit them)
+struct NormFuse {
+  const float* ss_in = nullptr; int chunks = 0; float eps = 0.f;
+  float* ss_out = nullptr;
+};
 int linear_fwd(int precision, const void* x, int64_t ldx, const Linear& lin, void* y, int64_t ldy, int M,
                int act, int gated, const void* residual, int64_t ldr, float out_scale, int out_dtype,
-               cudaStream_t stream);
+               cudaStream_t stream, const NormFuse& nf = NormFuse());
 
 }  // namespace ymt3

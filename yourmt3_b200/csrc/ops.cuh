@@ -49,6 +49,14 @@ struct GemmParams {
   const int* group_offsets; int num_groups; int64_t strideW;
   // optional per-row scale applied with out_scale (MoE combine weights), fp32 (M) or null
   const float* row_scale;
+  // Fused RMSNorm (bf16 tensor-core path only; decode step).  rmsnorm(x) W^T = diag(r) x (W . w_ln)^T with
+  // r = rsqrt(mean(x^2) + eps): the consumer GEMM reads x itself, has w_ln folded into its weight columns at pack
+  // time and multiplies every accumulator row by r BEFORE bias / activation; r comes from per-row partial sums of
+  // squares (norm_ss_in: (M, norm_ss_chunks) fp32, one partial per 32 columns of x, summed in a fixed order ->
+  // deterministic).  The producer GEMM (the one that writes x = residual + ...) emits those partials from the
+  // bf16-ROUNDED values it stores (ss_out: (M, ceil(N/32)) fp32), i.e. exactly the numbers a norm kernel would read.
+  const float* norm_ss_in; int norm_ss_chunks; float norm_eps;
+  float* ss_out;
 };
 
 int gemm_f32(const GemmParams& p, cudaStream_t stream);            // SIMT fp32 FFMA

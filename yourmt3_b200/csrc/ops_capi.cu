@@ -59,3 +59,17 @@ extern "C" int ymt3_op_decode_attention(int32_t dtype, const void* q, const void
   return decode_attention(q, H * 64, knew, vnew, H * 64, Kc, Vc, H * Lcap * 64, Lcap * 64, 64, (int)Lcap, step_dev,
                           (int)fixed_len, 1.0f, out, H * 64, (int)N, (int)H, 64, dtype, (cudaStream_t)stream);
 }
+
+extern "C" int ymt3_op_linear_normfused(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                        const float* ss_in, int64_t chunks, float eps, void* C, int64_t ldc,
+                                        const void* residual, int64_t ldr, float* ss_out, int64_t M, int64_t N, int64_t K,
+                                        int32_t act, int32_t gated, float out_scale, int32_t out_dtype, void* stream) {
+  YMT3_REQUIRE(M >= 0 && M < (1ll << 31) && N > 0 && N < (1ll << 31) && K > 0 && K < (1ll << 31),
+               "op_linear_normfused: bad shape");
+  GemmParams p{};
+  p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.C = C; p.ldc = ldc; p.bias = bias;
+  p.residual = residual; p.ldr = ldr; p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.act = act; p.gated = gated; p.out_scale = out_scale;
+  p.norm_ss_in = ss_in; p.norm_ss_chunks = (int)chunks; p.norm_eps = eps; p.ss_out = ss_out;
+  return gemm_bf16_tc(p, out_dtype, (cudaStream_t)stream);
+}

@@ -14,6 +14,9 @@ struct T5Layer {
   float* ln_sa = nullptr;  Linear qkv, o;           // layer.0 SelfAttention (q|k|v stacked)
   float* ln_ca = nullptr;  Linear xq, xkv, xo;      // layer.1 EncDecAttention (decoder only; k|v stacked)
   Linear xq_abs, xo_abs;                            // optional absorbed cross-attention (latent-space q / o + bias)
+  // bf16 decoder only: copies of the norm-consuming weights with the RMSNorm scale folded into their columns
+  // (fused RMSNorm, GemmParams::norm_ss_in): qkv <- ln_sa, xq / xq_abs <- ln_ca, wi <- ln_ff
+  Linear qkv_n, xq_n, xq_abs_n, wi_n;
   float* ln_ff = nullptr;  Linear wi, wo;           // DenseReluDense (wi_0/wi_1 interleaved -> gated epilogue)
 };
 
@@ -46,6 +49,15 @@ int load_layers(const ymt3_t5_cfg_t& c, const TensorTable& tt, bool decoder, Dev
       return rc;
     if ((rc = pack_rows(pool, {tt.require(ff + "DenseReluDense.wo.weight", D, F)}, F, c.precision, false, &L.wo, s)))
       return rc;
+    if (decoder && c.precision == YMT3_BF16) {
+      const std::string ca = b + "1.EncDecAttention.";
+      if ((rc = pack_rows(pool, {tt.require(sa + "q.weight", inner, D), tt.require(sa + "k.weight", inner, D),
+                                 tt.require(sa + "v.weight", inner, D)}, D, c.precision, false, &L.qkv_n, s, L.ln_sa))) return rc;
+      if ((rc = pack_rows(pool, {tt.require(ca + "q.weight", inner, D)}, D, c.precision, false, &L.xq_n, s, L.ln_ca))) return rc;
+      if ((rc = pack_rows(pool, {tt.require(ff + "DenseReluDense.wi_0.weight", F, D),
+                                 tt.require(ff + "DenseReluDense.wi_1.weight", F, D)}, D, c.precision, true, &L.wi_n, s,
+                          L.ln_ff))) return rc;
+    }
   }
   return pack_vec(pool, {tt.require("final_layer_norm.weight", D)}, false, final_ln, s);
 }
@@ -175,6 +187,9 @@ struct ymt3_t5dec {
   int n_pos = 0;
   void* embed = nullptr;     // (V, D) compute dtype
   Linear lm_head;            // (Vp, D), rows >= V are zero
+  Linear lm_head_n;          // bf16: final_layer_norm folded in (fused RMSNorm)
+  bool fuse_norm = false;    // bf16 && d_model % 128 == 0 && !YMT3_NO_FUSED_NORM
+  float* ss[3] = {nullptr, nullptr, nullptr};   // (cap_N, d_model / 32) sum-of-squares partials, rotating
   int Vp = 0;
   // per-(N, T_enc, Lmax) state
   int64_t cap_N = 0, cap_T = 0, cap_L = 0;
@@ -228,6 +243,8 @@ extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
           const std::string ca = "block." + std::to_string(i) + ".layer.1.EncDecAttention.";
           T5Layer& L = d->layers[i];
           rc = pack_rows(d->weights, {tt.require(ca + "q_absorbed.weight", HZ, D)}, D, YMT3_BF16, false, &L.xq_abs, 0);
+          if (!rc) rc = pack_rows(d->weights, {tt.require(ca + "q_absorbed.weight", HZ, D)}, D, YMT3_BF16, false, &L.xq_abs_n, 0,
+                                  L.ln_ca);
           if (!rc) rc = pack_rows(d->weights, {tt.require(ca + "o_absorbed.weight", D, HZ)}, HZ, YMT3_BF16, false, &L.xo_abs, 0);
           if (!rc) rc = pack_vec(d->weights, {tt.require(ca + "o_absorbed.bias", D)}, false, &L.xo_abs.bias, 0);
         }
@@ -248,6 +265,13 @@ extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
         if (!rc && cudaMemsetAsync(W, 0, (size_t)d->Vp * D * dtype_size(cfg->precision), 0) != cudaSuccess) rc = YMT3_ERR_CUDA;
         if (!rc) rc = convert(Lm->data, YMT3_F32, W, cfg->precision, (int64_t)V * D, 0);
         d->lm_head.W = W; d->lm_head.N = d->Vp; d->lm_head.K = D;
+        if (!rc && cfg->precision == YMT3_BF16) {
+          void* Wn = d->weights.alloc((size_t)d->Vp * D * 2);
+          if (!Wn) rc = YMT3_ERR_CUDA;
+          if (!rc && cudaMemsetAsync(Wn, 0, (size_t)d->Vp * D * 2, 0) != cudaSuccess) rc = YMT3_ERR_CUDA;
+          if (!rc) rc = pack_rows_at(Wn, 0, 1, Lm, D, YMT3_BF16, 0, d->final_ln);
+          d->lm_head_n.W = Wn; d->lm_head_n.N = d->Vp; d->lm_head_n.K = D;
+        }
       }
     }
   }
@@ -262,6 +286,7 @@ extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
       }
     }
   }
+  d->fuse_norm = cfg->precision == YMT3_BF16 && D % 128 == 0 && getenv("YMT3_NO_FUSED_NORM") == nullptr;
   if (!rc) {
     d->d_step = (int*)d->weights.alloc(64);
     d->d_unfinished = d->d_step + 4;
@@ -336,7 +361,9 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, int latent, cu
   }
   d->d_cur = (int*)d->ws.alloc(cN * 4);
   d->d_fin = (int*)d->ws.alloc(cN * 4);
-  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->kv_tmp;
+  for (int i = 0; i < 3; ++i) d->ss[i] = d->fuse_norm ? (float*)d->ws.alloc((size_t)cN * (D / 32) * 4) : nullptr;
+  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->kv_tmp &&
+            (!d->fuse_norm || (d->ss[0] && d->ss[1] && d->ss[2]));
   d->selfK.assign(c.num_layers, nullptr);
   d->selfV.assign(c.num_layers, nullptr);
   d->crossKV.assign(c.num_layers, nullptr);
@@ -367,46 +394,71 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
   // step so their in-graph cost can be measured by difference; the tokens are meaningless when it is set.
   // 1 = self-attention, 2 = cross-attention kernel, 4 = all GEMMs of the layers, 8 = norms
   static const int skip = getenv("YMT3_DEBUG_SKIP") ? atoi(getenv("YMT3_DEBUG_SKIP")) : 0;
-#define rmsnorm(...) ((skip & 8) ? 0 : rmsnorm(__VA_ARGS__))
-#define linear_fwd(...) ((skip & 4) ? 0 : linear_fwd(__VA_ARGS__))
-  if ((rc = embed_pos(d->d_cur, d->embed, d->pos, d->d_step, d->x, (int)N, D, dt, s))) return rc;
+  // bf16: RMSNorm is fused into the GEMMs around it (GemmParams::norm_ss_in / ss_out): the kernel that writes the
+  // residual stream x also emits per-row sum-of-squares partials, the GEMM that consumes norm(x) reads x itself with
+  // the norm weight folded into its columns and scales its accumulator rows by rsqrt(mean(x^2) + eps).  24 of the
+  // 107 launches of a step disappear.  fp32 keeps the reference order (separate norm kernels).
+  const bool fuse = d->fuse_norm;
+  const int ch = D / 32;
+  auto consume = [&](float* ss) { NormFuse n; n.ss_in = ss; n.chunks = ch; n.eps = c.layer_norm_eps; return n; };
+  auto produce = [&](float* ss) { NormFuse n; n.ss_out = ss; return n; };
+  // y = W norm(x): separate kernel + GEMM (reference order) or one GEMM on x with the folded weight Wn
+  auto normed_linear = [&](const float* ln, const Linear& W, const Linear& Wn, float* ss, void* y, int ny, int act,
+                           int gated, float scale, int out_dt) -> int {
+    if (fuse) {
+      if (skip & 4) return YMT3_OK;
+      return linear_fwd(dt, d->x, D, Wn, y, ny, (int)N, act, gated, nullptr, 0, scale, out_dt, s, consume(ss));
+    }
+    int r = (skip & 8) ? 0 : rmsnorm(d->x, ln, d->h, N, D, c.layer_norm_eps, dt, s);
+    if (r || (skip & 4)) return r;
+    return linear_fwd(dt, d->h, D, W, y, ny, (int)N, act, gated, nullptr, 0, scale, out_dt, s);
+  };
+  // x += W a (+ bias), emitting the sum-of-squares partials of the new x for the next norm
+  auto residual_linear = [&](const void* a, int lda, const Linear& W, float* ss) -> int {
+    if (skip & 4) return YMT3_OK;
+    return linear_fwd(dt, a, lda, W, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s, fuse ? produce(ss) : NormFuse());
+  };
+  float *sA = d->ss[0], *sB = d->ss[1], *sC = d->ss[2];
+  if ((rc = embed_pos(d->d_cur, d->embed, d->pos, d->d_step, d->x, (int)N, D, dt, s, fuse ? sA : nullptr))) return rc;
   for (int i = 0; i < c.num_layers; ++i) {
     const T5Layer& L = d->layers[i];
     // self-attention over the device-resident cache (modeling_t5.py:269-305, 356-377)
-    if ((rc = rmsnorm(d->x, L.ln_sa, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
-    if ((rc = linear_fwd(dt, d->h, D, L.qkv, d->qkv, 3 * inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
+    if ((rc = normed_linear(L.ln_sa, L.qkv, L.qkv_n, sA, d->qkv, 3 * inner, 0, 0, 1.f, dt))) return rc;
     if (!(skip & 1) && (rc = decode_attention(d->qkv, 3 * inner, (char*)d->qkv + inner * es, (char*)d->qkv + 2 * inner * es, 3 * inner,
                                d->selfK[i], d->selfV[i], (int64_t)H * d->cap_L * dk, (int64_t)d->cap_L * dk, dk, Lmax + n_prefix,
                                d->d_step, 0, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
       return rc;
-    if ((rc = linear_fwd(dt, d->attn, inner, L.o, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
-    // cross-attention over encoder K/V computed once (modeling_t5.py:387-408)
-    if ((rc = rmsnorm(d->x, L.ln_ca, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
+    if ((rc = residual_linear(d->attn, inner, L.o, sB))) return rc;
+    // cross-attention (modeling_t5.py:387-408)
     if (latent) {
       // absorbed form: latent-space query, attention over the shared latent tile, folded (Wo Wv Wp) output
       const int HZ = H * d->zdim;
-      if ((rc = linear_fwd(dt, d->h, D, L.xq_abs, d->qz, HZ, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
+      if ((rc = normed_linear(L.ln_ca, L.xq_abs, L.xq_abs_n, sB, d->qz, HZ, 0, 0, 1.f, dt))) return rc;
       if (!(skip & 2) && (rc = cross_attn_absorbed(d->qz, HZ, d->zbuf, d->cz, HZ, N, H, (int)T, (int)((T + 15) / 16 * 16), d->zdim, s))) return rc;
-      if ((rc = linear_fwd(dt, d->cz, HZ, L.xo_abs, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
+      if ((rc = residual_linear(d->cz, HZ, L.xo_abs, sC))) return rc;
     } else {
-    if ((rc = linear_fwd(dt, d->h, D, L.xq, d->qx, inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
-    if (!(skip & 2) && (rc = decode_attention(d->qx, inner, nullptr, nullptr, 0, d->crossKV[i],
-                               (char*)d->crossKV[i] + (size_t)N * inner * T * es, (int64_t)H * T * dk, T * dk, dk, 0,
-                               d->d_step, (int)T, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
-      return rc;
-    if ((rc = linear_fwd(dt, d->attn, inner, L.xo, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
+      // over encoder K/V computed once
+      if ((rc = normed_linear(L.ln_ca, L.xq, L.xq_n, sB, d->qx, inner, 0, 0, 1.f, dt))) return rc;
+      if (!(skip & 2) && (rc = decode_attention(d->qx, inner, nullptr, nullptr, 0, d->crossKV[i],
+                                 (char*)d->crossKV[i] + (size_t)N * inner * T * es, (int64_t)H * T * dk, T * dk, dk, 0,
+                                 d->d_step, (int)T, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
+        return rc;
+      if ((rc = residual_linear(d->attn, inner, L.xo, sC))) return rc;
     }
     // gated-GELU feed-forward
-    if ((rc = rmsnorm(d->x, L.ln_ff, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
-    if ((rc = linear_fwd(dt, d->h, D, L.wi, d->g, F, (int)N, YMT3_ACT_GELU_NEW, 1, nullptr, 0, 1.f, dt, s))) return rc;
-    if ((rc = linear_fwd(dt, d->g, F, L.wo, d->x, D, (int)N, 0, 0, d->x, D, 1.f, dt, s))) return rc;
+    if ((rc = normed_linear(L.ln_ff, L.wi, L.wi_n, sC, d->g, F, YMT3_ACT_GELU_NEW, 1, 1.f, dt))) return rc;
+    if ((rc = residual_linear(d->g, F, L.wo, sA))) return rc;
   }
-#undef rmsnorm
-#undef linear_fwd
-  if ((rc = rmsnorm(d->x, d->final_ln, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
-  // LM head; tied embeddings scale hidden by d_model^-0.5 (modeling_t5.py:1105-1110)
+  // final norm + LM head; tied embeddings scale hidden by d_model^-0.5 (modeling_t5.py:1105-1110)
   const float sc = c.tie_word_embeddings ? 1.0f / sqrtf((float)D) : 1.0f;
-  if ((rc = linear_fwd(dt, d->h, D, d->lm_head, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s))) return rc;
+  {
+    if (fuse) {
+      if ((rc = linear_fwd(dt, d->x, D, d->lm_head_n, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s, consume(sA)))) return rc;
+    } else {
+      if ((rc = rmsnorm(d->x, d->final_ln, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
+      if ((rc = linear_fwd(dt, d->h, D, d->lm_head, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s))) return rc;
+    }
+  }
   if ((rc = greedy_select(d->logits, d->Vp, c.vocab_size, (int)N, d->d_step, d->d_cur, d->d_fin, tokens_out, Lmax,
                           c.eos_id, c.pad_id, stop_at_eos, d->d_unfinished, n_prefix ? d->d_forced : nullptr, n_prefix, s)))
     return rc;

@@ -24,7 +24,10 @@
 // statistics are fp32, P is kept unnormalised and O is scaled by 1/l in fp32.
 // History (profiles/r01_cross_absorbed_*): v1 one CTA per sequence, cp.async, no prefetch: 73 us for 3328 sequences
 // (2.9 TB/s); v2 persistent + cp.async ring: same 73 us - ncu showed 6.8 k warp instructions per sequence, 28 % of
-// them cp.async address arithmetic, issue-bound at 8 warps/SM; v3 (this) TMA + register softmax.
+// them cp.async address arithmetic, issue-bound at 8 warps/SM; v3 (this) TMA + register softmax: 48 us (4.2 TB/s).
+// v4 experiment (NOT kept): a TMA producer warp + two 8-warp consumer groups on alternate sequences (named barriers,
+// full/empty mbarriers) ran 43 us but hung about once per 3000 launches (0.4 s watchdog kill) even after adding
+// warp reconvergence around every inline-asm wait/barrier; root cause not found in the time available.
 #include "ops.cuh"
 #include "decode.cuh"
 #include <cuda.h>
@@ -169,7 +172,10 @@ cross_attn_absorbed_kernel(const __grid_constant__ CUtensorMap mq, const __grid_
         stage_issue(&mq, &mz, ring, bar0, n, H, Tp);   // single-stage fallback (very long encoders): no prefetch
       }
     }
+    // mbarrier.try_wait is a per-thread poll (lanes may leave the spin loop on different iterations and the compiler
+    // cannot see that inside inline asm): reconverge before the warp-synchronous ldmatrix / mma below
     mbar_wait(bar0 + 8 * slot, (uint32_t)((it / stages) & 1));
+    __syncwarp();
     const uint32_t qs = ring + slot * stage_bytes;
     const uint32_t zs = qs + Q_STAGE_BYTES;
 

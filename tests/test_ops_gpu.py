@@ -257,3 +257,32 @@ def test_linear_fused_rmsnorm_producer(cuda_device, native_lib):
                                                    _lib.current_stream_ptr()))
     want = (x.float() ** 2).view(M, N // 32, 32).sum(-1)
     assert float((ss - want).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk", [(3, 8, 26, 26), (3, 8, 110, 110), (2, 8, 128, 128), (5, 2, 16, 16), (4, 8, 5, 37),
+                                       (700, 8, 110, 110)])
+def test_attention_bf16_dk16_tensor_core(cuda_device, native_lib, B, H, Sq, Sk):
+    """tiny-sequence tensor-core attention (attn_small_tc_kernel: bf16, dk 16) vs torch fp32 on the same bf16 inputs,
+    and vs the fp32-math SIMT kernel it replaces (YMT3_NO_TC_ATTN=1)."""
+    import os
+    g = torch.Generator().manual_seed(B + Sq * 7 + Sk)
+    q, k, v = (torch.randn(B, S, H, 16, generator=g).to(torch.bfloat16) for S in (Sq, Sk, Sk))
+    scale = 0.25
+    ref = OT.attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2), None,
+                       scale).view(B, Sq, H, 16)
+    qd, kd, vd = q.to(cuda_device), k.to(cuda_device), v.to(cuda_device)
+    outs = []
+    for no_tc in (False, True):
+        if no_tc:
+            os.environ["YMT3_NO_TC_ATTN"] = "1"
+        try:
+            o = torch.full((B, Sq, H, 16), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+            _lib.check(native_lib.ymt3_op_attention(1, qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, H, Sq,
+                                                    Sk, 16, scale, 0, torch.cuda.current_stream().cuda_stream))
+            outs.append(o.float().cpu())
+        finally:
+            os.environ.pop("YMT3_NO_TC_ATTN", None)
+    # bf16 probabilities + bf16 q*scale rounding + bf16 output: a few 1e-3 absolute on O(1) values
+    assert float((outs[0] - ref).abs().max()) < 3e-2
+    assert float((outs[0] - ref).abs().mean()) < 3e-3
+    assert float((outs[1] - ref).abs().max()) < 2e-2          # the SIMT kernel (only the output is rounded)

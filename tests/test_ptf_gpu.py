@@ -125,3 +125,21 @@ def test_transcribe_waveform_equals_segmented_inference(cuda_device, native_lib)
     b = m.inference(slice_padded_array(wave, 32767, 32767), stop_at_eos=False)
     assert a.shape == b.shape == (3, 13, 6)
     assert torch.equal(a, b)
+
+
+def test_perceiver_tf_bf16_tensor_core_attention_matches_simt(cuda_device, native_lib):
+    """RoPE + scale folded into the tensor-core tiny attention: the bf16 Perceiver-TF encoder output with the
+    tensor-core kernel vs with the fp32-math SIMT kernel (YMT3_NO_TC_ATTN=1) - same weights, same input."""
+    import os
+    m = small_model("yptf_moe_multi", "bf16", blocks=1).to(cuda_device)
+    x = torch.randn(2, 7, 128, 128, generator=torch.Generator().manual_seed(4)).to(cuda_device)
+    a = m.encoder(inputs_embeds=x)["last_hidden_state"].float().cpu()
+    os.environ["YMT3_NO_TC_ATTN"] = "1"
+    try:
+        b = m.encoder(inputs_embeds=x)["last_hidden_state"].float().cpu()
+    finally:
+        os.environ.pop("YMT3_NO_TC_ATTN", None)
+    d = (a - b).abs() / max(1.0, float(b.abs().max()))
+    # same stated bf16 tolerance as test_perceiver_tf_encoder_bf16: tiny median, MoE routing flips a bounded minority
+    assert float(d.median()) < 5e-3
+    assert float((d.amax(-1) > 0.1).float().mean()) < 0.15

@@ -9,6 +9,7 @@
 // broadcast Q reads), then the probabilities are exchanged through a per-warp
 // smem slab and every lane accumulates its DK/32 output dims.
 #include "ops.cuh"
+#include <stdlib.h>
 
 namespace ymt3 {
 
@@ -287,6 +288,236 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p, int G, in
   for (int d = 0; d < DK; ++d) store1<T>(O + (int64_t)r * p.o_ss + d, o[d] * inv);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiny-sequence attention on the tensor cores (bf16 IO, dk = 16, Sq, Sk <= 128, non-causal): the Perceiver-TF
+// latent (S = 26) and temporal (S = 110) self-attention of the throughput path.  ONE WARP per (batch, head):
+// Q, K, V rows (32 bytes each) are staged in shared memory as bf16 (lane per row; scale and rotate-half RoPE
+// applied in fp32 on the way in), then per 16-query tile  S = Q K^T  (mma.sync m16n8k16, one k-step, B fragments by
+// ldmatrix), a register softmax over the whole key range (fp32, quad shuffles), P repacked in registers from the
+// accumulator layout into A fragments, and  O = P V  (B fragments by ldmatrix.trans).  The fp32 SIMT kernel above
+// ran at 16 TFLOP/s (2.5 ms per temporal layer at B = 256); this one is bound by the 32-byte row gathers.
+// 16-byte chunk c of row r sits at r*32 + ((c ^ ((r >> 2) & 1)) << 4): conflict-free ldmatrix with 32-byte rows.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint32_t tc_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t tc_row_off(int r, int c) { return (uint32_t)(r * 32 + ((c ^ ((r >> 2) & 1)) << 4)); }
+__device__ __forceinline__ void tc_ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void tc_ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void tc_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tc_pack(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// stage `rows` rows of 16 bf16 (global row stride ss) into the swizzled tile; rows [rows, rows_pad) are zeroed.
+// HALF = rope_dim / 2 (compile time so the value array stays in registers); position = row index
+template <int HALF>
+__device__ __forceinline__ void tc_stage(unsigned char* tile, const __nv_bfloat16* src, int64_t ss, int rows, int rows_pad,
+                                         float scale, const float* rope_cos, const float* rope_sin, int lane) {
+  for (int r = lane; r < rows_pad; r += 32) {
+    uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
+    if (r < rows) {
+      const uint4* g = reinterpret_cast<const uint4*>(src + (int64_t)r * ss);
+      c0 = g[0];
+      c1 = g[1];
+      if (HALF > 0 || scale != 1.0f) {
+        float v[16];
+        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&c0);
+        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&c1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __bfloat1622float2(h0[i]), b = __bfloat1622float2(h1[i]);
+          v[2 * i] = a.x * scale; v[2 * i + 1] = a.y * scale;
+          v[8 + 2 * i] = b.x * scale; v[8 + 2 * i + 1] = b.y * scale;
+        }
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+          const float c = rope_cos[r * HALF + i], sn = rope_sin[r * HALF + i];
+          const float x1 = v[i], x2 = v[i + HALF];
+          v[i] = x1 * c - x2 * sn;
+          v[i + HALF] = x2 * c + x1 * sn;
+        }
+        c0 = make_uint4(tc_pack(v[0], v[1]), tc_pack(v[2], v[3]), tc_pack(v[4], v[5]), tc_pack(v[6], v[7]));
+        c1 = make_uint4(tc_pack(v[8], v[9]), tc_pack(v[10], v[11]), tc_pack(v[12], v[13]), tc_pack(v[14], v[15]));
+      }
+    }
+    *reinterpret_cast<uint4*>(tile + tc_row_off(r, 0)) = c0;
+    *reinterpret_cast<uint4*>(tile + tc_row_off(r, 1)) = c1;
+  }
+}
+
+// NT = Sk_pad / 8 key tiles (compile time so the score accumulators stay in registers)
+template <int NT, int HALF>
+__global__ void __launch_bounds__(128) attn_small_tc_kernel(AttnParams p, int64_t total_bh) {
+  extern __shared__ __align__(16) unsigned char tc_sm[];
+  constexpr int SKP = NT * 8;                 // padded key count (multiple of 16)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t bh = (int64_t)blockIdx.x * 4 + warp;
+  if (bh >= total_bh) return;                 // whole warp; no block-level barrier is used below
+  const int sqp = (p.Sq + 15) & ~15;
+  unsigned char* Qs = tc_sm + (size_t)warp * (sqp + 2 * SKP) * 32;
+  unsigned char* Ks = Qs + (size_t)sqp * 32;
+  unsigned char* Vs = Ks + (size_t)SKP * 32;
+  const int h = (int)(bh % p.H);
+  const int64_t b = bh / p.H;
+  int64_t bo = b, bi = 0;
+  if (p.inner > 1) {
+    bo = b / p.inner;
+    bi = b - bo * p.inner;
+  }
+  typedef __nv_bfloat16 T;
+  const T* Q = static_cast<const T*>(p.Q) + bo * p.q_sb + bi * p.q_sb2 + (int64_t)h * p.q_sh;
+  const T* K = static_cast<const T*>(p.K) + bo * p.k_sb + bi * p.k_sb2 + (int64_t)h * p.k_sh;
+  const T* V = static_cast<const T*>(p.V) + bo * p.v_sb + bi * p.v_sb2 + (int64_t)h * p.v_sh;
+  T* O = static_cast<T*>(p.O) + bo * p.o_sb + bi * p.o_sb2 + (int64_t)h * p.o_sh;
+  const int kv_len = p.kv_len ? min(p.kv_len[b], p.Sk) : p.Sk;
+  tc_stage<HALF>(Qs, Q, p.q_ss, p.Sq, sqp, p.scale, p.rope_cos, p.rope_sin, lane);
+  tc_stage<HALF>(Ks, K, p.k_ss, kv_len, SKP, 1.0f, p.rope_cos, p.rope_sin, lane);
+  tc_stage<0>(Vs, V, p.v_ss, kv_len, SKP, 1.0f, nullptr, nullptr, lane);
+  __syncwarp();
+
+  const int g = lane >> 2, t = lane & 3;
+  const int lr = lane & 7, lm = lane >> 3;
+  const uint32_t qs = tc_smem_addr(Qs), ks = tc_smem_addr(Ks), vs = tc_smem_addr(Vs);
+  for (int m0 = 0; m0 < p.Sq; m0 += 16) {
+    // A fragment of the 16 x 16 query tile: matrices (rows 0-7, c0), (rows 8-15, c0), (rows 0-7, c1), (rows 8-15, c1)
+    uint32_t a0, a1, a2, a3;
+    tc_ldsm_x4(qs + tc_row_off(m0 + lr + ((lm & 1) << 3), lm >> 1), a0, a1, a2, a3);
+    float sacc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; j += 2) {
+      // B fragments of key tiles j, j+1: matrices (keys 8j.., c0), (keys 8j.., c1), (keys 8j+8.., c0), (keys 8j+8.., c1)
+      uint32_t b0, b1, b2, b3;
+      tc_ldsm_x4(ks + tc_row_off(8 * j + lr + ((lm >> 1) << 3), lm & 1), b0, b1, b2, b3);
+      sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+      sacc[j + 1][0] = sacc[j + 1][1] = sacc[j + 1][2] = sacc[j + 1][3] = 0.f;
+      tc_mma(sacc[j], a0, a1, a2, a3, b0, b1);
+      tc_mma(sacc[j + 1], a0, a1, a2, a3, b2, b3);
+    }
+    // softmax over keys [0, kv_len) for rows g (c0, c1) and g + 8 (c2, c3); this thread holds keys 8j + 2t, +1
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int k0 = 8 * j + 2 * t;
+      if (k0 >= kv_len) sacc[j][0] = sacc[j][2] = -INFINITY;
+      if (k0 + 1 >= kv_len) sacc[j][1] = sacc[j][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(sacc[j][0], sacc[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(sacc[j][2], sacc[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float LOG2E = 1.4426950408889634f;
+    const float mb0 = mx0 == -INFINITY ? 0.f : mx0 * LOG2E, mb1 = mx1 == -INFINITY ? 0.f : mx1 * LOG2E;
+    float l0 = 0.f, l1 = 0.f;
+    float oacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      // P of key tiles 2kk, 2kk+1 = one k-step of 16 keys, repacked from the accumulator layout into an A fragment
+      float pv[8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        pv[4 * u + 0] = exp2f(fmaf(sacc[2 * kk + u][0], LOG2E, -mb0));
+        pv[4 * u + 1] = exp2f(fmaf(sacc[2 * kk + u][1], LOG2E, -mb0));
+        pv[4 * u + 2] = exp2f(fmaf(sacc[2 * kk + u][2], LOG2E, -mb1));
+        pv[4 * u + 3] = exp2f(fmaf(sacc[2 * kk + u][3], LOG2E, -mb1));
+      }
+      l0 += (pv[0] + pv[1]) + (pv[4] + pv[5]);
+      l1 += (pv[2] + pv[3]) + (pv[6] + pv[7]);
+      const uint32_t pa0 = tc_pack(pv[0], pv[1]), pa1 = tc_pack(pv[2], pv[3]);
+      const uint32_t pa2 = tc_pack(pv[4], pv[5]), pa3 = tc_pack(pv[6], pv[7]);
+      // B fragments of V for keys 16kk .. 16kk+15: (keys lo, c0), (keys hi, c0), (keys lo, c1), (keys hi, c1), transposed
+      uint32_t v0, v1, v2, v3;
+      tc_ldsm_x4_t(vs + tc_row_off(16 * kk + lr + ((lm & 1) << 3), lm >> 1), v0, v1, v2, v3);
+      tc_mma(oacc[0], pa0, pa1, pa2, pa3, v0, v1);
+      tc_mma(oacc[1], pa0, pa1, pa2, pa3, v2, v3);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+    // this thread: row g -> dims 2t, 2t+1 (tile 0) and 8 + 2t, +1 (tile 1); same for row g + 8
+    const int r0 = m0 + g, r1 = m0 + g + 8;
+    if (r0 < p.Sq) {
+      T* o = O + (int64_t)r0 * p.o_ss + 2 * t;
+      *reinterpret_cast<uint32_t*>(o) = tc_pack(oacc[0][0] * i0, oacc[0][1] * i0);
+      *reinterpret_cast<uint32_t*>(o + 8) = tc_pack(oacc[1][0] * i0, oacc[1][1] * i0);
+    }
+    if (r1 < p.Sq) {
+      T* o = O + (int64_t)r1 * p.o_ss + 2 * t;
+      *reinterpret_cast<uint32_t*>(o) = tc_pack(oacc[0][2] * i1, oacc[0][3] * i1);
+      *reinterpret_cast<uint32_t*>(o + 8) = tc_pack(oacc[1][2] * i1, oacc[1][3] * i1);
+    }
+    __syncwarp();
+  }
+}
+
+template <int NT, int HALF>
+bool launch_small_tc2(const AttnParams& p, cudaStream_t stream) {
+  const int sqp = (p.Sq + 15) & ~15;
+  const size_t smem = (size_t)4 * (sqp + 2 * NT * 8) * 32;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_small_tc_kernel<NT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * 128 * 32) !=
+        cudaSuccess)
+      return false;
+    configured = true;
+  }
+  const int64_t total_bh = (int64_t)p.B * p.H;
+  const int64_t blocks = (total_bh + 3) / 4;
+  if (blocks >= (1ll << 31)) return false;
+  attn_small_tc_kernel<NT, HALF><<<(unsigned)blocks, 128, smem, stream>>>(p, total_bh);
+  return true;
+}
+
+template <int NT>
+bool launch_small_tc(const AttnParams& p, cudaStream_t stream) {
+  switch (p.rope_dim) {
+    case 0: return launch_small_tc2<NT, 0>(p, stream);
+    case 8: return launch_small_tc2<NT, 4>(p, stream);
+    case 16: return launch_small_tc2<NT, 8>(p, stream);
+    default: return false;   // other rotary widths: the fp32 kernel
+  }
+}
+
+// bf16, dk 16, short non-causal sequences whose rows are 16-byte aligned: the tensor-core kernel
+bool try_launch_small_tc(const AttnParams& p, cudaStream_t stream) {
+  if (p.dk != 16 || p.causal || p.Sq > 128 || p.Sk > 128 || (p.rope_dim > 0 && p.Sq != p.Sk) || p.rope_dim > 16) return false;
+  if ((p.q_ss % 8 | p.k_ss % 8 | p.v_ss % 8 | p.q_sh % 8 | p.k_sh % 8 | p.v_sh % 8 | p.q_sb % 8 | p.k_sb % 8 | p.v_sb % 8 |
+       p.q_sb2 % 8 | p.k_sb2 % 8 | p.v_sb2 % 8 | p.o_ss % 2 | p.o_sh % 2 | p.o_sb % 2 | p.o_sb2 % 2) != 0)
+    return false;
+  if ((((uintptr_t)p.Q | (uintptr_t)p.K | (uintptr_t)p.V) & 15) != 0 || ((uintptr_t)p.O & 3) != 0) return false;
+  if (getenv("YMT3_NO_TC_ATTN")) return false;
+  const int nt = ((p.Sk + 15) / 16) * 2;
+  switch (nt) {
+    case 2: return launch_small_tc<2>(p, stream);
+    case 4: return launch_small_tc<4>(p, stream);
+    case 6: return launch_small_tc<6>(p, stream);
+    case 8: return launch_small_tc<8>(p, stream);
+    case 10: return launch_small_tc<10>(p, stream);
+    case 12: return launch_small_tc<12>(p, stream);
+    case 14: return launch_small_tc<14>(p, stream);
+    default: return launch_small_tc<16>(p, stream);
+  }
+}
+
+}  // namespace
+
 template <typename T, int DK>
 static bool try_launch_small(const AttnParams& p, cudaStream_t stream) {
   if (p.Sq > 128 || p.Sk > 128) return false;
@@ -303,6 +534,12 @@ static bool try_launch_small(const AttnParams& p, cudaStream_t stream) {
 
 template <typename T>
 static int launch_attn(const AttnParams& p, cudaStream_t stream) {
+  if constexpr (sizeof(T) == 2) {
+    if (try_launch_small_tc(p, stream)) {
+      YMT3_CUDA_CHECK(cudaGetLastError());
+      return YMT3_OK;
+    }
+  }
   if ((p.dk == 16 && try_launch_small<T, 16>(p, stream)) || (p.dk == 32 && try_launch_small<T, 32>(p, stream))) {
     YMT3_CUDA_CHECK(cudaGetLastError());
     return YMT3_OK;

@@ -29,8 +29,8 @@ int ymt3_num_sms() {
 bool ymt3_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("YMT3_NO_PDL");
-    v = (e && e[0] && e[0] != '0') ? 0 : 1;
+    const char* e = getenv("YMT3_PDL");   // opt-in: measured slower inside the decode graph (common.cuh)
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
   }
   return v == 1;
 }

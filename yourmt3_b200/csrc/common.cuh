@@ -49,7 +49,10 @@ int ymt3_num_sms();
 // drains, instead of after it has fully retired.  Contract: a kernel launched through ymt3_launch_pdl must call
 // pdl_wait() before its first access to global memory (griddepcontrol.wait returns once every prerequisite grid has
 // completed and its writes are visible, so RAW and WAR hazards are both covered) and pdl_launch_dependents() as
-// early as it likes.  Both are no-ops for ordinary launches.  YMT3_NO_PDL=1 disables the attribute (A/B timing).
+// early as it likes.  Both are no-ops for ordinary launches.  MEASURED (A/B on B200, CUDA-graph decode loop): no gain for
+// YPTF.MoE+Multi at 3328-6656 sequences (619.6 vs 614.5 ms) and 8 % SLOWER for T5-small at 256 sequences (1093 vs
+// 1003 ms per batch) - early-scheduled dependents sit on SM resources while they wait - so the attribute is OFF by
+// default and only set when YMT3_PDL=1.
 bool ymt3_pdl_enabled();
 #if defined(__CUDACC__)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -32,7 +32,8 @@ def run(dev):
     m16 = _small("bf16").to(dev)
     t16 = m16.inference(torch.from_numpy(audio).unsqueeze(1).to(dev), stop_at_eos=False).cpu().numpy().reshape(26, 8)
     agree = float((t16[:, 0] == got[:, 0]).mean())
-    print(f"smoke yptf_moe_multi bf16 (tcgen05 GEMMs / implicit-GEMM convs): first-token agreement with fp32 {agree:.2f}")
+    print(f"smoke yptf_moe_multi bf16 (tcgen05 GEMMs / implicit-GEMM convs, fused RMSNorm, absorbed cross-attention="
+          f"{m16._absorbed()}): first-token agreement with fp32 {agree:.2f}")
     assert agree >= 0.6
     # T5-small shape, 1 layer each, bf16
     cfg = ymt3.get_model_cfg("mt3_t5_small")

@@ -12,5 +12,7 @@ from .t5mod_helper import task_cond_dec_generate  # noqa: F401
 from .lm_head import LMHead  # noqa: F401
 from .ymt3 import YourMT3  # noqa: F401
 from .init_utils import init_nondegenerate_  # noqa: F401
+from .checkpoint import load_checkpoint  # noqa: F401
+from .midi import write_midi  # noqa: F401
 
 __version__ = "0.1.0"

@@ -58,3 +58,17 @@ def assert_frontend_close(got, ref, tol=1e-4, strict_everywhere=True):
         assert big.mean() > 0.99
         assert d[big].max() < tol, f"log-domain rel err {d[big].max():.3e} on bins within 40 dB of peak"
         assert d.max() < 1e-2
+
+
+def fill_by_name_(named_tensors, std=0.08, norm_jitter=0.1):
+    """Deterministic weights that depend only on the parameter NAME and shape (seed = crc32(name)), so the HF-side
+    generator of tests/golden/t5_hf_*.npz (tools/make_golden_t5.py) and the native-side tests build identical
+    weights without storing them.  >= 2-D: N(0, std); 1-D (norm scales): 1 + N(0, norm_jitter)."""
+    import zlib
+    with torch.no_grad():
+        for name, p in named_tensors:
+            g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+            if p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+            else:
+                p.copy_(1.0 + norm_jitter * torch.randn(p.shape, generator=g))

@@ -471,12 +471,14 @@ template <int NT, int HALF>
 bool launch_small_tc2(const AttnParams& p, cudaStream_t stream) {
   const int sqp = (p.Sq + 15) & ~15;
   const size_t smem = (size_t)4 * (sqp + 2 * NT * 8) * 32;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};   // per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     if (cudaFuncSetAttribute(attn_small_tc_kernel<NT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * 128 * 32) !=
         cudaSuccess)
       return false;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const int64_t total_bh = (int64_t)p.B * p.H;
   const int64_t blocks = (total_bh + 3) / 4;

@@ -323,10 +323,12 @@ int cross_attn_absorbed(const void* q, int64_t q_ld, const void* z, void* out, i
   int stages = 3;
   while (stages > 1 && absorbed_smem(Tp, stages) > max_smem) --stages;
   const size_t smem = absorbed_smem(Tp, stages) + 1024;
-  static size_t configured = 0;   // largest dynamic smem opted into so far
-  if (smem > configured) {
+  static size_t configured[64] = {0};   // per device: largest dynamic smem opted into so far
+  int dev = 0;
+  YMT3_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
     YMT3_CUDA_CHECK(cudaFuncSetAttribute(cross_attn_absorbed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
   }
   CUtensorMap mq, mz;
   int rc;

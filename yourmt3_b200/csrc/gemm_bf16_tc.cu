@@ -549,11 +549,13 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   t.ss_out = p.ss_out; t.ss_out_chunks = (p.N + 31) / 32;
   t.row_scale = p.row_scale; t.group_offsets = p.group_offsets; t.num_groups = groups; t.out_f32 = out_dtype == YMT3_F32;
   t.conv_T = cg.T; t.conv_F = cg.F; t.conv_cblocks = CONV ? cg.Cin / BK : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};   // per device (the attribute is per device and function)
+  int dev = 0;
+  YMT3_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SmemLayout<BN>::TOTAL));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   // persistent: one CTA per SM (or per tile when there are fewer tiles than SMs); in grouped mode the tile
   // count depends on device-side offsets, so all SMs are launched and idle CTAs exit after setup

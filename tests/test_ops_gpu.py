@@ -186,7 +186,10 @@ def test_norm_attention_bf16_io(cuda_device, native_lib):
 
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
-@pytest.mark.parametrize("N,H,step,Lcap", [(5, 6, 0, 16), (7, 6, 37, 64), (300, 6, 200, 256)])
+@pytest.mark.parametrize("N,H,step,Lcap", [(5, 6, 0, 16), (7, 6, 37, 64), (300, 6, 200, 256),
+                                            # few sequences, long cache: 8 / 4 warps per (sequence, head), incl. a
+                                            # ragged last block (step + 1 not a multiple of 16) and idle warps
+                                            (3, 6, 500, 1024), (64, 6, 1023, 1024), (150, 6, 3, 64), (1, 1, 17, 32)])
 def test_decode_attention_self_and_cross(cuda_device, native_lib, dtype, N, H, step, Lcap):
     """single-query attention over the KV cache (decode.cu) vs plain torch fp32: self mode appends the new K/V row at
     *step and attends [0, step]; cross mode attends [0, fixed_len)."""

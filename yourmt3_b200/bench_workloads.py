@@ -13,7 +13,7 @@ SEG_SAMPLES = 32767
 
 PRESETS = {
     # name: (model preset, audio overrides, default batch, precision)
-    "t5_small": ("mt3_t5_small", {}, 256, "bf16"),
+    "t5_small": ("mt3_t5_small", {}, 512, "bf16"),   # 626x at 256, 834x at 512 (profiles/r01_ab_decode_attn_split_length.txt)
     "t5_small_f32": ("mt3_t5_small", {}, 64, "f32"),
     "yptf": ("yptf", {"codec": "spec", "hop_length": 300}, 64, "bf16"),
     # batch: 887x realtime per GPU at 256, 957x at 512, 998x at 1024 (fixed per-kernel latencies of the decode step

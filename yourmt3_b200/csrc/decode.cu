@@ -107,12 +107,15 @@ template <> struct Slice8<__nv_bfloat16> {
   }
 };
 
-// ONE WARP per (sequence, head): no block barriers, no shared memory.  Lane = (grp 0..3, sub 0..7): the 8
-// lanes of a group share one key row (16-byte slices; the warp's 4 groups read 4 consecutive rows = 512
-// contiguous bytes in the self cache), each group walks keys grp, grp+4, ... four at a time (8 x 16-byte loads
+// W WARPS per (sequence, head); W = 1 (every large batch): no block barriers, no shared memory.  Lane = (grp 0..3,
+// sub 0..7): the 8 lanes of a group share one key row (16-byte slices; the warp's 4 groups read 4 consecutive rows =
+// 512 contiguous bytes in the self cache), each group walks keys grp, grp+4, ... four at a time (8 x 16-byte loads
 // in flight per lane) with a private online-softmax state; the 4 group states are merged with xor-shuffles.
-template <typename T>
-__global__ void __launch_bounds__(128, 6)
+// W > 1 (few sequences: the single-channel decoders at small batch, where W = 1 leaves 2-10 warps per SM and the
+// walk over up to 1024 keys is latency-bound): the W warps of a pair take the 16-key blocks round-robin and their
+// states are merged through shared memory by warp 0 of the pair (split-length / flash-decoding).
+template <typename T, int W>
+__global__ void __launch_bounds__(W > 4 ? 32 * W : 128, W > 4 ? 3 : 6)
 decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ knew, const T* __restrict__ vnew,
                    int64_t new_ld, T* __restrict__ Kc, T* __restrict__ Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss,
                    const int* __restrict__ step, int fixed_len, float scale, T* __restrict__ out, int64_t out_ld, int H,
@@ -120,9 +123,13 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
   constexpr int DK = 64, NG = 4, U = 4;
   pdl_launch_dependents();
   pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int64_t pair = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);   // (n, h) index, h fastest
-  if (pair >= total) return;
+  constexpr int WARPS = W > 4 ? W : 4, PPB = WARPS / W;   // warps / (sequence, head) pairs per block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wsub = warp % W;                                // this warp's share of the pair's key blocks
+  int64_t pair = (int64_t)blockIdx.x * PPB + warp / W;      // (n, h) index, h fastest
+  const bool valid = pair < total;
+  if (W == 1 && !valid) return;
+  if (!valid) pair = total - 1;                             // W > 1: idle warps still reach the block barrier
   const int h = (int)(pair % H);
   const int64_t n = pair / H;
   const int grp = lane >> 3, sub = lane & 7;
@@ -140,9 +147,12 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
     vn = vnew + n * new_ld + h * DK + 8 * sub;
     s_new = *step;
     len = s_new + 1;
-    if (lane < 8) Slice8<T>::copy(Kb + (int64_t)s_new * c_ss + 8 * sub, kn);
-    else if (lane < 16) Slice8<T>::copy(Vb + (int64_t)s_new * c_ss + 8 * sub, vn);
+    if (wsub == 0 && valid) {
+      if (lane < 8) Slice8<T>::copy(Kb + (int64_t)s_new * c_ss + 8 * sub, kn);
+      else if (lane < 16) Slice8<T>::copy(Vb + (int64_t)s_new * c_ss + 8 * sub, vn);
+    }
   }
+  if (!valid) len = 0;
   float qv[8];
 
   float m = -INFINITY, l = 0.f, o[8];
@@ -150,7 +160,8 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
 
   // uniform trip count for the whole warp (the shuffles below name all 32 lanes)
-  for (int base = 0; base < len; base += NG * U) {
+  bool first = true;
+  for (int base = wsub * NG * U; base < len; base += W * NG * U) {
     typename Slice8<T>::Raw kk[U], vv[U];   // kept packed until use (register pressure -> occupancy)
     float sc[U];
     bool has[U];
@@ -164,7 +175,8 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
         vv[u] = Slice8<T>::load_raw(fresh ? vn : Vb + (int64_t)j * c_ss + 8 * sub);
       }
     }
-    if (base == 0) {   // first consumption of q: after the first K/V loads are in flight
+    if (first) {   // first consumption of q: after the first K/V loads are in flight
+      first = false;
       Slice8<T>::unpack(qraw, qv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) qv[i] *= scale;
@@ -221,6 +233,32 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
     }
     m = M;
   }
+  if constexpr (W > 1) {
+    // states of the pair's W warps -> shared memory -> merged in warp order by its first warp
+    __shared__ float st[WARPS][8][10];
+    if (grp == 0) {
+      float* d = st[warp][sub];
+      d[0] = m; d[1] = l;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[2 + i] = o[i];
+    }
+    __syncthreads();
+    if (wsub != 0 || !valid) return;
+    if (grp == 0) {
+#pragma unroll
+      for (int w2 = 1; w2 < W; ++w2) {
+        const float* d = st[warp + w2][sub];
+        const float m2 = d[0], l2 = d[1];
+        const float M = fmaxf(m, m2);
+        const float a = m == -INFINITY ? 0.f : expf(m - M);
+        const float b2 = m2 == -INFINITY ? 0.f : expf(m2 - M);
+        l = l * a + l2 * b2;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = o[i] * a + d[2 + i] * b2;
+        m = M;
+      }
+    }
+  }
   if (grp == 0) {
     const float inv = 1.0f / l;
     T* dst = out + n * out_ld + h * DK + 8 * sub;
@@ -241,21 +279,41 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
                      void* Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss, int Lmax, const int* step, int fixed_len,
                      float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream) {
   if (N <= 0) return YMT3_OK;
-  (void)Lmax;
   YMT3_REQUIRE(dk == 64, "decode_attention: head dim must be 64 (got %d)", dk);
   YMT3_REQUIRE((q_ld % 8 | new_ld % 8 | c_sn % 8 | c_sh % 8 | c_ss % 8 | out_ld % 8) == 0,
                "decode_attention: strides must be multiples of 8 elements");
   const int64_t total = (int64_t)N * H;
-  const unsigned grid = (unsigned)((total + 3) / 4);
-  if (dtype == YMT3_F32)
-    YMT3_CUDA_CHECK(ymt3_launch_pdl(decode_attn_kernel<float>, dim3(grid), dim3(128), 0, stream, (const float*)q, q_ld,
-                                    (const float*)knew, (const float*)vnew, new_ld, (float*)Kc, (float*)Vc, c_sn, c_sh,
-                                    c_ss, step, fixed_len, scale, (float*)out, out_ld, H, total));
-  else
-    YMT3_CUDA_CHECK(ymt3_launch_pdl(decode_attn_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream,
-                                    (const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)knew,
-                                    (const __nv_bfloat16*)vnew, new_ld, (__nv_bfloat16*)Kc, (__nv_bfloat16*)Vc, c_sn,
-                                    c_sh, c_ss, step, fixed_len, scale, (__nv_bfloat16*)out, out_ld, H, total));
+  // warps per (sequence, head): 1 when the batch alone fills the SMs (>= 16 warps per SM), otherwise split the key
+  // range over 2 / 4 / 8 warps, never finer than one 16-key block per warp at the longest length this call can see
+  static int forced_w = -1;
+  if (forced_w < 0) {
+    const char* e = getenv("YMT3_DECODE_ATTN_WARPS");   // profiling aid: 1 / 2 / 4 / 8, 0 = automatic
+    forced_w = e ? atoi(e) : 0;
+  }
+  const int64_t want = (int64_t)ymt3_num_sms() * 16;
+  const int max_len = knew ? Lmax : fixed_len;
+  int w = 1;
+  while (w < 8 && total * w < want && 16 * (2 * w) <= max_len) w *= 2;
+  if (forced_w == 1 || forced_w == 2 || forced_w == 4 || forced_w == 8) w = forced_w;
+#define YMT3_LAUNCH_DECODE_ATTN(TT, WW)                                                                                \
+  YMT3_CUDA_CHECK(ymt3_launch_pdl(decode_attn_kernel<TT, WW>, dim3((unsigned)ymt3_div_up(total, (WW > 4 ? WW : 4) / WW)), \
+                                  dim3(32 * (WW > 4 ? WW : 4)), 0, stream, (const TT*)q, q_ld, (const TT*)knew,         \
+                                  (const TT*)vnew, new_ld, (TT*)Kc, (TT*)Vc, c_sn, c_sh, c_ss, step, fixed_len, scale,    \
+                                  (TT*)out, out_ld, H, total))
+#define YMT3_DISPATCH_DECODE_ATTN(TT)                                                                                  \
+  switch (w) {                                                                                                         \
+    case 1: YMT3_LAUNCH_DECODE_ATTN(TT, 1); break;                                                                     \
+    case 2: YMT3_LAUNCH_DECODE_ATTN(TT, 2); break;                                                                     \
+    case 4: YMT3_LAUNCH_DECODE_ATTN(TT, 4); break;                                                                     \
+    default: YMT3_LAUNCH_DECODE_ATTN(TT, 8); break;                                                                    \
+  }
+  if (dtype == YMT3_F32) {
+    YMT3_DISPATCH_DECODE_ATTN(float)
+  } else {
+    YMT3_DISPATCH_DECODE_ATTN(__nv_bfloat16)
+  }
+#undef YMT3_DISPATCH_DECODE_ATTN
+#undef YMT3_LAUNCH_DECODE_ATTN
   return YMT3_OK;
 }
 

@@ -116,6 +116,7 @@ struct TcParams {
   const float* row_scale;
   const float* norm_ss_in; int norm_ss_chunks; float norm_eps;   // fused RMSNorm, consumer side (ops.cuh)
   float* ss_out; int ss_out_chunks;                               // fused RMSNorm, producer side
+  unsigned long long* argmax_out; int argmax_n;                   // fused greedy selection (ops.cuh)
   const int* group_offsets;
   int num_groups;
   int out_f32;
@@ -422,6 +423,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         pre = rsqrtf(tot / (float)p.K + p.norm_eps);
       }
       constexpr int NCHUNK = BN / 32;
+      unsigned long long best_key = 0;   // fused greedy selection: best (logit, column) this thread produced
 #pragma unroll 1
       for (int ci = half; ci < NCHUNK + 2; ci += 2) {
         // (the loop runs one dummy round past the end so that every warp -- also those without a chunk when
@@ -456,6 +458,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               }
             }
             epi_dispatch(f, rs, p.act, p.gated);
+            if (p.argmax_out) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q)
+                if (c + q < p.argmax_n) {
+                  const unsigned long long key = argmax_key(f[q], c + q);
+                  best_key = key > best_key ? key : best_key;
+                }
+            }
             const int n_out = p.gated ? min(16, (p.N - c) >> 1) : min(32, p.N - c);
             const int64_t off = (int64_t)r * p.ldc + (p.gated ? (c >> 1) : c);
             const int64_t roff = (int64_t)r * p.ldr + (p.gated ? (c >> 1) : c);
@@ -467,6 +477,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         if (last) break;
       }
+      if (best_key) atomicMax(p.argmax_out + r, best_key);
     }
   }
 
@@ -547,6 +558,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   t.M = p.M; t.N = p.N; t.K = p.K; t.act = p.act; t.gated = p.gated; t.out_scale = p.out_scale;
   t.norm_ss_in = p.norm_ss_in; t.norm_ss_chunks = p.norm_ss_chunks; t.norm_eps = p.norm_eps;
   t.ss_out = p.ss_out; t.ss_out_chunks = (p.N + 31) / 32;
+  t.argmax_out = p.argmax_out; t.argmax_n = p.argmax_n;
   t.row_scale = p.row_scale; t.group_offsets = p.group_offsets; t.num_groups = groups; t.out_f32 = out_dtype == YMT3_F32;
   t.conv_T = cg.T; t.conv_F = cg.F; t.conv_cblocks = CONV ? cg.Cin / BK : 0;
   static bool attr_set[64] = {false};   // per device (the attribute is per device and function)
@@ -586,6 +598,9 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
                "gemm_bf16_tc: sum-of-squares output needs bf16, non-gated, N %% 32 == 0");
   YMT3_REQUIRE(!p.norm_ss_in || (p.norm_ss_chunks > 0 && ((uintptr_t)p.norm_ss_in & 15) == 0 && p.norm_ss_chunks % 4 == 0),
                "gemm_bf16_tc: fused-norm partials must be 16-byte aligned, a multiple of 4 per row");
+  YMT3_REQUIRE(!p.argmax_out || (out_dtype == YMT3_F32 && !p.gated && !p.residual && !p.group_offsets && p.argmax_n > 0 &&
+                                 p.argmax_n <= p.N),
+               "gemm_bf16_tc: fused arg-max needs fp32 output, no gate / residual / groups, 0 < argmax_n <= N");
   // pick BN so that the grid fills the 148 SMs (2 CTAs/SM resident) when the problem allows
   const int64_t mt = ymt3_div_up(p.M, BM);
   const int sms = ymt3_num_sms();

@@ -138,6 +138,17 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
         o.y = act_apply(v[1], p.act) * rs;
         o.z = act_apply(v[2], p.act) * rs;
         o.w = act_apply(v[3], p.act) * rs;
+        if (p.argmax_out) {   // fused greedy selection (ops.cuh); no residual in this mode
+          const float ov[4] = {o.x, o.y, o.z, o.w};
+          unsigned long long best_key = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < p.argmax_n) {
+              const unsigned long long key = argmax_key(ov[j], c + j);
+              best_key = key > best_key ? key : best_key;
+            }
+          if (best_key) atomicMax(p.argmax_out + r, best_key);
+        }
         if (R) {
           const float4 q = *reinterpret_cast<const float4*>(R + (int64_t)r * p.ldr + c);
           o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
@@ -151,6 +162,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
 int gemm_f32(const GemmParams& p, cudaStream_t stream) {
   YMT3_REQUIRE(!p.norm_ss_in && !p.ss_out, "gemm_f32: fused RMSNorm is a bf16 tensor-core path feature");
   YMT3_REQUIRE(p.A && p.W && p.C, "gemm_f32: null pointer");
+  YMT3_REQUIRE(!p.argmax_out || (!p.gated && !p.residual && !p.group_offsets && p.argmax_n > 0 && p.argmax_n <= p.N),
+               "gemm_f32: fused arg-max needs no gate / residual / groups, 0 < argmax_n <= N");
   if (p.M <= 0 || p.N <= 0) return YMT3_OK;
   YMT3_REQUIRE(p.K > 0 && p.K % 4 == 0 && p.lda % 4 == 0 && p.ldw % 4 == 0,
                "gemm_f32: K, lda, ldw must be multiples of 4 (K=%d lda=%lld ldw=%lld)", p.K,

@@ -110,6 +110,7 @@ int linear_fwd(int precision, const void* x, int64_t ldx, const Linear& lin, voi
                cudaStream_t stream, const NormFuse& nf) {
   GemmParams p{};
   p.norm_ss_in = nf.ss_in; p.norm_ss_chunks = nf.chunks; p.norm_eps = nf.eps; p.ss_out = nf.ss_out;
+  p.argmax_out = nf.argmax_out; p.argmax_n = nf.argmax_n;
   p.A = x; p.lda = ldx;
   p.W = lin.W; p.ldw = lin.K;
   p.C = y; p.ldc = ldy;

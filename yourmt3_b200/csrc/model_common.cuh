@@ -90,6 +90,7 @@ int pack_table(DevicePool& pool, const float* src_dev_or_host, bool src_on_host,
 struct NormFuse {
   const float* ss_in = nullptr; int chunks = 0; float eps = 0.f;
   float* ss_out = nullptr;
+  unsigned long long* argmax_out = nullptr; int argmax_n = 0;   // fused greedy selection (GemmParams::argmax_out)
 };
 int linear_fwd(int precision, const void* x, int64_t ldx, const Linear& lin, void* y, int64_t ldy, int M,
                int act, int gated, const void* residual, int64_t ldr, float out_scale, int out_dtype,

@@ -281,6 +281,14 @@ YMT3_API int ymt3_op_linear_normfused(const void* A, int64_t lda, const void* W,
                                       const float* ss_in, int64_t chunks, float eps, void* C, int64_t ldc,
                                       const void* residual, int64_t ldr, float* ss_out, int64_t M, int64_t N, int64_t K,
                                       int32_t act, int32_t gated, float out_scale, int32_t out_dtype, void* stream);
+/* Vocab projection with the greedy selection fused into its epilogue (the LM head of the decode step; HF
+ * modeling_t5.py:1105-1110 followed by torch.argmax): logits (M, N) fp32 = out_scale * (A @ W^T + bias) are stored AND
+ * every row's arg-max over columns [0, V) is left in keys[m] as  (ordered(logit) << 32) | (0xFFFFFFFF - column)  via
+ * atomicMax - largest logit, smallest column among equals (torch.argmax's first-maximum rule); column =
+ * 0xFFFFFFFF - (keys[m] & 0xFFFFFFFF).  keys (M) must be zero before the call. */
+YMT3_API int ymt3_op_linear_argmax(int32_t dtype, const void* A, int64_t lda, const void* W, int64_t ldw,
+                                   const float* bias, float* logits, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                                   int64_t V, float out_scale, uint64_t* keys, void* stream);
 /* Single-query attention over a device-resident KV cache alone (the decode step's dominant kernel; HF
  * modeling_t5.py:269-305 with use_cache): q (N, H*64); cache K/V (N, H, Lcap, 64).  knew/vnew (N, H*64) non-null:
  * self mode - the row is appended at index *step_dev, then keys [0, *step_dev] are attended.  knew == NULL: cross

@@ -289,3 +289,34 @@ def test_attention_bf16_dk16_tensor_core(cuda_device, native_lib, B, H, Sq, Sk):
     assert float((outs[0] - ref).abs().max()) < 3e-2
     assert float((outs[0] - ref).abs().mean()) < 3e-3
     assert float((outs[1] - ref).abs().max()) < 2e-2          # the SIMT kernel (only the output is rounded)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("M,V,K", [(7, 596, 512), (300, 596, 512), (3328, 1391, 512), (129, 40, 64)])
+def test_linear_argmax_fused_epilogue(cuda_device, native_lib, dtype, M, V, K):
+    """greedy selection fused into the vocab-projection epilogue: the stored fp32 logits are unchanged and the packed key
+    of every row decodes to torch.argmax of those logits over the first V columns (first maximum among equals - rows
+    with duplicated weight rows force exact ties, also across tiles); columns >= V never win."""
+    td, code = (torch.float32, 0) if dtype == "f32" else (torch.bfloat16, 1)
+    g = torch.Generator().manual_seed(M + V)
+    Vp = (V + 7) // 8 * 8
+    W = torch.randn(Vp, K, generator=g) * 0.05
+    W[V:] = 10.0 * W[:Vp - V].abs()                 # padding columns with LARGE logits must be ignored
+    W[5] = W[3]; W[V - 1] = W[3]; W[min(V - 2, 200)] = W[3]      # exact ties, some in another N tile
+    x = torch.randn(M, K, generator=g)
+    x[1] = W[3] * 50.0                              # row 1: the tied columns are the maximum
+    if M > 2:
+        x[2] = 0.0                                  # row 2: all logits equal (0) -> column 0
+    xd, Wd = x.to(cuda_device, td), W.to(cuda_device, td)
+    logits = torch.empty(M, Vp, dtype=torch.float32, device=cuda_device)
+    keys = torch.zeros(M, dtype=torch.int64, device=cuda_device)
+    _lib.check(native_lib.ymt3_op_linear_argmax(code, xd.data_ptr(), K, Wd.data_ptr(), K, None, logits.data_ptr(), Vp, M, Vp, K,
+                                                V, 0.125, keys.data_ptr(), _lib.current_stream_ptr()))
+    plain = torch.empty_like(logits)
+    _lib.check(native_lib.ymt3_op_linear(code, xd.data_ptr(), K, Wd.data_ptr(), K, None, plain.data_ptr(), Vp, None, 0, M, Vp, K,
+                                         0, 0, 0.125, 0, _lib.current_stream_ptr()))
+    assert torch.equal(logits, plain)
+    col = 0xFFFFFFFF - (keys & 0xFFFFFFFF)
+    ref = torch.argmax(logits[:, :V], dim=-1)
+    assert torch.equal(col, ref), (col[:8], ref[:8])
+    assert int(col[1]) == 3 and (M <= 2 or int(col[2]) == 0)

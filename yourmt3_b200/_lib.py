@@ -107,6 +107,7 @@ SIGNATURES = {
     "ymt3_op_attention": (_I, [C.c_int32, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, C.c_float, C.c_int32, _P]),
     "ymt3_op_linear_normfused": (_I, [_P, _I64, _P, _I64, _P, _P, _I64, C.c_float, _P, _I64, _P, _I64, _P, _I64, _I64, _I64,
                                       C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
+    "ymt3_op_linear_argmax": (_I, [C.c_int32, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, C.c_float, _P, _P]),
     "ymt3_op_decode_attention": (_I, [C.c_int32, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _P]),
     "ymt3_op_cross_attn_absorbed": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
 }

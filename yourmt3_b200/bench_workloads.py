@@ -60,8 +60,9 @@ class ModelWorkload:
     def _count_launches(self):
         dec_layers = self.model.model_cfg["decoder"][self.model.decoder_type]["num_layers"]
         # per layer: qkv, self-attention, o, cross q, cross-attention, cross o, wi, wo (+ 3 RMSNorm kernels on the fp32
-        # path; bf16 fuses them into the GEMMs); per step: embed, (final norm,) lm head, greedy select, advance
-        per_step = dec_layers * (8 if self.precision == "bf16" else 11) + (4 if self.precision == "bf16" else 5)
+        # path; bf16 fuses them into the GEMMs); per step: embed, (final norm,) lm head with the fused arg-max,
+        # select + advance
+        per_step = dec_layers * (8 if self.precision == "bf16" else 11) + (3 if self.precision == "bf16" else 4)
         return per_step * self.max_len + 64          # + frontend/encoder launches (lower bound)
 
     def step(self):

@@ -317,78 +317,60 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
   return YMT3_OK;
 }
 
-// Greedy selection. One warp per sequence. torch.argmax tie rule: first maximal index.
-//   tokens_out[n, *step] = finished[n] ? pad : argmax(logits[n, :V]);  finished |= (tok == eos)
-//   cur_tok[n] = tokens_out[n, *step];  unfinished_count += !finished (for the host's optional early stop)
-__global__ void __launch_bounds__(256)
-greedy_select_kernel(const float* __restrict__ logits, int64_t ld, int V, int N, const int* __restrict__ step,
-                     int* __restrict__ cur_tok, int* __restrict__ finished, int* __restrict__ tokens_out,
-                     int max_len, int eos_id, int pad_id, int stop_at_eos, int* __restrict__ unfinished_count,
-                     const int* __restrict__ forced, int n_forced) {
+// Greedy selection, second half.  The arg-max itself is fused into the vocab-projection epilogue
+// (GemmParams::argmax_out: largest logit, first index among equals = torch.argmax); ONE block reads the packed key of
+// every row and applies the loop rules of the reference's greedy generate:
+//   tokens_out[n, *step] = finished[n] ? pad : argmax;  finished |= (tok == eos);  cur_tok[n] = that token
+//   while *step < n_forced (task prefix) the next input is forced[n, *step], nothing is emitted, EOS is not tested
+// then re-arms the keys (0) for the next step, publishes the number of unfinished rows for the host's optional early
+// stop and - after a block barrier - advances the device step counter, so a step ends with this single launch.
+__global__ void __launch_bounds__(1024)
+select_advance_kernel(unsigned long long* __restrict__ keys, int N, int* __restrict__ step, int* __restrict__ cur_tok,
+                      int* __restrict__ finished, int* __restrict__ tokens_out, int max_len, int eos_id, int pad_id,
+                      int stop_at_eos, int* __restrict__ unfinished_count, const int* __restrict__ forced,
+                      int n_forced) {
   pdl_launch_dependents();
   pdl_wait();
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (n >= N) return;
-  const float* row = logits + (int64_t)n * ld;
-  float best = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int i = lane; i < V; i += 32) {
-    const float v = row[i];
-    if (v > best || (v == best && i < bi)) {
-      best = v;
-      bi = i;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) {
-      best = ov;
-      bi = oi;
-    }
-  }
-  if (lane == 0) {
-    const int s = *step;
-    if (s < n_forced) {
-      // task-prefix conditioning: the next decoder input is the given prefix token (teacher forced);
-      // nothing is emitted and EOS is not tested while the prefix is being consumed
+  __shared__ int s_unfinished;
+  if (threadIdx.x == 0) s_unfinished = 0;
+  __syncthreads();
+  const int s = *step;
+  int mine = 0;
+  for (int n = threadIdx.x; n < N; n += 1024) {
+    const unsigned long long key = keys[n];
+    keys[n] = 0ull;
+    if (s < n_forced) {   // task prefix: teacher-forced input, nothing emitted, EOS not tested
       cur_tok[n] = forced[(int64_t)n * n_forced + s];
-      atomicAdd(unfinished_count + (s & 1), 1);
-      return;
+      ++mine;
+      continue;
     }
     const int so = s - n_forced;
+    const int bi = key ? (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull)) : pad_id;
     int fin = finished[n];
-    int tok = fin ? pad_id : bi;
+    const int tok = fin ? pad_id : bi;
     if (stop_at_eos && tok == eos_id) fin = 1;
     finished[n] = fin;
     cur_tok[n] = tok;
     if (so < max_len) tokens_out[(int64_t)n * max_len + so] = tok;
-    if (!fin) atomicAdd(unfinished_count + (s & 1), 1);
+    if (!fin) ++mine;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_unfinished, mine);
+  __syncthreads();   // every thread has read *step
+  if (threadIdx.x == 0) {
+    unfinished_count[s & 1] = s_unfinished;   // rows still running after step s (host early-stop poll)
+    unfinished_count[(s + 1) & 1] = 0;
+    *step = s + 1;
   }
 }
 
-int greedy_select(const float* logits, int64_t ld, int V, int N, const int* step, int* cur_tok, int* finished,
-                  int* tokens_out, int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count,
-                  const int* forced, int n_forced, cudaStream_t stream) {
+int select_advance(unsigned long long* keys, int N, int* step, int* cur_tok, int* finished, int* tokens_out,
+                   int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count, const int* forced,
+                   int n_forced, cudaStream_t stream) {
   if (N <= 0) return YMT3_OK;
-  YMT3_CUDA_CHECK(ymt3_launch_pdl(greedy_select_kernel, dim3(ymt3_div_up(N, 8)), dim3(256), 0, stream, logits, ld, V, N,
-                                  step, cur_tok, finished, tokens_out, max_len, eos_id, pad_id, stop_at_eos,
-                                  unfinished_count, forced, n_forced));
-  return YMT3_OK;
-}
-
-// (*step)++ and reset the unfinished counter slot the NEXT step will accumulate into
-__global__ void advance_step_kernel(int* step, int* unfinished_count) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int s = *step + 1;
-  *step = s;
-  unfinished_count[s & 1] = 0;
-}
-
-int advance_step(int* step, int* unfinished_count, cudaStream_t stream) {
-  YMT3_CUDA_CHECK(ymt3_launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, stream, step, unfinished_count));
+  YMT3_CUDA_CHECK(ymt3_launch_pdl(select_advance_kernel, dim3(1), dim3(1024), 0, stream, keys, N, step, cur_tok, finished,
+                                  tokens_out, max_len, eos_id, pad_id, stop_at_eos, unfinished_count, forced, n_forced));
   return YMT3_OK;
 }
 

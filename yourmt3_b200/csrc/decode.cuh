@@ -15,10 +15,12 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
                      void* Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss, int Lmax, const int* step, int fixed_len,
                      float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream);
 
-// forced (N, n_forced) or null: while *step < n_forced the next input token is forced[n, *step] (task prefix)
-int greedy_select(const float* logits, int64_t ld, int V, int N, const int* step, int* cur_tok, int* finished,
-                  int* tokens_out, int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count,
-                  const int* forced, int n_forced, cudaStream_t stream);
+// The vocab-projection GEMM leaves one packed arg-max key per row (GemmParams::argmax_out, ops.cuh); this single-block
+// launch turns the keys into tokens (finished mask, EOS, forced (N, n_forced) task prefix or null), zeroes them and
+// advances *step.
+int select_advance(unsigned long long* keys, int N, int* step, int* cur_tok, int* finished, int* tokens_out,
+                   int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count, const int* forced,
+                   int n_forced, cudaStream_t stream);
 // Absorbed cross-attention (cross_absorbed.cu): q (N, H*zdim) bf16 latent-space queries, z (N, Tp, zdim) bf16 latents
 // (rows >= T zero), out (N, H*zdim) bf16 = softmax_t(q_h . z_t) z_t per head.  zdim must be 256, H <= 8, Tp % 16 == 0.
 int cross_attn_absorbed(const void* q, int64_t q_ld, const void* z, void* out, int64_t out_ld, int64_t N, int H, int T,
@@ -26,7 +28,6 @@ int cross_attn_absorbed(const void* q, int64_t q_ld, const void* z, void* out, i
 // (B, T, C, zdim) bf16 -> (B*C, Tp, zdim); destination rows >= T are left untouched
 int gather_latents(const void* src, void* dst, int64_t B, int T, int C, int Tp, int zdim, cudaStream_t stream);
 
-int advance_step(int* step, int* unfinished_count, cudaStream_t stream);
 int fill_i32(int* p, int v, int64_t n, cudaStream_t stream);
 
 }  // namespace ymt3

@@ -73,3 +73,17 @@ extern "C" int ymt3_op_linear_normfused(const void* A, int64_t lda, const void* 
   p.norm_ss_in = ss_in; p.norm_ss_chunks = (int)chunks; p.norm_eps = eps; p.ss_out = ss_out;
   return gemm_bf16_tc(p, out_dtype, (cudaStream_t)stream);
 }
+
+extern "C" int ymt3_op_linear_argmax(int32_t dtype, const void* A, int64_t lda, const void* W, int64_t ldw,
+                                     const float* bias, float* logits, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                                     int64_t V, float out_scale, uint64_t* keys, void* stream) {
+  YMT3_REQUIRE(M >= 0 && M < (1ll << 31) && N > 0 && N < (1ll << 31) && K > 0 && K < (1ll << 31) && V > 0 && V <= N,
+               "op_linear_argmax: bad shape");
+  YMT3_REQUIRE(keys, "op_linear_argmax: null keys");
+  GemmParams p{};
+  p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.C = logits; p.ldc = ldc; p.bias = bias;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.out_scale = out_scale;
+  p.argmax_out = reinterpret_cast<unsigned long long*>(keys); p.argmax_n = (int)V;
+  if (dtype == YMT3_F32) return gemm_f32(p, (cudaStream_t)stream);
+  return gemm_bf16_tc(p, YMT3_F32, (cudaStream_t)stream);
+}

@@ -198,6 +198,7 @@ struct ymt3_t5dec {
   std::vector<void*> selfK, selfV, crossKV;   // crossKV[i]: K (N, H, T, dk) followed by V (N, H, T, dk)
   void* kv_tmp = nullptr;                      // (N*T, 2*inner) projection output before the head split
   int *d_step = nullptr, *d_cur = nullptr, *d_fin = nullptr, *d_unfinished = nullptr;
+  unsigned long long* d_amax = nullptr;   // (cap_N) packed arg-max keys of the fused vocab projection
   int* h_unfinished = nullptr;  // pinned
   // the decode loop runs on an internal stream (graph capture is illegal on the legacy default
   // stream); it is ordered after / before the caller's stream with events, no host sync
@@ -361,8 +362,9 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, int latent, cu
   }
   d->d_cur = (int*)d->ws.alloc(cN * 4);
   d->d_fin = (int*)d->ws.alloc(cN * 4);
+  d->d_amax = (unsigned long long*)d->ws.alloc(cN * 8);
   for (int i = 0; i < 3; ++i) d->ss[i] = d->fuse_norm ? (float*)d->ws.alloc((size_t)cN * (D / 32) * 4) : nullptr;
-  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->kv_tmp &&
+  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->d_amax && d->kv_tmp &&
             (!d->fuse_norm || (d->ss[0] && d->ss[1] && d->ss[2]));
   d->selfK.assign(c.num_layers, nullptr);
   d->selfV.assign(c.num_layers, nullptr);
@@ -451,18 +453,19 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
   }
   // final norm + LM head; tied embeddings scale hidden by d_model^-0.5 (modeling_t5.py:1105-1110)
   const float sc = c.tie_word_embeddings ? 1.0f / sqrtf((float)D) : 1.0f;
-  {
-    if (fuse) {
-      if ((rc = linear_fwd(dt, d->x, D, d->lm_head_n, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s, consume(sA)))) return rc;
-    } else {
-      if ((rc = rmsnorm(d->x, d->final_ln, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
-      if ((rc = linear_fwd(dt, d->h, D, d->lm_head, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s))) return rc;
-    }
+  // greedy selection fused into the vocab-projection epilogue: every epilogue thread reduces its logits to one packed
+  // (value, column) key and atomicMax-es it into d_amax[row]; select_advance turns keys into tokens and ends the step.
+  // (A/B against the separate arg-max kernel + step-advance kernel: neutral, profiles/r01_ab_fused_select.txt.)
+  NormFuse nf = fuse ? consume(sA) : NormFuse();
+  nf.argmax_out = d->d_amax; nf.argmax_n = c.vocab_size;
+  if (fuse) {
+    if ((rc = linear_fwd(dt, d->x, D, d->lm_head_n, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s, nf))) return rc;
+  } else {
+    if ((rc = rmsnorm(d->x, d->final_ln, d->h, N, D, c.layer_norm_eps, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, d->h, D, d->lm_head, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s, nf))) return rc;
   }
-  if ((rc = greedy_select(d->logits, d->Vp, c.vocab_size, (int)N, d->d_step, d->d_cur, d->d_fin, tokens_out, Lmax,
-                          c.eos_id, c.pad_id, stop_at_eos, d->d_unfinished, n_prefix ? d->d_forced : nullptr, n_prefix, s)))
-    return rc;
-  return advance_step(d->d_step, d->d_unfinished, s);
+  return select_advance(d->d_amax, (int)N, d->d_step, d->d_cur, d->d_fin, tokens_out, Lmax, c.eos_id, c.pad_id,
+                        stop_at_eos, d->d_unfinished, n_prefix ? d->d_forced : nullptr, n_prefix, s);
 }
 
 }  // namespace
@@ -535,6 +538,7 @@ int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int
   if ((rc = fill_i32(d->d_step, 0, 8, s))) return rc;  // step + unfinished[2] (+pad)
   if ((rc = fill_i32(d->d_cur, c.start_id, N, s))) return rc;
   if ((rc = fill_i32(d->d_fin, 0, N, s))) return rc;
+  YMT3_CUDA_CHECK(cudaMemsetAsync(d->d_amax, 0, (size_t)N * 8, s));
   if ((rc = fill_i32(tokens_out, c.pad_id, N * max_len, s))) return rc;
   if (latent) {
     // the only per-call encoder-side work: latents regrouped per sequence (channel-major), time padded to 16

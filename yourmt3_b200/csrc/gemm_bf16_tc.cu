@@ -12,6 +12,8 @@
 // MMAs of tile i+1.
 #include "ops.cuh"
 #include <cuda.h>
+#include <cstring>
+#include <cstdlib>
 
 namespace ymt3 {
 
@@ -58,6 +60,18 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// TMA store of one staged box (shared -> global), bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {   // <= N groups may still be READING their smem source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -117,6 +131,7 @@ struct TcParams {
   const float* norm_ss_in; int norm_ss_chunks; float norm_eps;   // fused RMSNorm, consumer side (ops.cuh)
   float* ss_out; int ss_out_chunks;                               // fused RMSNorm, producer side
   unsigned long long* argmax_out; int argmax_n;                   // fused greedy selection (ops.cuh)
+  int tma_store;   // bf16 output leaves through per-warp smem staging + TMA stores (mapC) instead of 16-byte st.global
   const int* group_offsets;
   int num_groups;
   int out_f32;
@@ -166,6 +181,45 @@ __device__ __forceinline__ void epi_dispatch(float (&f)[32], float rs, int act, 
     default: epi_math<YMT3_ACT_GELU, true>(f, rs); break;
   }
 }
+// round `count` (multiple of 8, <= 32) outputs (+ residual R) of one row to bf16 and hand every 16-byte unit j to
+// sink(j, unit) as soon as it is packed; returns the sum of squares of the ROUNDED values when want_ss (fused RMSNorm
+// producer)
+template <typename Sink>
+__device__ __forceinline__ float epi_pack_bf16(const __nv_bfloat16* R, const float (&f)[32], int count, bool want_ss,
+                                               Sink&& sink) {
+  uint4 r[4];
+  if (R) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (8 * j < count) r[j] = *reinterpret_cast<const uint4*>(R + 8 * j);   // all residual loads in flight first
+  }
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (8 * j >= count) break;
+    uint4 pk;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+    if (R) {
+      const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&r[j]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q] + __bfloat162float(th[q].x),
+                                     f[8 * j + 2 * q + 1] + __bfloat162float(th[q].y));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
+    }
+    if (want_ss) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 v2 = __bfloat1622float2(h[q]);
+        sq = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, sq));
+      }
+    }
+    sink(j, pk);
+  }
+  return sq;
+}
 // store `count` (multiple of 8 for bf16 / 4 for f32, <= 32) consecutive outputs f[0..count) of one row (+ residual)
 // ss != null (bf16 output only): *ss = sum of squares of the bf16-rounded values stored (fused RMSNorm producer)
 template <bool OUT_F32>
@@ -190,37 +244,8 @@ __device__ __forceinline__ void epi_store(void* Cbase, const void* Rbase, int64_
   } else {
     __nv_bfloat16* C = static_cast<__nv_bfloat16*>(Cbase) + off;
     const __nv_bfloat16* R = Rbase ? static_cast<const __nv_bfloat16*>(Rbase) + off : nullptr;
-    uint4 r[4];
-    if (R) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (8 * j < count) r[j] = *reinterpret_cast<const uint4*>(R + 8 * j);   // all residual loads in flight first
-    }
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (8 * j >= count) break;
-      uint4 pk;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-      if (R) {
-        const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&r[j]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q] + __bfloat162float(th[q].x),
-                                       f[8 * j + 2 * q + 1] + __bfloat162float(th[q].y));
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * j + 2 * q], f[8 * j + 2 * q + 1]);
-      }
-      if (ss) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 v2 = __bfloat1622float2(h[q]);
-          sq = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, sq));
-        }
-      }
-      *reinterpret_cast<uint4*>(C + 8 * j) = pk;
-    }
+    const float sq = epi_pack_bf16(R, f, count, ss != nullptr,
+                                   [&](int j, const uint4& pk) { *reinterpret_cast<uint4*>(C + 8 * j) = pk; });
     if (ss) *ss = sq;
   }
 }
@@ -232,7 +257,11 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 512 + 1024;  // + barriers / tmem slot / group table + 1024 B alignment slack
+  // epilogue staging for the TMA stores: 8 warps x (32 rows x <= 128 B), 1024-byte aligned
+  static constexpr int STG_OFF = BAR_OFF + 1024;
+  static constexpr int STG_BYTES = 8 * 4096;
+  static constexpr int TOTAL = STG_OFF + STG_BYTES + 1024;  // barriers / tmem slot / group table, staging, alignment slack
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -245,7 +274,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // and tensor-map prefetch are paid once per CTA instead of once per tile (decisive for K = 128 GEMMs).
 template <int BN, bool CONV>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, TcParams p) {
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                    const __grid_constant__ CUtensorMap mapC, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
@@ -269,6 +299,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -400,6 +431,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // ===================== epilogue (warps 2..9) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;          // which interleaved set of 32-column chunks
+    // Each warp owns CPW ADJACENT 32-column chunks of the tile (BN = 128: two, else one).
+    // TMA-store path: the warp stages its 32 rows x (CPW * 64 B, gated: CPW * 32 B) of bf16 output in shared memory
+    // in the swizzle of mapC (Swizzle<log2(row bytes / 16), 4, 3>: conflict-free 16-byte writes) and one lane issues
+    // ONE box store per tile: full 32/64/128-byte row segments instead of 32 scattered 16-byte st.global per
+    // warp instruction.  A single buffer per warp suffices: its previous store is a whole tile old.
+    constexpr int CPW = BN == 128 ? 2 : 1;
+    uint8_t* stg = smem + L::STG_OFF + (warp - 2) * 4096;
+    const int stg_rb = CPW * (p.gated ? 32 : 64);                  // staged bytes per row
+    const int stg_row = lane * stg_rb;
+    const int stg_xor = ((stg_row >> 7) & ((stg_rb >> 4) - 1)) << 4;
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       int m0, row_end, n0, w_row0, g;
@@ -410,6 +451,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool row_ok = r < row_end;
+      // whole 32-row slab inside the tile's row range (always true without groups: TMA clips rows >= M itself;
+      // a group's ragged last slab must not spill into the next group's rows -> direct stores there)
+      const bool warp_tma = p.tma_store && m0 + quad * 32 < row_end && (!p.group_offsets || m0 + quad * 32 + 32 <= row_end);
       const float rs = p.out_scale * ((p.row_scale && row_ok) ? p.row_scale[r] : 1.0f);
       float pre = 1.0f;   // fused RMSNorm: r = rsqrt(mean(x^2) + eps) of this row of A, partials summed in a fixed order
       if (p.norm_ss_in && row_ok) {
@@ -424,12 +468,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
       constexpr int NCHUNK = BN / 32;
       unsigned long long best_key = 0;   // fused greedy selection: best (logit, column) this thread produced
+      const int c_first = n0 + half * CPW * 32;          // first accumulator column of this warp
+      const bool stage_any = warp_tma && half * CPW < NCHUNK && c_first < p.N;   // warp-uniform
+      if (stage_any) {
+        if (lane == 0) tma_store_wait_read<0>();   // the previous tile's box has left the staging buffer
+        __syncwarp();
+      }
 #pragma unroll 1
-      for (int ci = half; ci < NCHUNK + 2; ci += 2) {
-        // (the loop runs one dummy round past the end so that every warp -- also those without a chunk when
-        //  BN = 32 -- reaches the arrive below exactly once)
+      for (int k = 0; k < CPW; ++k) {
+        // (a warp without a chunk - BN = 32, second half - still runs its round to reach the arrive below)
+        const int ci = half * CPW + k;
         const bool has_chunk = ci < NCHUNK;
-        const bool last = ci + 2 >= NCHUNK;     // this warp's last round for this tile
+        const bool last = k == CPW - 1;         // this warp's last round for this tile
         uint32_t v[32];
         __syncwarp();
         if (has_chunk) tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + ci * 32), v);
@@ -472,13 +522,34 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             // residual may alias C (in-place x += ...): each element is read then written by this thread only
             const void* Rb = p.residual ? (const void*)(static_cast<const char*>(p.residual) + (roff - off) * (p.out_f32 ? 4 : 2)) : nullptr;
             if (p.out_f32) epi_store<true>(p.C, Rb, off, f, n_out);
-            else epi_store<false>(p.C, Rb, off, f, n_out, p.ss_out ? p.ss_out + (int64_t)r * p.ss_out_chunks + (c >> 5) : nullptr);
+            else if (!warp_tma)
+              epi_store<false>(p.C, Rb, off, f, n_out, p.ss_out ? p.ss_out + (int64_t)r * p.ss_out_chunks + (c >> 5) : nullptr);
+            else {
+              const __nv_bfloat16* R = Rb ? static_cast<const __nv_bfloat16*>(Rb) + off : nullptr;
+              uint8_t* dst = stg + stg_row;
+              const int u0 = k * (p.gated ? 2 : 4);    // first 16-byte unit of this chunk in the staged row
+              const int sx = stg_xor;
+              const float sq = epi_pack_bf16(R, f, n_out, p.ss_out != nullptr, [&](int q, const uint4& pk) {
+                *reinterpret_cast<uint4*>(dst + ((((u0 + q) << 4)) ^ sx)) = pk;
+              });
+              if (p.ss_out) p.ss_out[(int64_t)r * p.ss_out_chunks + (c >> 5)] = sq;
+            }
           }
         }
-        if (last) break;
+      }
+      if (stage_any) {
+        // generic-proxy smem writes -> visible to the async proxy, then one lane hands the box to the TMA engine
+        // (columns >= N and rows >= M of the box are clipped by the tensor map)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&mapC, stg, p.gated ? (c_first >> 1) : c_first, m0 + quad * 32);
+          tma_store_commit();
+        }
       }
       if (best_key) atomicMax(p.argmax_out + r, best_key);
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();   // smem sources read and writes complete before exit
   }
 
   // ---- teardown: everyone done with TMEM, then the allocating warp frees it ----
@@ -522,6 +593,24 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
   return YMT3_OK;
 }
 
+// bf16 output (rows, cols) with leading dimension ld: store box {row_bytes / 2 columns, 32 rows}, swizzle span = the
+// box row (32 / 64 / 128 bytes)
+int make_out_map(CUtensorMap* map, void* base, int64_t rows, int64_t cols, int64_t ld, int row_bytes) {
+  EncodeTiledFn enc = get_encode_fn();
+  YMT3_REQUIRE(enc, "gemm_bf16_tc: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)(row_bytes / 2), 32};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YMT3_REQUIRE(r == CUDA_SUCCESS, "gemm_bf16_tc: output cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+               (long long)rows, (long long)cols, (long long)ld);
+  return YMT3_OK;
+}
+
 // NHWC activation (B, T, F, C) bf16 contiguous -> 4-D map {C, F, T, B}, box {64, 128, 1, 1}
 int make_conv_map(CUtensorMap* map, const void* base, int64_t B, int64_t T, int64_t F, int64_t C) {
   EncodeTiledFn enc = get_encode_fn();
@@ -543,7 +632,8 @@ struct ConvGeom {
 
 template <int BN, bool CONV>
 int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGeom& cg = ConvGeom()) {
-  CUtensorMap mapA, mapW;
+  CUtensorMap mapA, mapW, mapC;
+  memset(&mapC, 0, sizeof(mapC));
   int rc;
   const int groups = p.group_offsets ? p.num_groups : 1;
   if constexpr (CONV) {
@@ -553,7 +643,18 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   }
   // grouped: weights of all groups are stacked along rows ((groups*N, K), strideW == N*ldw)
   if ((rc = make_map(&mapW, p.W, (int64_t)p.N * groups, p.K, p.ldw, BN))) return rc;
+  // bf16 outputs leave through TMA stores (full-line writes issued by one lane per 32 x 32 chunk instead of 32
+  // scattered 16-byte st.global per warp instruction); YMT3_GEMM_DIRECT_STORE=1 keeps the direct stores (A/B aid)
+  static const bool direct_store = getenv("YMT3_GEMM_DIRECT_STORE") != nullptr;
+  // (gated epilogues keep the direct stores: measured 383 -> 401 us on the MoE expert GEMM with 64-byte box rows,
+  //  its limiter is the epilogue math, not the stores - profiles/r01_ab_gemm_tma_store.txt)
+  static const bool tma_gated = getenv("YMT3_GEMM_TMA_GATED") != nullptr;
+  const int tma_store = out_dtype == YMT3_BF16 && !direct_store && (!p.gated || tma_gated);
+  if (tma_store && (rc = make_out_map(&mapC, p.C, p.M, p.gated ? p.N / 2 : p.N, p.ldc,
+                                      (BN == 128 ? 2 : 1) * (p.gated ? 32 : 64))))
+    return rc;
   TcParams t;
+  t.tma_store = tma_store;
   t.C = p.C; t.ldc = p.ldc; t.bias = p.bias; t.residual = p.residual; t.ldr = p.ldr;
   t.M = p.M; t.N = p.N; t.K = p.K; t.act = p.act; t.gated = p.gated; t.out_scale = p.out_scale;
   t.norm_ss_in = p.norm_ss_in; t.norm_ss_chunks = p.norm_ss_chunks; t.norm_eps = p.norm_eps;
@@ -576,7 +677,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   const int grid = p.group_offsets ? sms : (int)(tiles < sms ? tiles : sms);
   YMT3_REQUIRE(groups <= 32, "gemm_bf16_tc: at most 32 groups");
   YMT3_CUDA_CHECK(ymt3_launch_pdl(gemm_bf16_tc_kernel<BN, CONV>, dim3(grid), dim3(THREADS), SmemLayout<BN>::TOTAL, stream,
-                                  mapA, mapW, t));
+                                  mapA, mapW, mapC, t));
   return YMT3_OK;
 }
 

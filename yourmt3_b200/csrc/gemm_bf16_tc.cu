@@ -167,8 +167,8 @@ __device__ __forceinline__ void epi_math(float (&f)[32], float rs) {
     for (int j = 0; j < 32; ++j) f[j] = act_fast<ACT>(f[j]) * rs;
   }
 }
-__device__ __forceinline__ void epi_dispatch(float (&f)[32], float rs, int act, int gated) {
-  switch (act * 2 + gated) {   // warp-uniform
+__device__ __forceinline__ void epi_dispatch(float (&f)[32], float rs, int act, bool gated) {
+  switch (act * 2 + (gated ? 1 : 0)) {   // warp-uniform
     case YMT3_ACT_NONE * 2 + 0: epi_math<YMT3_ACT_NONE, false>(f, rs); break;
     case YMT3_ACT_NONE * 2 + 1: epi_math<YMT3_ACT_NONE, true>(f, rs); break;
     case YMT3_ACT_GELU_NEW * 2 + 0: epi_math<YMT3_ACT_GELU_NEW, false>(f, rs); break;
@@ -272,7 +272,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // producer runs ahead across tiles through a STAGES-deep smem ring; the accumulator is DOUBLE-BUFFERED in
 // TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1; barriers, TMEM allocation
 // and tensor-map prefetch are paid once per CTA instead of once per tile (decisive for K = 128 GEMMs).
-template <int BN, bool CONV>
+// EPI >= 0: epilogue specialised at compile time for (activation, gated, fp32 output) = (EPI >> 2, (EPI >> 1) & 1,
+// EPI & 1) with the store path fixed (bf16 non-gated: TMA store; gated / fp32: direct) - the executed SASS path shrinks
+// from ~4000 to ~1500 instructions (ncu on the generic kernel: `no_inst` / `branch_resolving` stalls all over the
+// epilogue, 460 warp instructions per 32-column chunk; profiles/r01_gemm_smallk_v4_tma_store_ncu_full.txt).
+// EPI < 0: every combination decided at run time (rare shapes, convolutions, A/B switches).
+template <int BN, bool CONV, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                     const __grid_constant__ CUtensorMap mapC, TcParams p) {
@@ -288,6 +293,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   int* gstart = reinterpret_cast<int*>(tmem_slot + 2);   // [num_groups + 1] tile-index prefix (grouped mode)
 
+  constexpr bool GEN = EPI < 0;
+  const int e_act = GEN ? p.act : (EPI >> 2);
+  const bool e_gated = GEN ? (p.gated != 0) : (((EPI >> 1) & 1) != 0);
+  const bool e_f32 = GEN ? (p.out_f32 != 0) : ((EPI & 1) != 0);
+  const bool e_tma = GEN ? (p.tma_store != 0) : (!e_gated && !e_f32);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -299,7 +309,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
-    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
+    if (e_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -438,7 +448,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // warp instruction.  A single buffer per warp suffices: its previous store is a whole tile old.
     constexpr int CPW = BN == 128 ? 2 : 1;
     uint8_t* stg = smem + L::STG_OFF + (warp - 2) * 4096;
-    const int stg_rb = CPW * (p.gated ? 32 : 64);                  // staged bytes per row
+    const int stg_rb = CPW * (e_gated ? 32 : 64);                  // staged bytes per row
     const int stg_row = lane * stg_rb;
     const int stg_xor = ((stg_row >> 7) & ((stg_rb >> 4) - 1)) << 4;
     int j = 0;
@@ -453,7 +463,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const bool row_ok = r < row_end;
       // whole 32-row slab inside the tile's row range (always true without groups: TMA clips rows >= M itself;
       // a group's ragged last slab must not spill into the next group's rows -> direct stores there)
-      const bool warp_tma = p.tma_store && m0 + quad * 32 < row_end && (!p.group_offsets || m0 + quad * 32 + 32 <= row_end);
+      const bool warp_tma = e_tma && m0 + quad * 32 < row_end && (!p.group_offsets || m0 + quad * 32 + 32 <= row_end);
       const float rs = p.out_scale * ((p.row_scale && row_ok) ? p.row_scale[r] : 1.0f);
       float pre = 1.0f;   // fused RMSNorm: r = rsqrt(mean(x^2) + eps) of this row of A, partials summed in a fixed order
       if (p.norm_ss_in && row_ok) {
@@ -507,7 +517,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                   if (c + q < p.N) f[q] += bias[c + q];
               }
             }
-            epi_dispatch(f, rs, p.act, p.gated);
+            if constexpr (GEN) epi_dispatch(f, rs, e_act, e_gated);
+            else epi_math<(EPI >> 2), ((EPI >> 1) & 1) != 0>(f, rs);
             if (p.argmax_out) {
 #pragma unroll
               for (int q = 0; q < 32; ++q)
@@ -516,18 +527,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                   best_key = key > best_key ? key : best_key;
                 }
             }
-            const int n_out = p.gated ? min(16, (p.N - c) >> 1) : min(32, p.N - c);
-            const int64_t off = (int64_t)r * p.ldc + (p.gated ? (c >> 1) : c);
-            const int64_t roff = (int64_t)r * p.ldr + (p.gated ? (c >> 1) : c);
+            const int n_out = e_gated ? min(16, (p.N - c) >> 1) : min(32, p.N - c);
+            const int64_t off = (int64_t)r * p.ldc + (e_gated ? (c >> 1) : c);
+            const int64_t roff = (int64_t)r * p.ldr + (e_gated ? (c >> 1) : c);
             // residual may alias C (in-place x += ...): each element is read then written by this thread only
-            const void* Rb = p.residual ? (const void*)(static_cast<const char*>(p.residual) + (roff - off) * (p.out_f32 ? 4 : 2)) : nullptr;
-            if (p.out_f32) epi_store<true>(p.C, Rb, off, f, n_out);
+            const void* Rb = p.residual ? (const void*)(static_cast<const char*>(p.residual) + (roff - off) * (e_f32 ? 4 : 2)) : nullptr;
+            if (e_f32) epi_store<true>(p.C, Rb, off, f, n_out);
             else if (!warp_tma)
               epi_store<false>(p.C, Rb, off, f, n_out, p.ss_out ? p.ss_out + (int64_t)r * p.ss_out_chunks + (c >> 5) : nullptr);
             else {
               const __nv_bfloat16* R = Rb ? static_cast<const __nv_bfloat16*>(Rb) + off : nullptr;
               uint8_t* dst = stg + stg_row;
-              const int u0 = k * (p.gated ? 2 : 4);    // first 16-byte unit of this chunk in the staged row
+              const int u0 = k * (e_gated ? 2 : 4);    // first 16-byte unit of this chunk in the staged row
               const int sx = stg_xor;
               const float sq = epi_pack_bf16(R, f, n_out, p.ss_out != nullptr, [&](int q, const uint4& pk) {
                 *reinterpret_cast<uint4*>(dst + ((((u0 + q) << 4)) ^ sx)) = pk;
@@ -543,13 +554,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&mapC, stg, p.gated ? (c_first >> 1) : c_first, m0 + quad * 32);
+          tma_store_2d(&mapC, stg, e_gated ? (c_first >> 1) : c_first, m0 + quad * 32);
           tma_store_commit();
         }
       }
       if (best_key) atomicMax(p.argmax_out + r, best_key);
     }
-    if (p.tma_store && lane == 0) tma_store_wait_all();   // smem sources read and writes complete before exit
+    if (e_tma && lane == 0) tma_store_wait_all();   // smem sources read and writes complete before exit
   }
 
   // ---- teardown: everyone done with TMEM, then the allocating warp frees it ----
@@ -630,7 +641,12 @@ struct ConvGeom {
   int B = 0, T = 0, F = 0, Cin = 0;
 };
 
-template <int BN, bool CONV>
+// epilogue combinations with a specialised kernel (non-convolution): plain bf16 / plain fp32 (LM head) / gated GELU
+// (decoder FFN) / gated SiLU (MoE experts); code = act * 4 + gated * 2 + out_f32
+constexpr int EPI_PLAIN_BF16 = 0, EPI_PLAIN_F32 = 1, EPI_GATED_GELU_NEW = YMT3_ACT_GELU_NEW * 4 + 2,
+              EPI_GATED_SILU = YMT3_ACT_SILU * 4 + 2;
+
+template <int BN, bool CONV, int EPI>
 int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGeom& cg = ConvGeom()) {
   CUtensorMap mapA, mapW, mapC;
   memset(&mapC, 0, sizeof(mapC));
@@ -645,7 +661,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   if ((rc = make_map(&mapW, p.W, (int64_t)p.N * groups, p.K, p.ldw, BN))) return rc;
   // bf16 outputs leave through TMA stores (full-line writes issued by one lane per 32 x 32 chunk instead of 32
   // scattered 16-byte st.global per warp instruction); YMT3_GEMM_DIRECT_STORE=1 keeps the direct stores (A/B aid)
-  static const bool direct_store = getenv("YMT3_GEMM_DIRECT_STORE") != nullptr;
+  static const bool direct_store = getenv("YMT3_GEMM_DIRECT_STORE") != nullptr;   // (forces the generic kernel)
   // (gated epilogues keep the direct stores: measured 383 -> 401 us on the MoE expert GEMM with 64-byte box rows,
   //  its limiter is the epilogue math, not the stores - profiles/r01_ab_gemm_tma_store.txt)
   static const bool tma_gated = getenv("YMT3_GEMM_TMA_GATED") != nullptr;
@@ -666,7 +682,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   int dev = 0;
   YMT3_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, CONV, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SmemLayout<BN>::TOTAL));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -676,7 +692,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   const int sms = ymt3_num_sms();
   const int grid = p.group_offsets ? sms : (int)(tiles < sms ? tiles : sms);
   YMT3_REQUIRE(groups <= 32, "gemm_bf16_tc: at most 32 groups");
-  YMT3_CUDA_CHECK(ymt3_launch_pdl(gemm_bf16_tc_kernel<BN, CONV>, dim3(grid), dim3(THREADS), SmemLayout<BN>::TOTAL, stream,
+  YMT3_CUDA_CHECK(ymt3_launch_pdl(gemm_bf16_tc_kernel<BN, CONV, EPI>, dim3(grid), dim3(THREADS), SmemLayout<BN>::TOTAL, stream,
                                   mapA, mapW, mapC, t));
   return YMT3_OK;
 }
@@ -706,9 +722,25 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   const int64_t mt = ymt3_div_up(p.M, BM);
   const int sms = ymt3_num_sms();
   // largest BN whose tile count still fills the SMs; otherwise maximise parallelism
-  if (p.N >= 128 && mt * ymt3_div_up(p.N, 128) >= sms) return launch<128, false>(p, out_dtype, stream);
-  if (p.N >= 64 && mt * ymt3_div_up(p.N, 64) >= sms) return launch<64, false>(p, out_dtype, stream);
-  return launch<32, false>(p, out_dtype, stream);
+  const int bn = (p.N >= 128 && mt * ymt3_div_up(p.N, 128) >= sms) ? 128
+                 : (p.N >= 64 && mt * ymt3_div_up(p.N, 64) >= sms) ? 64 : 32;
+  static const bool generic_only = getenv("YMT3_GEMM_DIRECT_STORE") || getenv("YMT3_GEMM_TMA_GATED") ||
+                                   getenv("YMT3_GEMM_GENERIC");   // A/B switches act on the run-time kernel
+  const int code = generic_only ? -1 : p.act * 4 + (p.gated ? 2 : 0) + (out_dtype == YMT3_F32 ? 1 : 0);
+#define YMT3_TC_LAUNCH(EPI)                                                        \
+  switch (bn) {                                                                    \
+    case 128: return launch<128, false, EPI>(p, out_dtype, stream);                \
+    case 64: return launch<64, false, EPI>(p, out_dtype, stream);                  \
+    default: return launch<32, false, EPI>(p, out_dtype, stream);                  \
+  }
+  switch (code) {
+    case EPI_PLAIN_BF16: YMT3_TC_LAUNCH(EPI_PLAIN_BF16)
+    case EPI_PLAIN_F32: YMT3_TC_LAUNCH(EPI_PLAIN_F32)
+    case EPI_GATED_GELU_NEW: YMT3_TC_LAUNCH(EPI_GATED_GELU_NEW)
+    case EPI_GATED_SILU: YMT3_TC_LAUNCH(EPI_GATED_SILU)
+    default: YMT3_TC_LAUNCH(-1)
+  }
+#undef YMT3_TC_LAUNCH
 }
 
 // 3x3 / stride 1 / zero-pad 1 convolution as an implicit GEMM on the tensor cores.
@@ -727,9 +759,9 @@ int conv3x3_bf16_tc(const void* x, int B, int T, int F, int Cin, const GemmParam
   YMT3_REQUIRE(p.N % 8 == 0 && p.ldc % 8 == 0 && (!p.residual || p.ldr % 8 == 0), "conv3x3_bf16_tc: Cout/ldc alignment");
   ConvGeom cg;
   cg.B = B; cg.T = T; cg.F = F; cg.Cin = Cin;
-  if (p.N % 128 == 0) return launch<128, true>(p, out_dtype, stream, cg);
-  if (p.N % 64 == 0) return launch<64, true>(p, out_dtype, stream, cg);
-  return launch<32, true>(p, out_dtype, stream, cg);
+  if (p.N % 128 == 0) return launch<128, true, -1>(p, out_dtype, stream, cg);
+  if (p.N % 64 == 0) return launch<64, true, -1>(p, out_dtype, stream, cg);
+  return launch<32, true, -1>(p, out_dtype, stream, cg);
 }
 
 }  // namespace ymt3

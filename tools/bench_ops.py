@@ -97,7 +97,7 @@ if what in ("decode_attn", "all"):
     Vc = torch.randn(N, H, Lcap, 64, device=dev).bfloat16()
     st = torch.zeros(1, dtype=torch.int32, device=dev)
     s_ = torch.cuda.current_stream().cuda_stream
-    for L in ([128] if once else [16, 64, 128, 192, 256]):
+    for L in ([128] if once else [1, 4, 16, 32, 64, 128, 192, 256]):
         st.fill_(L - 1)
         us = timeit(lambda: _lib.check(lib.ymt3_op_decode_attention(1, q.data_ptr(), kn.data_ptr(), vn.data_ptr(), Kc.data_ptr(),
                                                                     Vc.data_ptr(), st.data_ptr(), 0, o.data_ptr(), N, H, Lcap, s_)))

@@ -115,11 +115,11 @@ template <> struct Slice8<__nv_bfloat16> {
 // walk over up to 1024 keys is latency-bound): the W warps of a pair take the 16-key blocks round-robin and their
 // states are merged through shared memory by warp 0 of the pair (split-length / flash-decoding).
 template <typename T, int W>
-__global__ void __launch_bounds__(W > 4 ? 32 * W : 128, W > 4 ? 3 : 6)
+__global__ void __launch_bounds__(W > 4 ? 32 * W : 128, sizeof(T) == 2 ? (W > 4 ? 3 : 6) : (W > 4 ? 2 : 4))
 decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ knew, const T* __restrict__ vnew,
                    int64_t new_ld, T* __restrict__ Kc, T* __restrict__ Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss,
-                   const int* __restrict__ step, int fixed_len, float scale, T* __restrict__ out, int64_t out_ld, int H,
-                   int64_t total) {
+                   const int* __restrict__ step, int fixed_len, int cap, float scale, T* __restrict__ out,
+                   int64_t out_ld, int H, int64_t total) {
   constexpr int DK = 64, NG = 4, U = 4;
   pdl_launch_dependents();
   pdl_wait();
@@ -136,20 +136,37 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
   T* Kb = Kc + n * c_sn + (int64_t)h * c_sh;
   T* Vb = Vc + n * c_sn + (int64_t)h * c_sh;
   // Every independent load is issued before the first one is consumed (the warp issues in order, so a consumed load
-  // stalls everything behind it): step, q and - self mode - the new K/V row.  The new row is attended straight from
-  // knew/vnew (key index s_new) and appended to the cache on the side, so there is no store -> load round trip.
+  // stalls everything behind it): step, q, - self mode - the new K/V row AND the warp's first 16-key block of the
+  // cache, which is fetched SPECULATIVELY (rows < cap, the length bound known at launch) before *step has arrived:
+  // the short-cache steps, whose cost is two dependent round trips per wave of warps, lose one of them.  The new row
+  // is attended straight from registers (key index s_new) and appended to the cache on the side, so there is no
+  // store -> load round trip; whatever the speculative fetch read at or beyond s_new is masked / replaced.
   const typename Slice8<T>::Raw qraw = Slice8<T>::load_raw(q + n * q_ld + h * DK + 8 * sub);
-  int len = fixed_len, s_new = -1;
-  const T* kn = nullptr;
-  const T* vn = nullptr;
+  int s_raw = 0;
+  typename Slice8<T>::Raw knraw, vnraw;
   if (knew) {
-    kn = knew + n * new_ld + h * DK + 8 * sub;
-    vn = vnew + n * new_ld + h * DK + 8 * sub;
-    s_new = *step;
+    s_raw = *step;
+    knraw = Slice8<T>::load_raw(knew + n * new_ld + h * DK + 8 * sub);
+    vnraw = Slice8<T>::load_raw(vnew + n * new_ld + h * DK + 8 * sub);
+  }
+  constexpr int BLK = NG * U;
+  const int base0 = wsub * BLK;
+  typename Slice8<T>::Raw kk[U], vv[U];   // kept packed until use (register pressure -> occupancy)
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = base0 + u * NG + grp;
+    if (j < cap) {
+      kk[u] = Slice8<T>::load_raw(Kb + (int64_t)j * c_ss + 8 * sub);
+      vv[u] = Slice8<T>::load_raw(Vb + (int64_t)j * c_ss + 8 * sub);
+    }
+  }
+  int len = fixed_len, s_new = -1;
+  if (knew) {
+    s_new = s_raw;
     len = s_new + 1;
     if (wsub == 0 && valid) {
-      if (lane < 8) Slice8<T>::copy(Kb + (int64_t)s_new * c_ss + 8 * sub, kn);
-      else if (lane < 16) Slice8<T>::copy(Vb + (int64_t)s_new * c_ss + 8 * sub, vn);
+      if (lane < 8) *reinterpret_cast<typename Slice8<T>::Raw*>(Kb + (int64_t)s_new * c_ss + 8 * sub) = knraw;
+      else if (lane < 16) *reinterpret_cast<typename Slice8<T>::Raw*>(Vb + (int64_t)s_new * c_ss + 8 * sub) = vnraw;
     }
   }
   if (!valid) len = 0;
@@ -161,8 +178,8 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
 
   // uniform trip count for the whole warp (the shuffles below name all 32 lanes)
   bool first = true;
-  for (int base = wsub * NG * U; base < len; base += W * NG * U) {
-    typename Slice8<T>::Raw kk[U], vv[U];   // kept packed until use (register pressure -> occupancy)
+  bool preloaded = cap > 0;   // first block already in registers (cap == 0: A/B switch, no speculation)
+  for (int base = base0; base < len; base += W * BLK) {
     float sc[U];
     bool has[U];
 #pragma unroll
@@ -170,11 +187,16 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
       const int j = base + u * NG + grp;
       has[u] = j < len;
       if (has[u]) {
-        const bool fresh = j == s_new;
-        kk[u] = Slice8<T>::load_raw(fresh ? kn : Kb + (int64_t)j * c_ss + 8 * sub);
-        vv[u] = Slice8<T>::load_raw(fresh ? vn : Vb + (int64_t)j * c_ss + 8 * sub);
+        if (j == s_new) {
+          kk[u] = knraw;
+          vv[u] = vnraw;
+        } else if (!preloaded) {
+          kk[u] = Slice8<T>::load_raw(Kb + (int64_t)j * c_ss + 8 * sub);
+          vv[u] = Slice8<T>::load_raw(Vb + (int64_t)j * c_ss + 8 * sub);
+        }
       }
     }
+    preloaded = false;
     if (first) {   // first consumption of q: after the first K/V loads are in flight
       first = false;
       Slice8<T>::unpack(qraw, qv);
@@ -292,13 +314,15 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
   }
   const int64_t want = (int64_t)ymt3_num_sms() * 16;
   const int max_len = knew ? Lmax : fixed_len;
+  static const bool no_spec = getenv("YMT3_DECODE_ATTN_NO_SPEC") != nullptr;   // A/B aid: no speculative first block
+  const int cap = no_spec ? 0 : max_len;
   int w = 1;
   while (w < 8 && total * w < want && 16 * (2 * w) <= max_len) w *= 2;
   if (forced_w == 1 || forced_w == 2 || forced_w == 4 || forced_w == 8) w = forced_w;
 #define YMT3_LAUNCH_DECODE_ATTN(TT, WW)                                                                                \
   YMT3_CUDA_CHECK(ymt3_launch_pdl(decode_attn_kernel<TT, WW>, dim3((unsigned)ymt3_div_up(total, (WW > 4 ? WW : 4) / WW)), \
                                   dim3(32 * (WW > 4 ? WW : 4)), 0, stream, (const TT*)q, q_ld, (const TT*)knew,         \
-                                  (const TT*)vnew, new_ld, (TT*)Kc, (TT*)Vc, c_sn, c_sh, c_ss, step, fixed_len, scale,    \
+                                  (const TT*)vnew, new_ld, (TT*)Kc, (TT*)Vc, c_sn, c_sh, c_ss, step, fixed_len, cap, scale,     \
                                   (TT*)out, out_ld, H, total))
 #define YMT3_DISPATCH_DECODE_ATTN(TT)                                                                                  \
   switch (w) {                                                                                                         \

@@ -141,6 +141,8 @@ def _bf(x):
 @pytest.mark.parametrize("M,N,K", [
     (128, 128, 64), (128, 32, 64), (1, 64, 128), (200, 1152, 512), (832, 512, 384), (5000, 2048, 512),
     (40000, 512, 1024), (333, 600, 512), (16384, 128, 256), (77, 96, 72), (300, 1536, 128),
+    (20000, 600, 512),        # 128 x 256 tiles with a ragged last N tile (88 valid columns, TMA-store box clipped)
+    (6656, 1152, 512),        # the decode-step qkv shape at the default batch (256-wide tiles, 4.5 N tiles)
 ])
 def test_linear_bf16_tcgen05_shapes(cuda_device, native_lib, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
@@ -165,6 +167,18 @@ def test_linear_bf16_epilogues(cuda_device, native_lib, act, gated, out_f32):
     ref = (R if out_f32 else _bf(R)) + 0.5 * ref
     got = linear_bf16_native(native_lib, cuda_device, A, W, bias, act, gated, R, 0.5, out_f32)
     _close(got, ref, 3e-5 if out_f32 else 6e-3)
+
+
+@pytest.mark.parametrize("act", [1, 3])
+def test_linear_bf16_gated_wide_tiles(cuda_device, native_lib, act):
+    """gated epilogues on the 128 x 256 tile path (large M, N = 1024): the MoE expert / decoder FFN shapes."""
+    g = torch.Generator().manual_seed(act)
+    M, N, K = 20000, 1024, 128
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.1
+    z = _bf(A) @ _bf(W).T
+    ref = ACTS[act](z[:, 0::2]) * z[:, 1::2]
+    got = linear_bf16_native(native_lib, cuda_device, A, W, None, act, 1, None, 1.0, False)
+    _close(got, ref, 6e-3)
 
 
 def test_norm_attention_bf16_io(cuda_device, native_lib):

@@ -16,9 +16,10 @@ PRESETS = {
     "t5_small": ("mt3_t5_small", {}, 512, "bf16"),   # 626x at 256, 834x at 512 (profiles/r01_ab_decode_attn_split_length.txt)
     "t5_small_f32": ("mt3_t5_small", {}, 64, "f32"),
     "yptf": ("yptf", {"codec": "spec", "hop_length": 300}, 64, "bf16"),
-    # batch: 887x realtime per GPU at 256, 957x at 512, 998x at 1024 (fixed per-kernel latencies of the decode step
-    # amortise; the KV-cache-bound self-attention does not) -- 512 keeps one step near 1 s
-    "yptf_moe_multi": ("yptf_moe_multi", {"codec": "spec", "hop_length": 300}, 512, "bf16"),
+    # batch: 728 segments x 13 channels = 9464 rows = 74 M-tiles of 128, so the tile counts of the decode-step GEMMs
+    # are (near-)multiples of the 148 SMs; measured 1024x at 364, 1041x at 512, 1072x at 728, 1062x at 768, 1080x at
+    # 1024 per GPU (profiles/r01_sweep_batch.txt) -- 728 keeps one step under 1.5 s
+    "yptf_moe_multi": ("yptf_moe_multi", {"codec": "spec", "hop_length": 300}, 728, "bf16"),
 }
 DEFAULT = "yptf_moe_multi"   # the model BASELINE.json quotes the target on
 

@@ -255,11 +255,14 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  // epilogue staging for the TMA stores: 8 warps x STG_BOXES boxes of (32 rows x <= 128 B), 1024-byte aligned
+  static constexpr int STG_BOXES = BN == 256 ? 2 : 1;
+  static constexpr int STG_WARP_BYTES = STG_BOXES * 4096;
+  static constexpr int STG_BYTES = 8 * STG_WARP_BYTES;
+  static constexpr int RING_BUDGET = 226 * 1024 - 2048 - STG_BYTES;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  // epilogue staging for the TMA stores: 8 warps x (32 rows x <= 128 B), 1024-byte aligned
   static constexpr int STG_OFF = BAR_OFF + 1024;
-  static constexpr int STG_BYTES = 8 * 4096;
   static constexpr int TOTAL = STG_OFF + STG_BYTES + 1024;  // barriers / tmem slot / group table, staging, alignment slack
   static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
@@ -441,14 +444,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // ===================== epilogue (warps 2..9) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;          // which interleaved set of 32-column chunks
-    // Each warp owns CPW ADJACENT 32-column chunks of the tile (BN = 128: two, else one).
+    // Each warp owns CPW ADJACENT 32-column chunks of the tile (BN = 256: four, 128: two, else one).
     // TMA-store path: the warp stages its 32 rows x (CPW * 64 B, gated: CPW * 32 B) of bf16 output in shared memory
     // in the swizzle of mapC (Swizzle<log2(row bytes / 16), 4, 3>: conflict-free 16-byte writes) and one lane issues
-    // ONE box store per tile: full 32/64/128-byte row segments instead of 32 scattered 16-byte st.global per
-    // warp instruction.  A single buffer per warp suffices: its previous store is a whole tile old.
-    constexpr int CPW = BN == 128 ? 2 : 1;
-    uint8_t* stg = smem + L::STG_OFF + (warp - 2) * 4096;
-    const int stg_rb = CPW * (e_gated ? 32 : 64);                  // staged bytes per row
+    // one box store (two for BN = 256: a box row is at most the 128-byte swizzle span) per tile: full 32/64/128-byte
+    // row segments instead of 32 scattered 16-byte st.global per warp instruction.  A single buffer per warp
+    // suffices: its previous store is a whole tile old.
+    constexpr int CPW = BN >= 64 ? BN / 64 : 1;
+    uint8_t* stg = smem + L::STG_OFF + (warp - 2) * L::STG_WARP_BYTES;
+    const int stg_rb_all = CPW * (e_gated ? 32 : 64);              // staged bytes per row, all boxes
+    const int stg_rb = stg_rb_all > 128 ? 128 : stg_rb_all;        // bytes per row of one box
     const int stg_row = lane * stg_rb;
     const int stg_xor = ((stg_row >> 7) & ((stg_rb >> 4) - 1)) << 4;
     int j = 0;
@@ -537,8 +542,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               epi_store<false>(p.C, Rb, off, f, n_out, p.ss_out ? p.ss_out + (int64_t)r * p.ss_out_chunks + (c >> 5) : nullptr);
             else {
               const __nv_bfloat16* R = Rb ? static_cast<const __nv_bfloat16*>(Rb) + off : nullptr;
-              uint8_t* dst = stg + stg_row;
-              const int u0 = k * (e_gated ? 2 : 4);    // first 16-byte unit of this chunk in the staged row
+              const int b0 = k * (e_gated ? 32 : 64);  // byte offset of this chunk in the staged row (all boxes)
+              uint8_t* dst = stg + (b0 / stg_rb) * 4096 + stg_row;   // box, then this lane's row in it
+              const int u0 = (b0 % stg_rb) >> 4;                     // first 16-byte unit inside the box row
               const int sx = stg_xor;
               const float sq = epi_pack_bf16(R, f, n_out, p.ss_out != nullptr, [&](int q, const uint4& pk) {
                 *reinterpret_cast<uint4*>(dst + ((((u0 + q) << 4)) ^ sx)) = pk;
@@ -554,7 +560,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&mapC, stg, e_gated ? (c_first >> 1) : c_first, m0 + quad * 32);
+          const int co = e_gated ? (c_first >> 1) : c_first;       // first output column of this warp
+          const int n_out_cols = e_gated ? (p.N >> 1) : p.N;
+          for (int b = 0; b * stg_rb < stg_rb_all; ++b)
+            if (co + b * (stg_rb >> 1) < n_out_cols) tma_store_2d(&mapC, stg + b * 4096, co + b * (stg_rb >> 1), m0 + quad * 32);
           tma_store_commit();
         }
       }
@@ -666,8 +675,9 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   //  its limiter is the epilogue math, not the stores - profiles/r01_ab_gemm_tma_store.txt)
   static const bool tma_gated = getenv("YMT3_GEMM_TMA_GATED") != nullptr;
   const int tma_store = out_dtype == YMT3_BF16 && !direct_store && (!p.gated || tma_gated);
+  const int out_row_bytes = (BN >= 64 ? BN / 64 : 1) * (p.gated ? 32 : 64);
   if (tma_store && (rc = make_out_map(&mapC, p.C, p.M, p.gated ? p.N / 2 : p.N, p.ldc,
-                                      (BN == 128 ? 2 : 1) * (p.gated ? 32 : 64))))
+                                      out_row_bytes > 128 ? 128 : out_row_bytes)))
     return rc;
   TcParams t;
   t.tma_store = tma_store;
@@ -722,13 +732,31 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   const int64_t mt = ymt3_div_up(p.M, BM);
   const int sms = ymt3_num_sms();
   // largest BN whose tile count still fills the SMs; otherwise maximise parallelism
-  const int bn = (p.N >= 128 && mt * ymt3_div_up(p.N, 128) >= sms) ? 128
-                 : (p.N >= 64 && mt * ymt3_div_up(p.N, 64) >= sms) ? 64 : 32;
+  // Tile width: the mainloop of these GEMMs is bound by the L2 -> shared-memory fill (a 128 x BN tile moves
+  // (128 + BN) * K * 2 bytes for 128 * BN outputs), and every SM works through ceil(tiles / SMs) tiles, so pick the BN
+  // in {256, 128, 64, 32} that minimises rounds * (128 + BN) (ties: the wider tile).  With fewer tiles than SMs that is
+  // one round of the narrowest tile = parallelism first; at M = 6656 (52 M-tiles) it picks 256 for every GEMM of the
+  // decode step (e.g. N = 512: 104 tiles in ONE round instead of 208 tiles of 128 in two).  YMT3_GEMM_MAX_BN (A/B aid)
+  // caps BN.
+  static const int max_bn = getenv("YMT3_GEMM_MAX_BN") ? atoi(getenv("YMT3_GEMM_MAX_BN")) : 256;
+  int bn = 32;
+  {
+    int64_t best = -1;
+    const int cand[4] = {256, 128, 64, 32};
+    for (int i = 0; i < 4; ++i) {
+      const int b = cand[i];
+      if (b > max_bn || (b > 32 && p.N < b)) continue;
+      const int64_t tiles = mt * ymt3_div_up(p.N, b);
+      const int64_t cost = ymt3_div_up(tiles, sms) * (int64_t)(128 + b);
+      if (best < 0 || cost < best) { best = cost; bn = b; }
+    }
+  }
   static const bool generic_only = getenv("YMT3_GEMM_DIRECT_STORE") || getenv("YMT3_GEMM_TMA_GATED") ||
                                    getenv("YMT3_GEMM_GENERIC");   // A/B switches act on the run-time kernel
   const int code = generic_only ? -1 : p.act * 4 + (p.gated ? 2 : 0) + (out_dtype == YMT3_F32 ? 1 : 0);
 #define YMT3_TC_LAUNCH(EPI)                                                        \
   switch (bn) {                                                                    \
+    case 256: return launch<256, false, EPI>(p, out_dtype, stream);                \
     case 128: return launch<128, false, EPI>(p, out_dtype, stream);                \
     case 64: return launch<64, false, EPI>(p, out_dtype, stream);                  \
     default: return launch<32, false, EPI>(p, out_dtype, stream);                  \

@@ -4,6 +4,7 @@
 // a device-side finished mask, and the device step counter.
 #include "ops.cuh"
 #include "decode.cuh"
+#include <type_traits>
 
 namespace ymt3 {
 
@@ -138,9 +139,11 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
   // Every independent load is issued before the first one is consumed (the warp issues in order, so a consumed load
   // stalls everything behind it): step, q, - self mode - the new K/V row AND the warp's first 16-key block of the
   // cache, which is fetched SPECULATIVELY (rows < cap, the length bound known at launch) before *step has arrived:
-  // the short-cache steps, whose cost is two dependent round trips per wave of warps, lose one of them.  The new row
-  // is attended straight from registers (key index s_new) and appended to the cache on the side, so there is no
-  // store -> load round trip; whatever the speculative fetch read at or beyond s_new is masked / replaced.
+  // the short-cache steps, whose cost is two dependent round trips per wave of warps, lose one of them.
+  // Keys [0, lim) come from the cache (self mode: lim = *step, the rows written by earlier steps); the new row is
+  // attended straight from registers at the end and appended to the cache on the side, so there is no store -> load
+  // round trip and the key loop carries no "fresh row" test.  Cache rows are dense (row stride = DK, checked by the
+  // launcher): the 8 loads of a block use immediate offsets from two running pointers.
   const typename Slice8<T>::Raw qraw = Slice8<T>::load_raw(q + n * q_ld + h * DK + 8 * sub);
   int s_raw = 0;
   typename Slice8<T>::Raw knraw, vnraw;
@@ -151,94 +154,117 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
   }
   constexpr int BLK = NG * U;
   const int base0 = wsub * BLK;
+  const T* kp = Kb + (int64_t)(base0 + grp) * DK + 8 * sub;   // this lane's slice of its first row
+  const T* vp = Vb + (int64_t)(base0 + grp) * DK + 8 * sub;
   typename Slice8<T>::Raw kk[U], vv[U];   // kept packed until use (register pressure -> occupancy)
+  bool preloaded = cap > 0;               // first block already in registers (cap == 0: A/B switch, no speculation)
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int j = base0 + u * NG + grp;
-    if (j < cap) {
-      kk[u] = Slice8<T>::load_raw(Kb + (int64_t)j * c_ss + 8 * sub);
-      vv[u] = Slice8<T>::load_raw(Vb + (int64_t)j * c_ss + 8 * sub);
+    if (base0 + u * NG + grp < cap) {
+      kk[u] = Slice8<T>::load_raw(kp + u * NG * DK);
+      vv[u] = Slice8<T>::load_raw(vp + u * NG * DK);
     }
   }
-  int len = fixed_len, s_new = -1;
+  int lim = fixed_len;                    // keys [0, lim) are read from the cache
   if (knew) {
-    s_new = s_raw;
-    len = s_new + 1;
+    lim = s_raw;
     if (wsub == 0 && valid) {
-      if (lane < 8) *reinterpret_cast<typename Slice8<T>::Raw*>(Kb + (int64_t)s_new * c_ss + 8 * sub) = knraw;
-      else if (lane < 16) *reinterpret_cast<typename Slice8<T>::Raw*>(Vb + (int64_t)s_new * c_ss + 8 * sub) = vnraw;
+      if (lane < 8) *reinterpret_cast<typename Slice8<T>::Raw*>(Kb + (int64_t)lim * DK + 8 * sub) = knraw;
+      else if (lane < 16) *reinterpret_cast<typename Slice8<T>::Raw*>(Vb + (int64_t)lim * DK + 8 * sub) = vnraw;
     }
   }
-  if (!valid) len = 0;
+  if (!valid) lim = 0;
   float qv[8];
+  Slice8<T>::unpack(qraw, qv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qv[i] *= scale;
 
   float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
 
-  // uniform trip count for the whole warp (the shuffles below name all 32 lanes)
-  bool first = true;
-  bool preloaded = cap > 0;   // first block already in registers (cap == 0: A/B switch, no speculation)
-  for (int base = base0; base < len; base += W * BLK) {
+  // one 16-key block: scores of this group's 4 keys (8 lanes each, 3 xor-shuffles), online-softmax update.
+  // MASKED = false: all 16 keys valid, straight-line code; true: the ragged last block
+  auto block = [&](auto masked_tag, int base) {
+    constexpr bool MASKED = decltype(masked_tag)::value;
     float sc[U];
-    bool has[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = base + u * NG + grp;
-      has[u] = j < len;
-      if (has[u]) {
-        if (j == s_new) {
-          kk[u] = knraw;
-          vv[u] = vnraw;
-        } else if (!preloaded) {
-          kk[u] = Slice8<T>::load_raw(Kb + (int64_t)j * c_ss + 8 * sub);
-          vv[u] = Slice8<T>::load_raw(Vb + (int64_t)j * c_ss + 8 * sub);
-        }
-      }
-    }
-    preloaded = false;
-    if (first) {   // first consumption of q: after the first K/V loads are in flight
-      first = false;
-      Slice8<T>::unpack(qraw, qv);
+      float kf[8], sacc = 0.f;
+      Slice8<T>::unpack(kk[u], kf);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) qv[i] *= scale;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float sacc = 0.f;
-      if (has[u]) {
-        float kf[8];
-        Slice8<T>::unpack(kk[u], kf);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sacc = fmaf(qv[i], kf[i], sacc);
-      }
+      for (int i = 0; i < 8; ++i) sacc = fmaf(qv[i], kf[i], sacc);
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
-      sc[u] = has[u] ? sacc : -INFINITY;
+      sc[u] = (MASKED && base + u * NG + grp >= lim) ? -INFINITY : sacc;
     }
-    float mn = m;
+    const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
+    if (MASKED && mn == -INFINITY) return;   // this group has no valid key yet
+    const float corr = expf(m - mn);         // m = -inf -> 0
+    l *= corr;
 #pragma unroll
-    for (int u = 0; u < U; ++u) mn = fmaxf(mn, sc[u]);
-    if (mn > -INFINITY) {
-      const float corr = expf(m - mn);   // m = -inf -> 0
-      l *= corr;
+    for (int i = 0; i < 8; ++i) o[i] *= corr;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] *= corr;
+    for (int u = 0; u < U; ++u) {
+      const float pu = expf(sc[u] - mn);     // masked key: exp(-inf) = 0, its (possibly garbage) V must not be used
+      if (MASKED && sc[u] == -INFINITY) continue;
+      l += pu;
+      float vf[8];
+      Slice8<T>::unpack(vv[u], vf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(pu, vf[i], o[i]);
+    }
+    m = mn;
+  };
+
+  // uniform trip count for the whole warp (the shuffles name all 32 lanes)
+  int base = base0;
+  for (; base + BLK <= lim; base += W * BLK) {
+    if (!preloaded) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (has[u]) {
-          const float pu = expf(sc[u] - mn);
-          l += pu;
-          float vf[8];
-          Slice8<T>::unpack(vv[u], vf);
+        kk[u] = Slice8<T>::load_raw(kp + u * NG * DK);
+        vv[u] = Slice8<T>::load_raw(vp + u * NG * DK);
+      }
+    }
+    preloaded = false;
+    kp += W * BLK * DK;
+    vp += W * BLK * DK;
+    block(std::false_type(), base);
+  }
+  if (base < lim) {   // ragged last block of this warp
+    if (!preloaded) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = fmaf(pu, vf[i], o[i]);
+      for (int u = 0; u < U; ++u) {
+        if (base + u * NG + grp < lim) {
+          kk[u] = Slice8<T>::load_raw(kp + u * NG * DK);
+          vv[u] = Slice8<T>::load_raw(vp + u * NG * DK);
         }
       }
-      m = mn;
     }
+    block(std::true_type(), base);
   }
+  if (knew && wsub == 0 && valid && grp == 0) {
+    // the new key / value row, from registers: one more online-softmax step in group 0 (the merge below
+    // treats the other groups' untouched states as empty)
+    float kf[8], sacc = 0.f;
+    Slice8<T>::unpack(knraw, kf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sacc = fmaf(qv[i], kf[i], sacc);
+    sacc += __shfl_xor_sync(0x000000ffu, sacc, 1);
+    sacc += __shfl_xor_sync(0x000000ffu, sacc, 2);
+    sacc += __shfl_xor_sync(0x000000ffu, sacc, 4);
+    const float mn = fmaxf(m, sacc);
+    const float corr = expf(m - mn), pu = expf(sacc - mn);
+    l = l * corr + pu;
+    float vf[8];
+    Slice8<T>::unpack(vnraw, vf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(pu, vf[i], o[i] * corr);
+    m = mn;
+  }
+  __syncwarp();
   // merge the 4 group states (lanes with equal `sub`): xor 8, then xor 16
 #pragma unroll
   for (int off = 8; off <= 16; off <<= 1) {
@@ -302,6 +328,7 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
                      float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream) {
   if (N <= 0) return YMT3_OK;
   YMT3_REQUIRE(dk == 64, "decode_attention: head dim must be 64 (got %d)", dk);
+  YMT3_REQUIRE(c_ss == 64, "decode_attention: cache rows must be dense (row stride %lld != 64)", (long long)c_ss);
   YMT3_REQUIRE((q_ld % 8 | new_ld % 8 | c_sn % 8 | c_sh % 8 | c_ss % 8 | out_ld % 8) == 0,
                "decode_attention: strides must be multiples of 8 elements");
   const int64_t total = (int64_t)N * H;

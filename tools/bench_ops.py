@@ -88,6 +88,19 @@ if what in ("decode", "all"):
         byts = z.numel() * 2 + 2 * q.numel() * 2
         print(f"cross_attn_absorbed N={N} H={H} T={T}: {us:8.1f} us  {byts / us / 1e3:8.1f} GB/s (z + q + out bytes)", flush=True)
 
+if what == "xattn":
+    # absorbed cross-attention alone at the B = 256 / 728 shapes of YPTF.MoE+Multi
+    for (N, H, T) in [(3328, 6, 110), (9464, 6, 110)]:
+        Tp = (T + 15) // 16 * 16
+        q = torch.randn(N, H * 256, device=dev).bfloat16()
+        z = torch.zeros(N, Tp, 256, device=dev, dtype=torch.bfloat16)
+        z[:, :T] = torch.randn(N, T, 256, device=dev).bfloat16()
+        o = torch.empty_like(q)
+        s_ = torch.cuda.current_stream().cuda_stream
+        us = timeit(lambda: _lib.check(lib.ymt3_op_cross_attn_absorbed(q.data_ptr(), z.data_ptr(), o.data_ptr(), N, H, T, Tp, s_)))
+        byts = z.numel() * 2 + 2 * q.numel() * 2
+        print(f"cross_attn_absorbed N={N} H={H} T={T}: {us:8.1f} us  {byts / us / 1e3:8.1f} GB/s (z + q + out bytes)", flush=True)
+
 if what in ("decode_attn", "all"):
     # self-attention over a bf16 KV cache (decode.cu) at the YPTF.MoE+Multi B=256 shape, cache length L
     N, H, Lcap = 3328, 6, 256

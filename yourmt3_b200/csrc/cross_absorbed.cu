@@ -13,10 +13,10 @@
 // kernel that was 35 % of the decode step.  Same function of the same weights; the association order differs,
 // so it is used on the bf16 path only (the fp32 token-exact path keeps the reference order).
 //
-// Kernel: PERSISTENT, one CTA (8 warps) per SM walking sequences n = blockIdx.x, += gridDim.x.  One elected thread
-// stages the (Tp x 256) bf16 latent tile and the sequence's H latent-space queries with TMA (four {64 col x rows}
-// boxes each, 128-byte hardware swizzle -> conflict-free ldmatrix, one mbarrier per stage) through a ring of up to 3
-// stages, so the tiles of the next two sequences are in flight while the current one is consumed.  Both products
+// Kernel: PERSISTENT CTAs (8 warps) walking sequences n = blockIdx.x, += gridDim.x.  One elected thread stages the
+// (Tp x 256) bf16 latent tile and the sequence's H latent-space queries with TMA (four {64 col x rows} boxes each,
+// 128-byte hardware swizzle -> conflict-free ldmatrix, one mbarrier per stage) through a ring of 1..3 stages.
+// Default shape: THREE CTAs per SM with one stage each (see the launcher): their load / compute phases interleave.  Both products
 // run on the tensor cores (mma.sync m16n8k16 - a skinny M = 6 heads batched product, HBM-bound by construction):
 //     S (H x Tp)  = Q' (H x 256) . Z^T       B fragments by ldmatrix        (Z rows = keys)
 //     O (H x 256) = P  (H x Tp)  . Z         B fragments by ldmatrix.trans
@@ -25,12 +25,15 @@
 // History (profiles/r01_cross_absorbed_*): v1 one CTA per sequence, cp.async, no prefetch: 73 us for 3328 sequences
 // (2.9 TB/s); v2 persistent + cp.async ring: same 73 us - ncu showed 6.8 k warp instructions per sequence, 28 % of
 // them cp.async address arithmetic, issue-bound at 8 warps/SM; v3 (this) TMA + register softmax: 48 us (4.2 TB/s).
+// v5 (this): same kernel, 1 stage x 3 co-resident CTAs per SM instead of 3 stages x 1 CTA: 121 -> 103.5 us for 9464
+// sequences (5.8 TB/s), end to end +2.4 %.
 // v4 experiment (NOT kept): a TMA producer warp + two 8-warp consumer groups on alternate sequences (named barriers,
 // full/empty mbarriers) ran 43 us but hung about once per 3000 launches (0.4 s watchdog kill) even after adding
 // warp reconvergence around every inline-asm wait/barrier; root cause not found in the time available.
 #include "ops.cuh"
 #include "decode.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace ymt3 {
 
@@ -320,8 +323,17 @@ int cross_attn_absorbed(const void* q, int64_t q_ld, const void* z, void* out, i
   YMT3_REQUIRE(q_ld == (int64_t)H * ZD && out_ld % 8 == 0, "cross_attn_absorbed: q must be contiguous (N, H*%d)", ZD);
   YMT3_REQUIRE(N * (int64_t)(Tp > H ? Tp : H) < (1ll << 31), "cross_attn_absorbed: too many rows");
   const size_t max_smem = 227 * 1024 - 1024;   // 1 KB slack for the 1024-byte alignment of the dynamic segment
-  int stages = 3;
-  while (stages > 1 && absorbed_smem(Tp, stages) > max_smem) --stages;
+  // pipeline shape: `stages` tiles per CTA x `ctas` persistent CTAs per SM.  Default 1 x 3: three co-resident CTAs
+  // (65 KB of shared memory, 72 registers per thread) each hold ONE tile and the hardware interleaves their phases -
+  // while one waits for its TMA load the others run their score / softmax / P.Z phases, which a single CTA with a
+  // 3-deep ring cannot overlap (its 8 warps move through the phases in lock step).  Measured (9464 sequences):
+  // 3 x 1 121 us = 4.96 TB/s, 1 x 3 103.5 us = 5.80 TB/s (89 % of measured HBM), 1 x 2 120 us, 2 x 1 122 us
+  // (profiles/r01_ab_xattn_shape.txt).  YMT3_XATTN_STAGES / YMT3_XATTN_CTAS override (A/B aids).
+  static const int env_stages = getenv("YMT3_XATTN_STAGES") ? atoi(getenv("YMT3_XATTN_STAGES")) : 0;
+  static const int env_ctas = getenv("YMT3_XATTN_CTAS") ? atoi(getenv("YMT3_XATTN_CTAS")) : 0;
+  int stages = env_stages >= 1 && env_stages <= 3 ? env_stages : 1;
+  const int ctas = env_ctas >= 1 && env_ctas <= 3 ? env_ctas : 3;
+  while (stages > 1 && (absorbed_smem(Tp, stages) + 1024) * ctas > max_smem + 1024 - 2048 * (ctas - 1)) --stages;
   const size_t smem = absorbed_smem(Tp, stages) + 1024;
   static size_t configured[64] = {0};   // per device: largest dynamic smem opted into so far
   int dev = 0;
@@ -334,7 +346,8 @@ int cross_attn_absorbed(const void* q, int64_t q_ld, const void* z, void* out, i
   int rc;
   if ((rc = make_row_map(&mq, q, N * H, H))) return rc;
   if ((rc = make_row_map(&mz, z, N * Tp, Tp))) return rc;
-  const int64_t grid = N < ymt3_num_sms() ? N : ymt3_num_sms();
+  const int64_t max_grid = (int64_t)ymt3_num_sms() * ctas;
+  const int64_t grid = N < max_grid ? N : max_grid;
   YMT3_CUDA_CHECK(ymt3_launch_pdl(cross_attn_absorbed_kernel, dim3((unsigned)grid), dim3(NTHREAD), smem, stream, mq, mz,
                                   (__nv_bfloat16*)out, out_ld, N, H, T, Tp, stages));
   return YMT3_OK;

@@ -235,6 +235,35 @@ def test_decode_attention_self_and_cross(cuda_device, native_lib, dtype, N, H, s
     assert float((out.float() - ref).abs().max()) < tol
 
 
+@pytest.mark.parametrize("B,H,Sq,Sk", [(5, 1, 26, 128), (3, 1, 24, 128), (2, 2, 32, 100), (4, 1, 7, 128), (3, 1, 16, 40),
+                                       (600, 1, 26, 128)])
+def test_attention_bf16_dk128_tensor_core(cuda_device, native_lib, B, H, Sq, Sk):
+    """wide-head tensor-core cross-attention (attn_wide_tc_kernel: bf16, dk 128, Sq <= 32, Sk <= 128 = the Perceiver-TF
+    spectral cross-attention) vs torch fp32 on the same bf16 inputs, and vs the SIMT kernel it replaces."""
+    import os
+    g = torch.Generator().manual_seed(B + Sq * 7 + Sk)
+    q, k, v = (torch.randn(B, S, H, 128, generator=g).to(torch.bfloat16) for S in (Sq, Sk, Sk))
+    scale = 1.0 / math.sqrt(128)
+    ref = OT.attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2), None,
+                       scale).view(B, Sq, H, 128)
+    qd, kd, vd = q.to(cuda_device), k.to(cuda_device), v.to(cuda_device)
+    outs = []
+    for no_tc in (False, True):
+        if no_tc:
+            os.environ["YMT3_NO_TC_ATTN"] = "1"
+        try:
+            o = torch.full((B, Sq, H, 128), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+            _lib.check(native_lib.ymt3_op_attention(1, qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), o.data_ptr(), B, H, Sq,
+                                                    Sk, 128, scale, 0, torch.cuda.current_stream().cuda_stream))
+            outs.append(o.float().cpu())
+        finally:
+            os.environ.pop("YMT3_NO_TC_ATTN", None)
+    # bf16 probabilities + bf16 output rounding on O(0.3) values
+    assert float((outs[0] - ref).abs().max()) < 2e-2
+    assert float((outs[0] - ref).abs().mean()) < 2e-3
+    assert float((outs[1] - ref).abs().max()) < 1e-2          # the SIMT kernel (only the output is rounded)
+
+
 @pytest.mark.parametrize("M,N,K,gated", [(300, 1152, 512, 0), (3328, 2048, 512, 1), (77, 600, 512, 0)])
 def test_linear_fused_rmsnorm_consumer(cuda_device, native_lib, M, N, K, gated):
     """GEMM on the un-normalised x with the norm weight folded into W and the row scale taken from sum-of-squares

@@ -487,6 +487,168 @@ bool launch_small_tc2(const AttnParams& p, cudaStream_t stream) {
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core cross-attention for ONE WIDE head (bf16, dk = 128, Sq <= 32 queries, Sk <= 128 keys): the Perceiver-TF
+// spectral cross-attention (26 latents attend 128 frequency tokens per time step; HF modeling_perceiver.py:135-242 with
+// num_heads = 1).  The generic kernel staged fp32 K/V per 16-query tile (K/V read twice, fp32 FFMA dot products) and ran
+// at ~10x its HBM floor.  Here one CTA (4 warps) owns one (batch, head): Q (32 x 128), K and V (128 x 128 each) are
+// staged ONCE as bf16 by cp.async into swizzled shared memory (72 KB, 3 CTAs per SM); warp w takes query tile w & 1
+// and output-dim half w >> 1: S = Q K^T for its 16 rows over all keys (mma.sync m16n8k16, B fragments by ldmatrix), a
+// register softmax (fp32, quad shuffles), P repacked in registers into A fragments, O = P V for its 64 dims
+// (ldmatrix.trans).  The two warps of a query tile recompute S (cheap) instead of exchanging it: no barrier after staging.
+// 16-byte chunk c (0..15) of row r sits at r*256 + ((c ^ (r & 7)) << 4): conflict-free ldmatrix with 256-byte rows.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t xw_off(int r, int c) { return (uint32_t)(r * 256 + ((c ^ (r & 7)) << 4)); }
+__device__ __forceinline__ void xw_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(128, 3) attn_wide_tc_kernel(AttnParams p) {
+  extern __shared__ __align__(128) unsigned char xw_sm[];
+  typedef __nv_bfloat16 T;
+  constexpr int SQP = 32, SKP = 128, NT = SKP / 8;
+  unsigned char* Qs = xw_sm;                   // 32 rows x 256 B
+  unsigned char* Ks = Qs + SQP * 256;          // 128 rows x 256 B
+  unsigned char* Vs = Ks + SKP * 256;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = (int)(blockIdx.x % p.H);
+  const int64_t b = blockIdx.x / p.H;
+  int64_t bo = b, bi = 0;
+  if (p.inner > 1) {
+    bo = b / p.inner;
+    bi = b - bo * p.inner;
+  }
+  const T* Q = static_cast<const T*>(p.Q) + bo * p.q_sb + bi * p.q_sb2 + (int64_t)h * p.q_sh;
+  const T* K = static_cast<const T*>(p.K) + bo * p.k_sb + bi * p.k_sb2 + (int64_t)h * p.k_sh;
+  const T* V = static_cast<const T*>(p.V) + bo * p.v_sb + bi * p.v_sb2 + (int64_t)h * p.v_sh;
+  T* O = static_cast<T*>(p.O) + bo * p.o_sb + bi * p.o_sb2 + (int64_t)h * p.o_sh;
+  const int kv_len = p.kv_len ? min(p.kv_len[b], p.Sk) : p.Sk;
+  const uint32_t qs = tc_smem_addr(Qs), ks = tc_smem_addr(Ks), vs = tc_smem_addr(Vs);
+
+  // stage: 16 chunks of 16 bytes per row; rows past the valid range are zero-filled with plain stores
+  for (int idx = tid; idx < SKP * 16; idx += 128) {
+    const int r = idx >> 4, c = idx & 15;
+    if (r < kv_len) {
+      xw_cp16(ks + xw_off(r, c), K + (int64_t)r * p.k_ss + 8 * c);
+      xw_cp16(vs + xw_off(r, c), V + (int64_t)r * p.v_ss + 8 * c);
+    } else {
+      *reinterpret_cast<uint4*>(Ks + xw_off(r, c)) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(Vs + xw_off(r, c)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  for (int idx = tid; idx < SQP * 16; idx += 128) {
+    const int r = idx >> 4, c = idx & 15;
+    if (r < p.Sq) xw_cp16(qs + xw_off(r, c), Q + (int64_t)r * p.q_ss + 8 * c);
+    else *reinterpret_cast<uint4*>(Qs + xw_off(r, c)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const int lr = lane & 7, lm = lane >> 3;
+  const int m0 = (warp & 1) * 16;              // query tile of this warp
+  const int dh = warp >> 1;                    // output-dim half of this warp
+  if (m0 >= p.Sq) return;                      // (no barrier below)
+
+  // S = Q K^T: 16 rows x 128 keys, 8 k-steps over the 128 dims
+  float sacc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    uint32_t a0, a1, a2, a3;   // matrices (rows 0-7, c), (rows 8-15, c), (rows 0-7, c+1), (rows 8-15, c+1)
+    tc_ldsm_x4(qs + xw_off(m0 + lr + ((lm & 1) << 3), 2 * kk + (lm >> 1)), a0, a1, a2, a3);
+#pragma unroll
+    for (int j = 0; j < NT; j += 2) {
+      uint32_t b0, b1, b2, b3;  // (keys 8j.., c), (keys 8j.., c+1), (keys 8j+8.., c), (keys 8j+8.., c+1)
+      tc_ldsm_x4(ks + xw_off(8 * j + lr + ((lm >> 1) << 3), 2 * kk + (lm & 1)), b0, b1, b2, b3);
+      tc_mma(sacc[j], a0, a1, a2, a3, b0, b1);
+      tc_mma(sacc[j + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+  // softmax over keys [0, kv_len) for rows g (c0, c1) and g + 8 (c2, c3); this thread holds keys 8j + 2t, +1
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int k0 = 8 * j + 2 * t;
+    if (k0 >= kv_len) sacc[j][0] = sacc[j][2] = -INFINITY;
+    if (k0 + 1 >= kv_len) sacc[j][1] = sacc[j][3] = -INFINITY;
+    mx0 = fmaxf(mx0, fmaxf(sacc[j][0], sacc[j][1]));
+    mx1 = fmaxf(mx1, fmaxf(sacc[j][2], sacc[j][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float sl = p.scale * 1.4426950408889634f;   // softmax(scale * s) via exp2
+  const float mb0 = mx0 == -INFINITY ? 0.f : mx0 * sl, mb1 = mx1 == -INFINITY ? 0.f : mx1 * sl;
+  float l0 = 0.f, l1 = 0.f;
+  float oacc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+    // P of key tiles 2kk, 2kk+1 = one k-step of 16 keys, repacked from the accumulator layout into an A fragment
+    float pv[8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      pv[4 * u + 0] = exp2f(fmaf(sacc[2 * kk + u][0], sl, -mb0));
+      pv[4 * u + 1] = exp2f(fmaf(sacc[2 * kk + u][1], sl, -mb0));
+      pv[4 * u + 2] = exp2f(fmaf(sacc[2 * kk + u][2], sl, -mb1));
+      pv[4 * u + 3] = exp2f(fmaf(sacc[2 * kk + u][3], sl, -mb1));
+    }
+    l0 += (pv[0] + pv[1]) + (pv[4] + pv[5]);
+    l1 += (pv[2] + pv[3]) + (pv[6] + pv[7]);
+    const uint32_t pa0 = tc_pack(pv[0], pv[1]), pa1 = tc_pack(pv[2], pv[3]);
+    const uint32_t pa2 = tc_pack(pv[4], pv[5]), pa3 = tc_pack(pv[6], pv[7]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      // V for keys 16kk..16kk+15, dims 64dh + 16nt .. +15: (keys lo, c), (keys hi, c), (keys lo, c+1), (keys hi, c+1), transposed
+      uint32_t v0, v1, v2, v3;
+      tc_ldsm_x4_t(vs + xw_off(16 * kk + lr + ((lm & 1) << 3), 8 * dh + 2 * nt + (lm >> 1)), v0, v1, v2, v3);
+      tc_mma(oacc[2 * nt], pa0, pa1, pa2, pa3, v0, v1);
+      tc_mma(oacc[2 * nt + 1], pa0, pa1, pa2, pa3, v2, v3);
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+  // this thread: rows m0 + g and m0 + g + 8, dims 64dh + 8n + 2t, +1 for n = 0..7
+  const int r0 = m0 + g, r1 = m0 + g + 8;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int d = 64 * dh + 8 * n + 2 * t;
+    if (r0 < p.Sq) *reinterpret_cast<uint32_t*>(O + (int64_t)r0 * p.o_ss + d) = tc_pack(oacc[n][0] * i0, oacc[n][1] * i0);
+    if (r1 < p.Sq) *reinterpret_cast<uint32_t*>(O + (int64_t)r1 * p.o_ss + d) = tc_pack(oacc[n][2] * i1, oacc[n][3] * i1);
+  }
+}
+
+// bf16, one wide head (dk 128), few queries, <= 128 keys, 16-byte aligned rows: the kernel above
+bool try_launch_wide_tc(const AttnParams& p, cudaStream_t stream) {
+  if (p.dk != 128 || p.causal || p.Sq > 32 || p.Sk > 128 || p.rope_dim > 0) return false;
+  if ((p.q_ss % 8 | p.k_ss % 8 | p.v_ss % 8 | p.q_sh % 8 | p.k_sh % 8 | p.v_sh % 8 | p.q_sb % 8 | p.k_sb % 8 | p.v_sb % 8 |
+       p.q_sb2 % 8 | p.k_sb2 % 8 | p.v_sb2 % 8 | p.o_ss % 2 | p.o_sh % 2 | p.o_sb % 2 | p.o_sb2 % 2) != 0)
+    return false;
+  if ((((uintptr_t)p.Q | (uintptr_t)p.K | (uintptr_t)p.V) & 15) != 0 || ((uintptr_t)p.O & 3) != 0) return false;
+  if (getenv("YMT3_NO_TC_ATTN")) return false;
+  const int64_t blocks = (int64_t)p.B * p.H;
+  if (blocks >= (1ll << 31)) return false;
+  const size_t smem = (32 + 2 * 128) * 256;
+  static bool configured[64] = {false};   // per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    if (cudaFuncSetAttribute(attn_wide_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return false;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  attn_wide_tc_kernel<<<(unsigned)blocks, 128, smem, stream>>>(p);
+  return true;
+}
+
 template <int NT>
 bool launch_small_tc(const AttnParams& p, cudaStream_t stream) {
   switch (p.rope_dim) {
@@ -537,7 +699,7 @@ static bool try_launch_small(const AttnParams& p, cudaStream_t stream) {
 template <typename T>
 static int launch_attn(const AttnParams& p, cudaStream_t stream) {
   if constexpr (sizeof(T) == 2) {
-    if (try_launch_small_tc(p, stream)) {
+    if (try_launch_small_tc(p, stream) || try_launch_wide_tc(p, stream)) {
       YMT3_CUDA_CHECK(cudaGetLastError());
       return YMT3_OK;
     }

@@ -4,11 +4,12 @@
 O=gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > $O/final_pytest_gpu.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -12 > $O/final_smoke.txt
+timeout 300 python tools/stress_cross_absorbed.py 9464 3328 5000 4000 > $O/final_stress_xattn.txt 2>&1
 timeout 600 python bench.py 2>$O/final_bench_default.err | tail -1 > $O/final_bench_default.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > $O/final_bench_reference_arm.json
 timeout 300 python bench.py --workload frontend --steps 10 2>/dev/null | tail -1 > $O/final_bench_frontend.json
 timeout 300 python bench.py --workload t5_small --steps 3 --no-cpu-baseline 2>/dev/null | tail -1 > $O/final_bench_t5_small.json
 timeout 300 python bench.py --workload yptf --steps 3 --no-cpu-baseline 2>/dev/null | tail -1 > $O/final_bench_yptf_b64.json
 timeout 300 python bench.py --workload yptf --batch 256 --steps 3 --no-cpu-baseline 2>/dev/null | tail -1 > $O/final_bench_yptf_b256.json
-YMT3_PDL=1 timeout 300 python bench.py --steps 3 --no-cpu-baseline 2>/dev/null | tail -1 > $O/final_bench_default_pdl.json
-tail -2 $O/final_pytest_gpu.txt; tail -2 $O/final_smoke.txt
+timeout 300 python bench.py --batch 512 --steps 3 --no-cpu-baseline 2>/dev/null | tail -1 > $O/final_bench_default_b512.json
+tail -2 $O/final_pytest_gpu.txt; tail -2 $O/final_smoke.txt; cat $O/final_stress_xattn.txt

@@ -12,9 +12,16 @@ copies (SP = site-packages/transformers/models/t5/modeling_t5.py):
 * KV cache semantics (self K/V appended per step, cross K/V computed once)  SP:269-305
 * logits * d_model**-0.5 when embeddings are tied                    SP:1105-1110
 
+* relative attention bias (bucketed, learned per head in block 0, shared by all blocks)  SP:200-268, 625, 755-760
+
+Position handling is SWITCHABLE: when the state dict holds
+``block.0.layer.0.SelfAttention.relative_attention_bias.weight`` the HF relative bias is added to
+every self-attention score (bidirectional buckets in the encoder, unidirectional in the decoder);
+otherwise no bias is used (upstream's absolute-position variant).  Both are pinned against HF.
+
 Upstream specifics restated from memory of mimbres/YourMT3 ([RECALL], unverifiable here):
 absolute sinusoidal position encoding added to ``inputs_embeds`` (no relative attention
-bias), decoder start token 0 (= pad), EOS = 1, rows that emitted EOS are padded with 0,
+bias by default), decoder start token 0 (= pad), EOS = 1, rows that emitted EOS are padded with 0,
 the loop stops when every row is finished or ``max_length`` is reached
 (``t5mod_helper.task_cond_dec_generate``).
 
@@ -65,6 +72,34 @@ def attention(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor] = None, sc
     return o.transpose(1, 2).reshape(B, Sq, H * dk)
 
 
+def relative_position_bucket(rel: Tensor, bidirectional: bool, num_buckets: int = 32, max_distance: int = 128) -> Tensor:
+    """HF ``T5Attention._relative_position_bucket`` (SP:200-246): rel = key_pos - query_pos (int64) -> bucket id."""
+    ret = torch.zeros_like(rel)
+    if bidirectional:
+        num_buckets //= 2
+        ret = ret + (rel > 0).to(torch.long) * num_buckets
+        rel = rel.abs()
+    else:
+        rel = -torch.min(rel, torch.zeros_like(rel))
+    max_exact = num_buckets // 2
+    is_small = rel < max_exact
+    large = max_exact + (torch.log(rel.float() / max_exact) / math.log(max_distance / max_exact)
+                         * (num_buckets - max_exact)).to(torch.long)
+    large = torch.min(large, torch.full_like(large, num_buckets - 1))
+    return ret + torch.where(is_small, rel, large)
+
+
+def relative_bias(sd, prefix: str, q_pos: Tensor, k_len: int, bidirectional: bool, max_distance: int = 128) -> Optional[Tensor]:
+    """HF ``compute_bias`` (SP:248-268) for query positions q_pos (Sq,) over keys 0..k_len-1 -> (1, H, Sq, k_len),
+    or None when the state dict carries no relative attention bias (absolute-position variant)."""
+    w = sd.get(prefix + "block.0.layer.0.SelfAttention.relative_attention_bias.weight")
+    if w is None:
+        return None
+    rel = torch.arange(k_len, dtype=torch.long, device=w.device)[None, :] - q_pos.to(torch.long)[:, None]
+    bucket = relative_position_bucket(rel, bidirectional, num_buckets=w.shape[0], max_distance=max_distance)
+    return w[bucket].permute(2, 0, 1)[None]           # (Sq, Sk, H) -> (1, H, Sq, Sk)
+
+
 def t5_self_attention_layer(sd, pre, x, n_heads, eps, mask=None):
     h = rms_norm(x, sd[pre + "layer_norm.weight"], eps)
     a = pre + "SelfAttention."
@@ -86,9 +121,11 @@ def t5_encoder(sd: Dict[str, Tensor], x: Tensor, *, n_layers: int, n_heads: int,
     """inputs_embeds (B, T, d_model) -> last_hidden_state (B, T, d_model)."""
     if pos is not None:
         x = x + pos[: x.shape[1]]
+    T = x.shape[1]
+    bias = relative_bias(sd, prefix, torch.arange(T), T, bidirectional=True)
     for i in range(n_layers):
         b = f"{prefix}block.{i}.layer."
-        x, _ = t5_self_attention_layer(sd, b + "0.", x, n_heads, eps)
+        x, _ = t5_self_attention_layer(sd, b + "0.", x, n_heads, eps, mask=bias)
         x = t5_ff_layer(sd, b + "1.", x, eps)
     return rms_norm(x, sd[prefix + "final_layer_norm.weight"], eps)
 
@@ -99,6 +136,9 @@ def t5_decoder_full(sd, x, enc_hs, *, n_layers, n_heads, eps=1e-6, prefix="", po
     if pos is not None:
         x = x + pos[:S]
     causal = torch.full((S, S), float("-inf"), device=x.device).triu(1)
+    bias = relative_bias(sd, prefix, torch.arange(S), S, bidirectional=False)
+    if bias is not None:
+        causal = causal + bias
     for i in range(n_layers):
         b = f"{prefix}block.{i}.layer."
         x, _ = t5_self_attention_layer(sd, b + "0.", x, n_heads, eps, mask=causal)
@@ -131,6 +171,8 @@ class T5DecoderState:
         sd, H, eps = self.sd, self.n_heads, self.eps
         if self.pos is not None:
             x = x + self.pos[self.len: self.len + 1]
+        # relative bias of the single query at position len over keys 0..len (SP:296-303 with a cache)
+        bias = relative_bias(sd, self.prefix, torch.tensor([self.len]), self.len + 1, bidirectional=False)
         for i in range(self.n_layers):
             b = f"{self.prefix}block.{i}.layer."
             h = rms_norm(x, sd[b + "0.layer_norm.weight"], eps)
@@ -142,7 +184,7 @@ class T5DecoderState:
                 k = torch.cat([self.self_k[i], k], dim=2)
                 v = torch.cat([self.self_v[i], v], dim=2)
             self.self_k[i], self.self_v[i] = k, v
-            x = x + attention(q, k, v) @ sd[a + "o.weight"].T
+            x = x + attention(q, k, v, bias) @ sd[a + "o.weight"].T
             h = rms_norm(x, sd[b + "1.layer_norm.weight"], eps)
             a = b + "1.EncDecAttention."
             q = _heads(h @ sd[a + "q.weight"].T, H)

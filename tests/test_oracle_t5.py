@@ -13,7 +13,7 @@ from transformers import T5Config  # noqa: E402
 from transformers.models.t5.modeling_t5 import T5Stack  # noqa: E402
 
 
-def make_stacks(n_layers=2, seed=0, std=0.05):
+def make_stacks(n_layers=2, seed=0, std=0.05, relative_bias=False):
     cfg = T5Config(vocab_size=64, d_model=512, d_kv=64, d_ff=1024, num_layers=n_layers, num_decoder_layers=n_layers,
                    num_heads=6, feed_forward_proj="gated-gelu", dropout_rate=0.0, layer_norm_epsilon=1e-6,
                    is_decoder=False, use_cache=False)
@@ -26,7 +26,10 @@ def make_stacks(n_layers=2, seed=0, std=0.05):
         with torch.no_grad():
             for n, p in m.named_parameters():
                 if "relative_attention_bias" in n:
-                    p.zero_()
+                    if relative_bias:
+                        p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+                    else:
+                        p.zero_()
                 elif p.dim() >= 2:
                     p.copy_(torch.randn(p.shape, generator=g) * std)
                 else:
@@ -63,6 +66,34 @@ def test_decoder_full_and_incremental_match_hf():
             past = h.past_key_values
             assert torch.allclose(o, ref[:, t:t + 1], atol=3e-5, rtol=1e-5)
             assert torch.allclose(o, h.last_hidden_state, atol=3e-5, rtol=1e-5)
+
+
+def test_relative_attention_bias_matches_hf():
+    """the HF relative position bias (bucketed, block 0, shared) is switchable in the oracle - encoder
+    (bidirectional buckets, lengths beyond max_distance), decoder full and incremental (unidirectional)."""
+    enc, dec = make_stacks(seed=7, relative_bias=True)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 150, 512, generator=g)            # > max_distance 128: the logarithmic buckets saturate
+    with torch.no_grad():
+        ref = enc(inputs_embeds=x).last_hidden_state
+        got = OT.t5_encoder(enc.state_dict(), x, n_layers=2, n_heads=6)
+        assert torch.allclose(got, ref, atol=3e-5, rtol=1e-5)
+        off = OT.t5_encoder({k: v for k, v in enc.state_dict().items() if "relative_attention_bias" not in k}, x,
+                            n_layers=2, n_heads=6)
+        assert float((off - ref).abs().max()) > 1e-2     # the bias matters: the switch is not vacuous
+        enc_hs = torch.randn(2, 19, 512, generator=g)
+        y = torch.randn(2, 40, 512, generator=g)
+        sd = dec.state_dict()
+        ref = dec(inputs_embeds=y, encoder_hidden_states=enc_hs, use_cache=False).last_hidden_state
+        assert torch.allclose(OT.t5_decoder_full(sd, y, enc_hs, n_layers=2, n_heads=6), ref, atol=3e-5, rtol=1e-5)
+        st = OT.T5DecoderState(sd, enc_hs, n_layers=2, n_heads=6)
+        for t in range(40):
+            assert torch.allclose(st.step(y[:, t:t + 1]), ref[:, t:t + 1], atol=3e-4, rtol=1e-4)   # fp32 summation order
+    # bucket function against HF's static method on a grid of offsets
+    from transformers.models.t5.modeling_t5 import T5Attention
+    rel = torch.arange(-300, 301)[None, :]
+    for bidir in (True, False):
+        assert torch.equal(OT.relative_position_bucket(rel, bidir), T5Attention._relative_position_bucket(rel, bidir))
 
 
 def test_sinusoidal_table_properties():

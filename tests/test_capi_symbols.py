@@ -36,6 +36,31 @@ def test_abi_version_and_error_string(native_lib):
     assert rc == 1 and b"n_fft=2048" in native_lib.ymt3_last_error()
 
 
+def test_op_argument_validation_without_gpu(native_lib):
+    """every per-op entry point checks shapes / alignment / null pointers BEFORE its first CUDA call, returns a
+    non-zero status and leaves a message (the same contract the GPU tests rely on for error behaviour)."""
+    buf = (ctypes.c_float * 4096)()
+    p = ctypes.addressof(buf)
+    # fused arg-max vocab projection: V must be in (0, N], keys must be given
+    assert native_lib.ymt3_op_linear_argmax(1, p, 64, p, 64, None, p, 64, 8, 64, 64, 65, 1.0, p, None) != 0
+    assert b"bad shape" in native_lib.ymt3_last_error()
+    assert native_lib.ymt3_op_linear_argmax(1, p, 64, p, 64, None, p, 64, 8, 64, 64, 60, 1.0, None, None) != 0
+    assert b"null keys" in native_lib.ymt3_last_error()
+    # tensor-core linear: K must be a multiple of 8
+    assert native_lib.ymt3_op_linear(1, p, 60, p, 60, None, p, 64, None, 0, 8, 64, 60, 0, 0, 1.0, 1, None) != 0
+    assert b"multiples of 8" in native_lib.ymt3_last_error()
+    # decode attention: cross mode needs 0 < fixed_len <= capacity; self mode needs the device step
+    assert native_lib.ymt3_op_decode_attention(1, p, None, None, p, p, None, 300, p, 2, 6, 256, None) != 0
+    assert b"bad length" in native_lib.ymt3_last_error()
+    assert native_lib.ymt3_op_decode_attention(1, p, p, p, p, p, None, 0, p, 2, 6, 256, None) != 0
+    assert b"bad length" in native_lib.ymt3_last_error()
+    # absorbed cross-attention: padded length must be a multiple of 16 and <= 128
+    assert native_lib.ymt3_op_cross_attn_absorbed(p, p, p, 4, 6, 110, 111, None) != 0
+    assert b"encoder length" in native_lib.ymt3_last_error()
+    assert native_lib.ymt3_op_cross_attn_absorbed(p, p, p, 4, 9, 110, 112, None) != 0
+    assert b"heads" in native_lib.ymt3_last_error()
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     monkeypatch.setattr(_lib, "_lib", None)

@@ -1,0 +1,98 @@
+"""CPU tier: the pure index maps / packings / heuristics of this repo's GEMM epilogue and fused greedy selection
+(yourmt3_b200/csrc/index_maps.h, compiled for the host by tests/host_emu) pinned against independent restatements:
+torch.argmax for the packed arg-max keys, the published TMA swizzle patterns (Swizzle<B,4,3>) and shared-memory bank
+arithmetic for the staging layout, a brute-force cost search for the tile-width rule."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from yourmt3_b200 import build as B
+    lib = C.CDLL(B.build_host_emu())
+    lib.emu_argmax_key.restype = C.c_uint64
+    lib.emu_argmax_key.argtypes = [C.c_float, C.c_int]
+    lib.emu_argmax_rows.restype = None
+    lib.emu_argmax_rows.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.emu_tma_box_offset.restype = C.c_int
+    lib.emu_tma_box_offset.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.emu_gemm_choose_bn.restype = C.c_int
+    lib.emu_gemm_choose_bn.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int]
+    return lib
+
+
+def test_argmax_key_is_monotone_and_breaks_ties_towards_the_first_column(emu):
+    vals = [float("-inf"), -3.0e38, -1.0, -1e-30, -0.0, 0.0, 1e-45, 1e-30, 0.5, 1.0, 3.0e38, float("inf")]
+    keys = [emu.emu_argmax_key(v, 7) for v in vals]
+    for (va, ka), (vb, kb) in zip(zip(vals, keys), zip(vals[1:], keys[1:])):
+        assert (ka < kb) if va < vb else (ka == kb), (va, vb)          # -0.0 == +0.0 -> equal keys
+    assert all(k > 0 for k in keys)                                     # 0 is reserved for "no column seen"
+    assert emu.emu_argmax_key(1.25, 3) > emu.emu_argmax_key(1.25, 4)    # equal values: smaller column wins
+    k = emu.emu_argmax_key(-2.0, 595)
+    assert 0xFFFFFFFF - (k & 0xFFFFFFFF) == 595
+
+
+@pytest.mark.parametrize("M,V,bn", [(64, 596, 128), (17, 596, 256), (33, 1391, 64), (9, 40, 32), (5, 600, 128)])
+def test_emulated_epilogue_reduction_equals_torch_argmax(emu, M, V, bn):
+    g = torch.Generator().manual_seed(M + V)
+    N = (V + 7) // 8 * 8
+    x = torch.randn(M, N, generator=g)
+    x[:, V:] = 100.0                                   # padded vocabulary columns must never win
+    x[0, :V] = 0.0                                     # all equal -> column 0
+    x[1, 5] = x[1, 300 % V] = x[1, V - 1] = 50.0       # exact ties across chunks / tiles -> first
+    x[2, :V] = -0.0
+    x[2, 3] = 0.0                                      # +0.0 == -0.0: still column 0
+    if M > 3:
+        x[3, :V] = float("-inf")
+        x[3, V - 1] = -1e30
+    xc = np.ascontiguousarray(x.numpy())
+    keys = np.zeros(M, dtype=np.uint64)
+    emu.emu_argmax_rows(xc.ctypes.data, M, N, N, V, bn, keys.ctypes.data)
+    col = (0xFFFFFFFF - (keys & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    ref = torch.argmax(x[:, :V], dim=-1).numpy()
+    assert np.array_equal(col, ref)
+    assert col[0] == 0 and col[1] == min(5, 300 % V) and col[2] == 0
+
+
+@pytest.mark.parametrize("rb,bits", [(32, 1), (64, 2), (128, 3)])
+def test_tma_staging_offsets_follow_the_hardware_swizzle_and_are_conflict_free(emu, rb, bits):
+    units = rb // 16
+    seen = set()
+    for u in range(units):
+        banks = []
+        for row in range(32):
+            off = emu.emu_tma_box_offset(row, u, rb)
+            lin = row * rb + u * 16
+            # Swizzle<bits, 4, 3>: address bits [4, 4+bits) ^= bits [7, 7+bits) (box base 1024-byte aligned)
+            want = lin ^ (((lin >> 7) & ((1 << bits) - 1)) << 4)
+            assert off == want
+            assert off // rb == row                     # the swizzle permutes units inside a row only
+            seen.add(off)
+            banks.append((off % 128) // 16)
+        # a warp-wide 16-byte store (lane = row) needs 4 shared-memory wavefronts of 8 x 16 B: every 16-byte bank group
+        # must be hit exactly 4 times, i.e. no conflict beyond the unavoidable minimum
+        assert sorted(banks) == sorted(list(range(8)) * 4)
+    assert len(seen) == 32 * units                      # a bijection onto the box
+
+
+def test_tile_width_rule_is_the_argmin_of_the_cost_model(emu):
+    sms = 148
+    for m_tiles in (1, 7, 26, 52, 74, 313, 1430, 2860):
+        for N in (32, 96, 128, 384, 512, 600, 1024, 1152, 1536, 2048, 8192):
+            bn = emu.emu_gemm_choose_bn(m_tiles, N, sms, 256)
+            cands = [b for b in (256, 128, 64, 32) if b == 32 or N >= b]
+            cost = {b: -(-(m_tiles * -(-N // b)) // sms) * (128 + b) for b in cands}
+            assert bn in cands and cost[bn] == min(cost.values())
+            assert all(cost[b] > cost[bn] for b in cands if b > bn)      # ties go to the wider tile
+            assert emu.emu_gemm_choose_bn(m_tiles, N, sms, 128) <= 128     # the A/B cap is honoured
+    # the cases DESIGN.md quotes: decode-step GEMMs at 52 M-tiles take 256-wide tiles, tiny problems the narrowest
+    assert emu.emu_gemm_choose_bn(52, 512, sms, 256) == 256
+    assert emu.emu_gemm_choose_bn(52, 1152, sms, 256) == 256
+    assert emu.emu_gemm_choose_bn(1, 512, sms, 256) == 32
+    assert emu.emu_gemm_choose_bn(1430, 384, sms, 256) == 128

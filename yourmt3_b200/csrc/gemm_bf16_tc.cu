@@ -455,7 +455,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int stg_rb_all = CPW * (e_gated ? 32 : 64);              // staged bytes per row, all boxes
     const int stg_rb = stg_rb_all > 128 ? 128 : stg_rb_all;        // bytes per row of one box
     const int stg_row = lane * stg_rb;
-    const int stg_xor = ((stg_row >> 7) & ((stg_rb >> 4) - 1)) << 4;
+    const int stg_xor = tma_swizzle_xor(lane, stg_rb);   // index_maps.h
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       int m0, row_end, n0, w_row0, g;
@@ -731,7 +731,6 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   // pick BN so that the grid fills the 148 SMs (2 CTAs/SM resident) when the problem allows
   const int64_t mt = ymt3_div_up(p.M, BM);
   const int sms = ymt3_num_sms();
-  // largest BN whose tile count still fills the SMs; otherwise maximise parallelism
   // Tile width: the mainloop of these GEMMs is bound by the L2 -> shared-memory fill (a 128 x BN tile moves
   // (128 + BN) * K * 2 bytes for 128 * BN outputs), and every SM works through ceil(tiles / SMs) tiles, so pick the BN
   // in {256, 128, 64, 32} that minimises rounds * (128 + BN) (ties: the wider tile).  With fewer tiles than SMs that is
@@ -739,18 +738,7 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   // decode step (e.g. N = 512: 104 tiles in ONE round instead of 208 tiles of 128 in two).  YMT3_GEMM_MAX_BN (A/B aid)
   // caps BN.
   static const int max_bn = getenv("YMT3_GEMM_MAX_BN") ? atoi(getenv("YMT3_GEMM_MAX_BN")) : 256;
-  int bn = 32;
-  {
-    int64_t best = -1;
-    const int cand[4] = {256, 128, 64, 32};
-    for (int i = 0; i < 4; ++i) {
-      const int b = cand[i];
-      if (b > max_bn || (b > 32 && p.N < b)) continue;
-      const int64_t tiles = mt * ymt3_div_up(p.N, b);
-      const int64_t cost = ymt3_div_up(tiles, sms) * (int64_t)(128 + b);
-      if (best < 0 || cost < best) { best = cost; bn = b; }
-    }
-  }
+  const int bn = gemm_choose_bn(mt, p.N, sms, max_bn);   // index_maps.h
   static const bool generic_only = getenv("YMT3_GEMM_DIRECT_STORE") || getenv("YMT3_GEMM_TMA_GATED") ||
                                    getenv("YMT3_GEMM_GENERIC");   // A/B switches act on the run-time kernel
   const int code = generic_only ? -1 : p.act * 4 + (p.gated ? 2 : 0) + (out_dtype == YMT3_F32 ? 1 : 0);

@@ -4,6 +4,7 @@
 // accumulation, softmax and normalisation statistics are always fp32.
 #pragma once
 #include "common.cuh"
+#include "index_maps.h"   // argmax_key, TMA staging maps, tile-width heuristic (shared with tests/host_emu)
 
 #define YMT3_F32 0
 #define YMT3_BF16 1
@@ -58,18 +59,11 @@ struct GemmParams {
   const float* norm_ss_in; int norm_ss_chunks; float norm_eps;
   float* ss_out;
   // Fused greedy selection (vocab projection of the decode step; fp32 output, no residual, not gated): every
-  // epilogue thread folds the columns < argmax_n it produced into one packed key (argmax_key below) and issues one
+  // epilogue thread folds the columns < argmax_n it produced into one packed key (argmax_key, index_maps.h) and issues one
   // atomicMax per row and tile into argmax_out (M keys, zero before the launch).  The maximum key is the largest
   // logit with the SMALLEST column index among equals = torch.argmax's first-maximum rule.
   unsigned long long* argmax_out; int argmax_n;
 };
-
-// monotone packing of (fp32 value, column): larger value wins, then the smaller column
-__device__ __forceinline__ unsigned long long argmax_key(float v, int col) {
-  unsigned int u = __float_as_uint(v + 0.0f);   // -0.0 -> +0.0 (equal values must produce equal high words)
-  u = (u >> 31) ? ~u : (u | 0x80000000u);
-  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)col);
-}
 
 int gemm_f32(const GemmParams& p, cudaStream_t stream);            // SIMT fp32 FFMA
 int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream);  // tcgen05/TMEM/TMA

@@ -29,3 +29,5 @@ EMU_API void emu_argmax_rows(const float* logits, long long M, long long ld, int
 
 EMU_API int emu_tma_box_offset(int row, int unit, int rb) { return tma_box_offset(row, unit, rb); }
 EMU_API int emu_gemm_choose_bn(long long m_tiles, int N, int sms, int max_bn) { return gemm_choose_bn(m_tiles, N, sms, max_bn); }
+EMU_API unsigned emu_tc_row_off(int r, int c) { return tc_row_off(r, c); }
+EMU_API unsigned emu_xw_off(int r, int c) { return xw_off(r, c); }

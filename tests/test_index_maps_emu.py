@@ -24,6 +24,9 @@ def emu():
     lib.emu_tma_box_offset.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.emu_gemm_choose_bn.restype = C.c_int
     lib.emu_gemm_choose_bn.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int]
+    for f in (lib.emu_tc_row_off, lib.emu_xw_off):
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_int, C.c_int]
     return lib
 
 
@@ -96,3 +99,23 @@ def test_tile_width_rule_is_the_argmin_of_the_cost_model(emu):
     assert emu.emu_gemm_choose_bn(52, 1152, sms, 256) == 256
     assert emu.emu_gemm_choose_bn(1, 512, sms, 256) == 32
     assert emu.emu_gemm_choose_bn(1430, 384, sms, 256) == 128
+
+
+@pytest.mark.parametrize("name,row_bytes,rows", [("emu_tc_row_off", 32, 128), ("emu_xw_off", 256, 128)])
+def test_attention_tile_swizzles_are_bijective_and_ldmatrix_conflict_free(emu, name, row_bytes, rows):
+    """the mma.sync attention kernels stage Q/K/V rows of 32 bytes (dk 16) or 256 bytes (dk 128) in shared memory and
+    read them with ldmatrix: every 8-lane phase fetches the SAME logical 16-byte chunk of 8 consecutive rows, which must
+    land in 8 different 16-byte bank groups; the map must also be a bijection that keeps a chunk inside its row."""
+    f = getattr(emu, name)
+    chunks = row_bytes // 16
+    seen = set()
+    for r in range(rows):
+        for c in range(chunks):
+            off = f(r, c)
+            assert off % 16 == 0 and off // row_bytes == r
+            seen.add(off)
+    assert len(seen) == rows * chunks
+    for r0 in range(0, rows, 8):                      # ldmatrix phases start at multiples of 8 rows in both kernels
+        for c in range(chunks):
+            groups = {(f(r0 + i, c) % 128) // 16 for i in range(8)}
+            assert len(groups) == 8, (name, r0, c)

@@ -301,7 +301,6 @@ __global__ void __launch_bounds__(128) attn_small_kernel(AttnParams p, int G, in
 namespace {
 
 __device__ __forceinline__ uint32_t tc_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t tc_row_off(int r, int c) { return (uint32_t)(r * 32 + ((c ^ ((r >> 2) & 1)) << 4)); }
 __device__ __forceinline__ void tc_ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -498,7 +497,6 @@ bool launch_small_tc2(const AttnParams& p, cudaStream_t stream) {
 // (ldmatrix.trans).  The two warps of a query tile recompute S (cheap) instead of exchanging it: no barrier after staging.
 // 16-byte chunk c (0..15) of row r sits at r*256 + ((c ^ (r & 7)) << 4): conflict-free ldmatrix with 256-byte rows.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t xw_off(int r, int c) { return (uint32_t)(r * 256 + ((c ^ (r & 7)) << 4)); }
 __device__ __forceinline__ void xw_cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }

@@ -36,6 +36,14 @@ YMT3_HD int tma_swizzle_xor(int row, int rb) { return (((row * rb) >> 7) & ((rb 
 // byte offset inside the box of 16-byte unit `unit` of row `row`
 YMT3_HD int tma_box_offset(int row, int unit, int rb) { return row * rb + ((unit << 4) ^ tma_swizzle_xor(row, rb)); }
 
+// ---- swizzled shared-memory tiles of the mma.sync attention kernels (attention.cu) ---------------------------------
+// 16-byte chunk c of row r.  ldmatrix reads 8 rows x 16 bytes per 8-lane phase: the 8 addresses of a phase (8 consecutive
+// rows, same logical chunk) must fall into 8 different 16-byte bank groups.
+// dk 16 tiles (32-byte rows, 2 chunks): chunk ^= bit 2 of the row
+YMT3_HD uint32_t tc_row_off(int r, int c) { return (uint32_t)(r * 32 + ((c ^ ((r >> 2) & 1)) << 4)); }
+// dk 128 tiles (256-byte rows, 16 chunks): low 3 bits of the chunk ^= row & 7
+YMT3_HD uint32_t xw_off(int r, int c) { return (uint32_t)(r * 256 + ((c ^ (r & 7)) << 4)); }
+
 // ---- tile width of the tcgen05 GEMM (host) --------------------------------------------------------------------------
 // The mainloop is bound by the L2 -> shared-memory fill: a 128 x BN tile moves (128 + BN) * K * 2 bytes for 128 * BN
 // outputs, and every SM walks ceil(tiles / sms) tiles, so BN in {256, 128, 64, 32} is the argmin of

@@ -1,5 +1,5 @@
 #!/bin/bash
-# End-of-session evidence run on one B200 (no profiler): tests, smoke, every bench workload, reference arm, PDL A/B.
+# End-of-session evidence run on one B200 (no profiler): tests, smoke, cross-attention stress, every bench workload, reference arm.
 # usage (GPU box): bash tools/final_round_run.sh   (writes gpurun_out/final_*.{txt,json})
 O=gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > $O/final_pytest_gpu.txt

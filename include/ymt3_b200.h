@@ -186,6 +186,18 @@ YMT3_API int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* dec, const void* enc_hs_
 YMT3_API int ymt3_t5dec_generate_latent(ymt3_t5dec_t* dec, const void* latents_dev, int64_t B, int64_t T_enc, int32_t C,
                                         const int32_t* prefix_ids_dev, int32_t P, int32_t max_len, int32_t stop_at_eos,
                                         int32_t early_stop_interval, int32_t* tokens_out_dev, void* stream);
+/* Teacher-forced scoring.  Replaces upstream model/ymt3.py YourMT3.forward(x, target_tokens) on the decoder side
+ * (decoder(inputs_embeds = embed(shift_right(labels)), encoder_hidden_states) -> lm_head logits; HF
+ * modeling_t5.py:637-792 with a causal mask, evaluated here incrementally over the KV cache with the SAME kernels and
+ * CUDA graph as generation).  forced_ids_dev (N, L) int32: the decoder inputs are [start, forced[:, 0..L-2]]; step t
+ * predicts forced[:, t].  argmax_out_dev (N, L) int32 (optional): the model's greedy choice at every step;
+ * logit_steps_host (n_logit_steps HOST ints in [0, L)) + logits_out_dev (n_logit_steps, N, vocab) fp32 (optional):
+ * the logits of the selected steps.  C == 0: enc_dev is (N = B, T_enc, d_model) hidden states; C > 0: enc_dev is
+ * the latent array (B, T_enc, C, zdim) of ymt3_t5dec_generate_latent and N = B*C.  L <= cfg.max_length. */
+YMT3_API int ymt3_t5dec_score_forced(ymt3_t5dec_t* dec, const void* enc_dev, int64_t B, int64_t T_enc, int32_t C,
+                                     const int32_t* forced_ids_dev, int32_t L, int32_t* argmax_out_dev,
+                                     const int32_t* logit_steps_host, int32_t n_logit_steps, float* logits_out_dev,
+                                     void* stream);
 /* fp32 logits of the LAST executed step, (N, vocab) (for logit-tolerance tests) */
 YMT3_API int ymt3_t5dec_last_logits(ymt3_t5dec_t* dec, float* logits_out_dev, int64_t N, void* stream);
 
@@ -292,7 +304,9 @@ YMT3_API int ymt3_op_linear_argmax(int32_t dtype, const void* A, int64_t lda, co
 /* Single-query attention over a device-resident KV cache alone (the decode step's dominant kernel; HF
  * modeling_t5.py:269-305 with use_cache): q (N, H*64); cache K/V (N, H, Lcap, 64).  knew/vnew (N, H*64) non-null:
  * self mode - the row is appended at index *step_dev, then keys [0, *step_dev] are attended.  knew == NULL: cross
- * mode over keys [0, fixed_len).  out (N, H*64).  No scaling (T5). */
+ * mode over keys [0, fixed_len).  out (N, H*64).  No scaling (T5).  Contract: *step_dev < Lcap; a launch whose step
+ * counter is at or beyond the cache capacity writes nothing (no append, `out` untouched) instead of running out of
+ * bounds. */
 YMT3_API int ymt3_op_decode_attention(int32_t dtype, const void* q, const void* knew, const void* vnew, void* Kc,
                                       void* Vc, const int32_t* step_dev, int64_t fixed_len, void* out, int64_t N,
                                       int64_t H, int64_t Lcap, void* stream);
@@ -300,6 +314,17 @@ YMT3_API int ymt3_op_decode_attention(int32_t dtype, const void* q, const void* 
  * rows >= T zero, out (N, H*256) bf16 = per head softmax_t(q_h . z_t) z_t;  Tp % 16 == 0, H <= 8. */
 YMT3_API int ymt3_op_cross_attn_absorbed(const void* q, const void* z, void* out, int64_t N, int64_t H, int64_t T,
                                          int64_t Tp, void* stream);
+
+/* Sparse MoE feed-forward alone (upstream model/ff_layer.py MoE [RECALL] = HF modeling_mixtral.py:62-135): out =
+ * residual + sum_k w_k * W2[e_k](act(W1[e_k] x) * W3[e_k] x) with (w, e) = renormalised top-k of the fp32 router softmax.
+ * x / residual (or NULL) / out: (N, D) in `dtype`; gate (E, D) fp32; w13 (E, 2*I, D) in `dtype`, rows interleaved
+ * (2j = w1[j] = the activated half, 2j+1 = w3[j]); w2 (E, D, I) in `dtype`; act as in ymt3_op_linear.
+ * workspace: ymt3_op_moe_workspace_bytes(...) device bytes, caller-owned.  Fused router + top-k, device-side expert
+ * sort (no host sync), two grouped GEMMs (fp32 FFMA or tcgen05), gather-combine; deterministic. */
+YMT3_API int64_t ymt3_op_moe_workspace_bytes(int64_t N, int32_t D, int32_t I, int32_t E, int32_t topk, int32_t dtype);
+YMT3_API int ymt3_op_moe_ff(int32_t dtype, const void* x, const void* residual, void* out, int64_t N,
+                            const float* gate, const void* w13, const void* w2, int32_t D, int32_t I, int32_t E,
+                            int32_t topk, int32_t act, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -82,11 +82,20 @@ def apply_rope(x: Tensor, rot_dim: int) -> Tensor:
     return torch.cat([xr * cos + rot * sin, xp], dim=-1)
 
 
+ROUTER_TRACE = None   # tests set this to a list: every moe_ff call appends (name, per-token routing gap)
+
+
 def moe_ff(sd, pre: str, x: Tensor, *, num_experts: int, topk: int, act: str) -> Tensor:
     """x: (N, D). Mixtral-style routed gated MLP (modeling_mixtral.py:74-98, 109-116)."""
     logits = x @ sd[pre + "gate.weight"].T
     probs = torch.softmax(logits.float(), dim=-1)
     w, idx = torch.topk(probs, topk, dim=-1)
+    if ROUTER_TRACE is not None and topk < num_experts:
+        # conditioning of each routing decision: logit gap between the last selected and the first rejected expert,
+        # relative to the token's logit scale (a gap at fp32 round-off level means ANY fp32 implementation may route
+        # the token differently - the parity tests pick instances where no decision is that close and assert it)
+        srt = torch.sort(logits.float(), dim=-1, descending=True).values
+        ROUTER_TRACE.append((pre, (srt[:, topk - 1] - srt[:, topk]) / logits.float().abs().amax(-1).clamp_min(1e-30)))
     w = w / w.sum(dim=-1, keepdim=True)
     out = torch.zeros_like(x)
     for e in range(num_experts):

@@ -78,3 +78,25 @@ def test_midi_round_trip_and_metrics():
         assert math.isfinite(n.offset) and n.offset > n.onset
     progs = {(n.program, n.is_drum) for n in back}
     assert progs == {(n.program, n.is_drum) for n in notes}
+
+
+def test_load_checkpoint_file_with_pickled_hparams(tmp_path):
+    """Lightning-style file: non-tensor objects next to the state dict -> clear error by default, loads with
+    trusted=True; upstream-only buffers (rotary tables, num_batches_tracked) are ignored, not 'unexpected'."""
+    import argparse
+    import pytest
+    import torch
+    import yourmt3_b200 as ymt3
+    from yourmt3_b200 import checkpoint as CK
+    cfg = ymt3.get_model_cfg("mt3_t5_small")
+    cfg["encoder"]["t5"]["num_layers"] = cfg["decoder"]["t5"]["num_layers"] = 1
+    m = ymt3.YourMT3(model_cfg=cfg)
+    sd = {"model." + k: v.clone() for k, v in m.state_dict().items()}
+    sd["model.encoder.rotary.inv_freq"] = torch.ones(4)
+    sd["model.pre_encoder.bn.num_batches_tracked"] = torch.tensor(3)
+    p = tmp_path / "lightning.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": argparse.Namespace(lr=1e-3), "epoch": 3}, p)
+    with pytest.raises(RuntimeError, match="trusted=True"):
+        CK.load_checkpoint(m, str(p))
+    missing, unexpected = CK.load_checkpoint(m, str(p), trusted=True)
+    assert missing == [] and unexpected == []

@@ -34,3 +34,19 @@ def test_tie_section_and_eos():
             EC.encode_event("pitch", 70)]
     notes = EC.tokens_to_notes(toks)
     assert len(notes) == 1 and notes[0].pitch == 64 and abs(notes[0].onset - 0.1) < 1e-9 and notes[0].program == 3
+
+
+def test_shift_tokens_are_absolute_from_segment_start():
+    """Hand-written token fixture (NOT produced by notes_to_tokens): MT3 run-length rule.  A shift token carries the
+    absolute 10 ms tick from the segment start; consecutive shifts add up; any other event resets the run, so
+    `shift 50, pitch, shift 120, pitch` puts the second onset at 1.20 s, not at 1.70 s."""
+    sh, pi, ve, tie = (lambda v: EC.encode_event("shift", v)), (lambda v: EC.encode_event("pitch", v)), \
+        (lambda v: EC.encode_event("velocity", v)), EC.encode_event("tie", 0)
+    toks = [tie, sh(50), ve(1), pi(60), sh(120), pi(62), sh(205), sh(3), pi(64), sh(204), ve(0), pi(60), EC.EOS]
+    notes = EC.tokens_to_notes(toks, start_time=10.0)
+    assert [(n.pitch, round(n.onset - 10.0, 2)) for n in notes] == [(60, 0.5), (62, 1.2), (64, 2.08)]
+    assert abs(notes[0].offset - 12.04) < 1e-9                      # note-off of pitch 60 at absolute tick 204
+    # the encoder emits exactly one absolute shift per time change
+    enc = EC.notes_to_tokens([EC.Note(0.5, 60), EC.Note(1.2, 62)])
+    shifts = [EC.decode_event(t)[1] for t in enc if EC.decode_event(t)[0] == "shift"]
+    assert shifts == [50, 120]

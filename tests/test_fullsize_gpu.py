@@ -1,5 +1,6 @@
-"""Size-independent properties of the whole path at BASELINE.json's full architecture and batch sizes (no oracle can
-run there in seconds): every sequence is an independent unit, so its tokens may not depend on WHERE in the batch it
+"""Size-independent properties of the whole path at BASELINE.json's full architecture AND bench-sized batches (oracle
+parity at the full architecture is tests/test_fulldepth_gpu.py; the CPU oracle cannot run hundreds of segments in
+seconds, properties can): every sequence is an independent unit, so its tokens may not depend on WHERE in the batch it
 sits, on how the batch is split, or on what its neighbours are.  That exercises, at full size, the row independence
 of every kernel on the path (implicit-GEMM convs, Perceiver-TF attention, MoE routing / expert sort / grouped GEMMs,
 absorbed cross-attention, KV-cache attention, fused-norm GEMMs, greedy selection) and their determinism."""

@@ -363,3 +363,29 @@ def test_linear_argmax_fused_epilogue(cuda_device, native_lib, dtype, M, V, K):
     ref = torch.argmax(logits[:, :V], dim=-1)
     assert torch.equal(col, ref), (col[:8], ref[:8])
     assert int(col[1]) == 3 and (M <= 2 or int(col[2]) == 0)
+
+
+def test_decode_attention_step_beyond_capacity_writes_nothing(cuda_device, native_lib):
+    """contract of ymt3_op_decode_attention: *step < Lcap.  A counter at / beyond the capacity must not append out
+    of bounds: the launch leaves the caches and `out` untouched (guard in decode_attn_kernel)."""
+    lib, dev = native_lib, cuda_device
+    N, H, Lcap = 37, 6, 16
+    g = torch.Generator().manual_seed(4)
+    q, kn, vn = (torch.randn(N, H * 64, generator=g).to(dev) for _ in range(3))
+    # caches followed by a guard band in the same allocation: an out-of-bounds append would land in the band
+    buf = torch.randn(2, N * H * Lcap * 64 + 4096, generator=g).to(dev)
+    before = buf.clone()
+    out = torch.full((N, H * 64), 7.0, device=dev)
+    for bad in (Lcap, Lcap + 5):
+        step = torch.tensor([bad], dtype=torch.int32, device=dev)
+        _lib.check(lib.ymt3_op_decode_attention(_lib.DTYPE_F32, q.data_ptr(), kn.data_ptr(), vn.data_ptr(), buf[0].data_ptr(),
+                                                buf[1].data_ptr(), step.data_ptr(), 0, out.data_ptr(), N, H, Lcap,
+                                                _lib.current_stream_ptr()), "decode_attention")
+        torch.cuda.synchronize()
+        assert torch.equal(buf, before) and bool((out == 7.0).all())
+    step = torch.tensor([Lcap - 1], dtype=torch.int32, device=dev)       # last legal step still works
+    _lib.check(lib.ymt3_op_decode_attention(_lib.DTYPE_F32, q.data_ptr(), kn.data_ptr(), vn.data_ptr(), buf[0].data_ptr(),
+                                            buf[1].data_ptr(), step.data_ptr(), 0, out.data_ptr(), N, H, Lcap,
+                                            _lib.current_stream_ptr()), "decode_attention")
+    torch.cuda.synchronize()
+    assert not bool((out == 7.0).any()) and torch.equal(buf[:, N * H * Lcap * 64:], before[:, N * H * Lcap * 64:])

@@ -48,7 +48,7 @@ def _worker(rank, world, port, n_seg, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     audio = torch.zeros(n_seg, 1, 64)
     audio[:, 0, 0] = torch.arange(n_seg, dtype=torch.float32)
-    out = transcribe_sharded(_fake_infer, audio, bsz=2, device=torch.device("cpu"), pad_id=0)
+    out = transcribe_sharded(_fake_infer, audio, bsz=2, device=torch.device("cpu"), pad_id=0, token_shape=(3, 5))
     q.put((rank, out.numpy()))
     dist.barrier()
     dist.destroy_process_group()
@@ -80,3 +80,10 @@ def test_single_process_path():
     audio[:, 0, 0] = torch.arange(5, dtype=torch.float32)
     out = transcribe_sharded(_fake_infer, audio, bsz=2, device=torch.device("cpu"))
     assert out.shape == (5, 3, 5) and int(out[4, 0, 0]) == 400
+
+
+def test_empty_shard_without_token_shape_is_an_error():
+    with pytest.raises(ValueError, match="token_shape"):
+        transcribe_sharded(_fake_infer, torch.zeros(0, 1, 64), bsz=2, device=torch.device("cpu"))
+    out = transcribe_sharded(_fake_infer, torch.zeros(0, 1, 64), bsz=2, device=torch.device("cpu"), token_shape=(3, 5))
+    assert out.shape == (0, 3, 5)

@@ -91,6 +91,7 @@ SIGNATURES = {
     "ymt3_t5dec_generate_prefixed": (_I, [_P, _P, _I64, _I64, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "ymt3_t5dec_generate_latent": (_I, [_P, _P, _I64, _I64, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,
                                         _P]),
+    "ymt3_t5dec_score_forced": (_I, [_P, _P, _I64, _I64, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, _P, _P]),
     "ymt3_t5dec_last_logits": (_I, [_P, _P, _I64, _P]),
     "ymt3_res3b_create": (_I, [C.POINTER(Res3bCfg), C.POINTER(Tensor), _I, C.POINTER(_P)]),
     "ymt3_res3b_destroy": (_I, [_P]),
@@ -110,6 +111,9 @@ SIGNATURES = {
     "ymt3_op_linear_argmax": (_I, [C.c_int32, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, C.c_float, _P, _P]),
     "ymt3_op_decode_attention": (_I, [C.c_int32, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _P]),
     "ymt3_op_cross_attn_absorbed": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "ymt3_op_moe_workspace_bytes": (_I64, [_I64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "ymt3_op_moe_ff": (_I, [C.c_int32, _P, _P, _P, _I64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                            _P, _P]),
 }
 
 

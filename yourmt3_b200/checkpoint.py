@@ -14,6 +14,10 @@ import torch
 
 WRAPPER_PREFIXES = ("state_dict.", "model.", "module.", "_orig_mod.", "net.")
 TRAINING_ONLY = ("loss", "criterion", "metric", "ema_", "optimizer", "lr_scheduler")
+# upstream buffers that are recomputed here (never an error when a checkpoint carries them) [RECALL names]:
+# persistent sinusoidal / rotary tables, mel filterbank + window copies under other attribute paths, pitch-shift layer
+IGNORABLE_BUFFERS = ("inv_freq", "pos_emb.pe", "positional_encoding", "cached_cos", "cached_sin", "pshifters",
+                     "spectrogram.mel_stft", "spectrogram.stft", "num_batches_tracked")
 
 
 def strip_prefixes(state: Mapping[str, torch.Tensor], target_keys: Iterable[str],
@@ -51,7 +55,7 @@ def adapt_state_dict(model: torch.nn.Module, checkpoint: Mapping) -> Tuple[Dict[
             if tuple(v.shape) != tuple(own[k].shape):
                 raise ValueError(f"checkpoint tensor {k!r} has shape {tuple(v.shape)}, the model expects {tuple(own[k].shape)}")
             adapted[k] = v.detach().to(own[k].dtype)
-        elif not any(t in k.lower() for t in TRAINING_ONLY):
+        elif not any(t in k.lower() for t in TRAINING_ONLY) and not any(t in k for t in IGNORABLE_BUFFERS):
             unexpected.append(k)
     # tied LM head: the reference stores the embedding once
     if "lm_head.lm_head.weight" in own and "lm_head.lm_head.weight" not in adapted and "embed_tokens.weight" in adapted \
@@ -61,11 +65,26 @@ def adapt_state_dict(model: torch.nn.Module, checkpoint: Mapping) -> Tuple[Dict[
     return adapted, missing, unexpected
 
 
-def load_checkpoint(model: torch.nn.Module, checkpoint, strict: bool = True, map_location="cpu") -> Tuple[List[str], List[str]]:
+def load_checkpoint(model: torch.nn.Module, checkpoint, strict: bool = True, map_location="cpu",
+                    trusted: bool = False) -> Tuple[List[str], List[str]]:
     """Load a reference checkpoint (path or dict) into ``model``; returns (missing, unexpected).  ``strict`` raises
-    if anything is missing or unexpected (after dropping training-only entries)."""
+    if anything is missing or unexpected (after dropping training-only entries and known-ignorable buffers).
+
+    Files are read with ``torch.load(weights_only=True)``.  Lightning ``.ckpt`` files usually also pickle
+    non-tensor objects (hyper-parameters as argparse / AttributeDict, callbacks); that load then fails and this
+    function says so instead of surfacing a bare UnpicklingError.  ``trusted=True`` opts in to a full unpickle -
+    only for files whose origin you trust, unpickling executes code."""
     if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "__fspath__"):
-        checkpoint = torch.load(checkpoint, map_location=map_location, weights_only=True)
+        path = checkpoint
+        try:
+            checkpoint = torch.load(path, map_location=map_location, weights_only=not trusted)
+        except Exception as e:   # pickle.UnpicklingError and friends
+            if trusted:
+                raise
+            raise RuntimeError(
+                f"could not read {path!r} with weights_only=True ({type(e).__name__}: {str(e)[:200]}). Lightning "
+                "checkpoints often carry pickled hyper-parameters / callbacks; pass trusted=True to unpickle a file "
+                "you trust, or re-save it as {'state_dict': ...} with tensors only.") from e
     adapted, missing, unexpected = adapt_state_dict(model, checkpoint)
     if strict and (missing or unexpected):
         raise KeyError(f"checkpoint does not match the model: missing {missing[:8]}{'...' if len(missing) > 8 else ''}, "

@@ -119,7 +119,7 @@ template <typename T, int W>
 __global__ void __launch_bounds__(W > 4 ? 32 * W : 128, sizeof(T) == 2 ? (W > 4 ? 3 : 6) : (W > 4 ? 2 : 4))
 decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ knew, const T* __restrict__ vnew,
                    int64_t new_ld, T* __restrict__ Kc, T* __restrict__ Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss,
-                   const int* __restrict__ step, int fixed_len, int cap, float scale, T* __restrict__ out,
+                   const int* __restrict__ step, int fixed_len, int cap, int rows_cap, float scale, T* __restrict__ out,
                    int64_t out_ld, int H, int64_t total) {
   constexpr int DK = 64, NG = 4, U = 4;
   pdl_launch_dependents();
@@ -149,6 +149,9 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
   typename Slice8<T>::Raw knraw, vnraw;
   if (knew) {
     s_raw = *step;
+    // contract (include/ymt3_b200.h): *step < Lcap.  A step counter at or beyond the cache capacity would append out
+    // of bounds; every warp of the launch sees the same *step, so the whole grid leaves uniformly (out is untouched)
+    if (s_raw >= rows_cap) return;
     knraw = Slice8<T>::load_raw(knew + n * new_ld + h * DK + 8 * sub);
     vnraw = Slice8<T>::load_raw(vnew + n * new_ld + h * DK + 8 * sub);
   }
@@ -349,7 +352,7 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
 #define YMT3_LAUNCH_DECODE_ATTN(TT, WW)                                                                                \
   YMT3_CUDA_CHECK(ymt3_launch_pdl(decode_attn_kernel<TT, WW>, dim3((unsigned)ymt3_div_up(total, (WW > 4 ? WW : 4) / WW)), \
                                   dim3(32 * (WW > 4 ? WW : 4)), 0, stream, (const TT*)q, q_ld, (const TT*)knew,         \
-                                  (const TT*)vnew, new_ld, (TT*)Kc, (TT*)Vc, c_sn, c_sh, c_ss, step, fixed_len, cap, scale,     \
+                                  (const TT*)vnew, new_ld, (TT*)Kc, (TT*)Vc, c_sn, c_sh, c_ss, step, fixed_len, cap, max_len, scale, \
                                   (TT*)out, out_ld, H, total))
 #define YMT3_DISPATCH_DECODE_ATTN(TT)                                                                                  \
   switch (w) {                                                                                                         \
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(1024)
 select_advance_kernel(unsigned long long* __restrict__ keys, int N, int* __restrict__ step, int* __restrict__ cur_tok,
                       int* __restrict__ finished, int* __restrict__ tokens_out, int max_len, int eos_id, int pad_id,
                       int stop_at_eos, int* __restrict__ unfinished_count, const int* __restrict__ forced,
-                      int n_forced) {
+                      int n_forced, int* __restrict__ score_out) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ int s_unfinished;
@@ -392,6 +395,8 @@ select_advance_kernel(unsigned long long* __restrict__ keys, int N, int* __restr
     keys[n] = 0ull;
     if (s < n_forced) {   // task prefix: teacher-forced input, nothing emitted, EOS not tested
       cur_tok[n] = forced[(int64_t)n * n_forced + s];
+      // teacher-forced scoring (ymt3_t5dec_score_forced): record what the model WOULD have emitted at this step
+      if (score_out) score_out[(int64_t)n * n_forced + s] = key ? (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull)) : pad_id;
       ++mine;
       continue;
     }
@@ -418,10 +423,10 @@ select_advance_kernel(unsigned long long* __restrict__ keys, int N, int* __restr
 
 int select_advance(unsigned long long* keys, int N, int* step, int* cur_tok, int* finished, int* tokens_out,
                    int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count, const int* forced,
-                   int n_forced, cudaStream_t stream) {
+                   int n_forced, cudaStream_t stream, int* score_out) {
   if (N <= 0) return YMT3_OK;
   YMT3_CUDA_CHECK(ymt3_launch_pdl(select_advance_kernel, dim3(1), dim3(1024), 0, stream, keys, N, step, cur_tok, finished,
-                                  tokens_out, max_len, eos_id, pad_id, stop_at_eos, unfinished_count, forced, n_forced));
+                                  tokens_out, max_len, eos_id, pad_id, stop_at_eos, unfinished_count, forced, n_forced, score_out));
   return YMT3_OK;
 }
 

@@ -17,10 +17,10 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
 
 // The vocab-projection GEMM leaves one packed arg-max key per row (GemmParams::argmax_out, ops.cuh); this single-block
 // launch turns the keys into tokens (finished mask, EOS, forced (N, n_forced) task prefix or null), zeroes them and
-// advances *step.
+// advances *step.  score_out (optional, (N, n_forced)): the arg-max of every FORCED step (teacher-forced scoring).
 int select_advance(unsigned long long* keys, int N, int* step, int* cur_tok, int* finished, int* tokens_out,
                    int max_len, int eos_id, int pad_id, int stop_at_eos, int* unfinished_count, const int* forced,
-                   int n_forced, cudaStream_t stream);
+                   int n_forced, cudaStream_t stream, int* score_out = nullptr);
 // Absorbed cross-attention (cross_absorbed.cu): q (N, H*zdim) bf16 latent-space queries, z (N, Tp, zdim) bf16 latents
 // (rows >= T zero), out (N, H*zdim) bf16 = softmax_t(q_h . z_t) z_t per head.  zdim must be 256, H <= 8, Tp % 16 == 0.
 int cross_attn_absorbed(const void* q, int64_t q_ld, const void* z, void* out, int64_t out_ld, int64_t N, int H, int T,

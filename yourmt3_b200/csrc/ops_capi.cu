@@ -1,6 +1,7 @@
 // Per-op C-ABI entry points (include/ymt3_b200.h, "Per-op entry points").
 #include "ops.cuh"
 #include "decode.cuh"
+#include "moe.cuh"
 #include "../../include/ymt3_b200.h"
 
 using namespace ymt3;
@@ -86,4 +87,21 @@ extern "C" int ymt3_op_linear_argmax(int32_t dtype, const void* A, int64_t lda, 
   p.argmax_out = reinterpret_cast<unsigned long long*>(keys); p.argmax_n = (int)V;
   if (dtype == YMT3_F32) return gemm_f32(p, (cudaStream_t)stream);
   return gemm_bf16_tc(p, YMT3_F32, (cudaStream_t)stream);
+}
+
+extern "C" int64_t ymt3_op_moe_workspace_bytes(int64_t N, int32_t D, int32_t I, int32_t E, int32_t topk, int32_t dtype) {
+  if (N <= 0 || D <= 0 || I <= 0 || E <= 0 || topk <= 0) return 0;
+  return (int64_t)moe_workspace_bytes(N, D, I, E, topk, dtype);
+}
+
+extern "C" int ymt3_op_moe_ff(int32_t dtype, const void* x, const void* residual, void* out, int64_t N,
+                              const float* gate, const void* w13, const void* w2, int32_t D, int32_t I, int32_t E,
+                              int32_t topk, int32_t act, void* workspace, void* stream) {
+  YMT3_REQUIRE(dtype == YMT3_F32 || dtype == YMT3_BF16, "op_moe_ff: bad dtype %d", dtype);
+  YMT3_REQUIRE(N >= 0 && D > 0 && I > 0, "op_moe_ff: bad shape");
+  if (N == 0) return YMT3_OK;
+  YMT3_REQUIRE(x && out && gate && w13 && w2 && workspace, "op_moe_ff: null argument");
+  MoEWeights w;
+  w.gate = gate; w.w13 = w13; w.w2 = w2; w.D = D; w.I = I; w.E = E; w.topk = topk; w.act = act;
+  return moe_forward(dtype, x, residual, out, N, w, workspace, (cudaStream_t)stream);
 }

@@ -207,8 +207,10 @@ struct ymt3_t5dec {
   // cached CUDA graph of one decode step
   cudaGraphExec_t graph = nullptr;
   int64_t graph_N = -1, graph_T = -1, graph_L = -1;
-  int graph_stop = -1, graph_prefix = -1;
-  int32_t* graph_tokens = nullptr;
+  int graph_stop = -1, graph_prefix = -1, graph_score = -1;
+  int32_t* tok_buf = nullptr;   // (cap_N, cap_L) tokens of the running call: the graph writes here (stable pointer), one
+                                // D2D copy hands them to the caller's buffer, so a fresh output tensor per call does
+                                // not re-instantiate the graph
   int* d_forced = nullptr;   // (cap_N, cap_P) task-prefix tokens
   int64_t cap_P = 0;
   // absorbed cross-attention (bf16, cross_absorbed.cu): present when the tensor table carried *.q_absorbed.weight
@@ -333,6 +335,9 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, int latent, cu
     d->graph = nullptr;
     d->graph_N = -1;
   }
+  // capacities only ever grow (a ragged last batch or alternating K/V <-> latent calls must not shrink them and
+  // force a re-allocation + graph re-capture on the next full batch): take the maxima BEFORE resetting the caps
+  const int64_t cN = N > d->cap_N ? N : d->cap_N, cT = T > d->cap_T ? T : d->cap_T, cL = Lmax > d->cap_L ? Lmax : d->cap_L;
   d->ws.release();
   d->d_forced = nullptr;
   d->cap_P = 0;
@@ -341,7 +346,6 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, int latent, cu
   const ymt3_t5_cfg_t& c = d->c;
   const int D = c.d_model, inner = c.num_heads * c.d_kv, F = c.d_ff;
   const size_t es = dtype_size(c.precision);
-  const int64_t cN = N > d->cap_N ? N : d->cap_N, cT = T > d->cap_T ? T : d->cap_T, cL = Lmax > d->cap_L ? Lmax : d->cap_L;
   d->x = d->ws.alloc(cN * D * es);
   d->h = d->ws.alloc(cN * D * es);
   d->qkv = d->ws.alloc(cN * 3 * inner * es);
@@ -363,8 +367,9 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, int latent, cu
   d->d_cur = (int*)d->ws.alloc(cN * 4);
   d->d_fin = (int*)d->ws.alloc(cN * 4);
   d->d_amax = (unsigned long long*)d->ws.alloc(cN * 8);
+  d->tok_buf = (int32_t*)d->ws.alloc((size_t)cN * cL * 4);
   for (int i = 0; i < 3; ++i) d->ss[i] = d->fuse_norm ? (float*)d->ws.alloc((size_t)cN * (D / 32) * 4) : nullptr;
-  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->d_amax && d->kv_tmp &&
+  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->d_amax && d->tok_buf && d->kv_tmp &&
             (!d->fuse_norm || (d->ss[0] && d->ss[1] && d->ss[2]));
   d->selfK.assign(c.num_layers, nullptr);
   d->selfV.assign(c.num_layers, nullptr);
@@ -387,7 +392,7 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, int latent, cu
 
 // all kernels of ONE decode step; every step-dependent value is read from device memory
 int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int32_t* tokens_out, int n_prefix,
-             int latent, cudaStream_t s) {
+             int latent, cudaStream_t s, int32_t* score_out = nullptr) {
   const ymt3_t5_cfg_t& c = d->c;
   const int D = c.d_model, H = c.num_heads, dk = c.d_kv, inner = H * dk, F = c.d_ff, dt = c.precision;
   const size_t es = dtype_size(dt);
@@ -465,7 +470,7 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
     if ((rc = linear_fwd(dt, d->h, D, d->lm_head, d->logits, d->Vp, (int)N, 0, 0, nullptr, 0, sc, YMT3_F32, s, nf))) return rc;
   }
   return select_advance(d->d_amax, (int)N, d->d_step, d->d_cur, d->d_fin, tokens_out, Lmax, c.eos_id, c.pad_id,
-                        stop_at_eos, d->d_unfinished, n_prefix ? d->d_forced : nullptr, n_prefix, s);
+                        stop_at_eos, d->d_unfinished, n_prefix ? d->d_forced : nullptr, n_prefix, s, score_out);
 }
 
 }  // namespace
@@ -477,9 +482,15 @@ extern "C" int ymt3_t5dec_generate(ymt3_t5dec_t* d, const void* enc_hs, int64_t 
 }
 
 namespace {
+struct ScoreOpts {
+  int32_t* argmax_out = nullptr;        // (N, P): the model's arg-max at every teacher-forced step
+  const int32_t* logit_steps = nullptr; // HOST array of step indices whose logits are copied out
+  int n_logit_steps = 0;
+  float* logits_out = nullptr;          // (n_logit_steps, N, V) fp32 device
+};
 int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int latent_channels,
                   const int32_t* prefix_ids, int32_t P, int32_t max_len, int32_t stop_at_eos,
-                  int32_t early_stop_interval, int32_t* tokens_out, void* stream);
+                  int32_t early_stop_interval, int32_t* tokens_out, void* stream, const ScoreOpts* score = nullptr);
 }
 
 extern "C" int ymt3_t5dec_generate_prefixed(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T,
@@ -502,14 +513,15 @@ namespace {
 // (N / C, T, C, zdim) and the cross-attention runs in its absorbed form.
 int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int latent_channels,
                   const int32_t* prefix_ids, int32_t P, int32_t max_len, int32_t stop_at_eos,
-                  int32_t early_stop_interval, int32_t* tokens_out, void* stream) {
+                  int32_t early_stop_interval, int32_t* tokens_out, void* stream, const ScoreOpts* score) {
   const int latent = latent_channels > 0;
-  YMT3_REQUIRE(d && tokens_out, "t5dec_generate: null argument");
+  const bool scoring = score != nullptr;   // teacher-forced scoring: every step forced, nothing generated (max_len 0)
+  YMT3_REQUIRE(d && (tokens_out || scoring), "t5dec_generate: null argument");
   if (N <= 0) return YMT3_OK;
   YMT3_REQUIRE(enc_hs && T > 0, "t5dec_generate: bad encoder states");
   YMT3_REQUIRE(P >= 0 && (P == 0 || prefix_ids), "t5dec_generate: bad task prefix");
-  YMT3_REQUIRE(max_len > 0 && max_len + P <= d->c.max_length, "t5dec_generate: max_len %d + prefix %d outside (0, %d]",
-               max_len, P, d->c.max_length);
+  YMT3_REQUIRE((max_len > 0 || (scoring && P > 0)) && max_len + P <= d->c.max_length,
+               "t5dec_generate: max_len %d + prefix %d outside (0, %d]", max_len, P, d->c.max_length);
   YMT3_REQUIRE(!d->pos || max_len + P <= d->n_pos, "t5dec_generate: position table too short");
   const ymt3_t5_cfg_t& c = d->c;
   const int D = c.d_model, inner = c.num_heads * c.d_kv, dt = c.precision;
@@ -539,7 +551,12 @@ int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int
   if ((rc = fill_i32(d->d_cur, c.start_id, N, s))) return rc;
   if ((rc = fill_i32(d->d_fin, 0, N, s))) return rc;
   YMT3_CUDA_CHECK(cudaMemsetAsync(d->d_amax, 0, (size_t)N * 8, s));
-  if ((rc = fill_i32(tokens_out, c.pad_id, N * max_len, s))) return rc;
+  if ((rc = fill_i32(d->tok_buf, c.pad_id, N * max_len, s))) return rc;
+  int32_t* score_buf = nullptr;
+  if (scoring && score->argmax_out) {
+    // (N, P) arg-max record of the forced steps shares the token buffer's tail (cap_N * cap_L >= N * (P + max_len))
+    score_buf = d->tok_buf + N * max_len;
+  }
   if (latent) {
     // the only per-call encoder-side work: latents regrouped per sequence (channel-major), time padded to 16
     const int64_t Tp = (T + 15) / 16 * 16;
@@ -560,7 +577,7 @@ int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int
   // one decode step captured into a CUDA graph (all step-dependent scalars live on the device)
   const bool use_graph = getenv("YMT3_NO_GRAPH") == nullptr && !caller_capturing;
   if (use_graph && (!d->graph || d->graph_N != N || d->graph_T != T || d->graph_L != max_len ||
-                    d->graph_tokens != tokens_out || d->graph_stop != stop_at_eos || d->graph_prefix != P ||
+                    d->graph_score != (score_buf != nullptr) || d->graph_stop != stop_at_eos || d->graph_prefix != P ||
                     d->graph_latent != latent)) {
     if (d->graph) {
       cudaGraphExecDestroy(d->graph);
@@ -568,7 +585,7 @@ int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int
     }
     cudaGraph_t g = nullptr;
     YMT3_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, P, latent, s);
+    rc = dec_step(d, N, T, max_len, stop_at_eos, d->tok_buf, P, latent, s, score_buf);
     cudaError_t ce = cudaStreamEndCapture(s, &g);
     if (rc) {
       if (g) cudaGraphDestroy(g);
@@ -579,7 +596,7 @@ int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int
     cudaGraphDestroy(g);
     YMT3_CUDA_CHECK(ce);
     d->graph_N = N; d->graph_T = T; d->graph_L = max_len;
-    d->graph_tokens = tokens_out;
+    d->graph_score = score_buf != nullptr;
     d->graph_stop = stop_at_eos;
     d->graph_prefix = P;
     d->graph_latent = latent;
@@ -587,8 +604,13 @@ int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int
   for (int t = 0; t < max_len + P; ++t) {
     if (use_graph) {
       YMT3_CUDA_CHECK(cudaGraphLaunch(d->graph, s));
-    } else if ((rc = dec_step(d, N, T, max_len, stop_at_eos, tokens_out, P, latent, s))) {
+    } else if ((rc = dec_step(d, N, T, max_len, stop_at_eos, d->tok_buf, P, latent, s, score_buf))) {
       return rc;
+    }
+    for (int k = 0; scoring && k < score->n_logit_steps; ++k) {
+      if (score->logit_steps[k] != t) continue;
+      YMT3_CUDA_CHECK(cudaMemcpy2DAsync(score->logits_out + (size_t)k * N * c.vocab_size, (size_t)c.vocab_size * 4, d->logits,
+                                        (size_t)d->Vp * 4, (size_t)c.vocab_size * 4, (size_t)N, cudaMemcpyDeviceToDevice, s));
     }
     if (stop_at_eos && early_stop_interval > 0 && (t + 1) % early_stop_interval == 0 && t + 1 < max_len + P) {
       // rows still unfinished after step t were counted into slot (t & 1)
@@ -597,6 +619,10 @@ int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int
       if (*d->h_unfinished == 0) break;
     }
   }
+  if (tokens_out && max_len > 0)
+    YMT3_CUDA_CHECK(cudaMemcpyAsync(tokens_out, d->tok_buf, (size_t)N * max_len * 4, cudaMemcpyDeviceToDevice, s));
+  if (score_buf)
+    YMT3_CUDA_CHECK(cudaMemcpyAsync(score->argmax_out, score_buf, (size_t)N * P * 4, cudaMemcpyDeviceToDevice, s));
   if (!caller_capturing) {
     YMT3_CUDA_CHECK(cudaEventRecord(d->ev_out, s));
     YMT3_CUDA_CHECK(cudaStreamWaitEvent(caller, d->ev_out, 0));
@@ -604,6 +630,22 @@ int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int
   return YMT3_OK;
 }
 }  // namespace
+
+extern "C" int ymt3_t5dec_score_forced(ymt3_t5dec_t* d, const void* enc, int64_t B, int64_t T, int32_t C,
+                                       const int32_t* forced_ids, int32_t L, int32_t* argmax_out,
+                                       const int32_t* logit_steps_host, int32_t n_logit_steps, float* logits_out,
+                                       void* stream) {
+  YMT3_REQUIRE(d && forced_ids && L > 0, "t5dec_score_forced: null argument");
+  YMT3_REQUIRE(C >= 0 && (C == 0 || d->zdim > 0), "t5dec_score_forced: latent mode needs absorbed cross-attention weights");
+  YMT3_REQUIRE(n_logit_steps >= 0 && (n_logit_steps == 0 || (logit_steps_host && logits_out)),
+               "t5dec_score_forced: bad logit capture arguments");
+  for (int k = 0; k < n_logit_steps; ++k)
+    YMT3_REQUIRE(logit_steps_host[k] >= 0 && logit_steps_host[k] < L, "t5dec_score_forced: logit step %d outside [0, %d)",
+                 logit_steps_host[k], L);
+  ScoreOpts so;
+  so.argmax_out = argmax_out; so.logit_steps = logit_steps_host; so.n_logit_steps = n_logit_steps; so.logits_out = logits_out;
+  return generate_impl(d, enc, C > 0 ? B * C : B, T, C, forced_ids, L, 0, 0, 0, nullptr, stream, &so);
+}
 
 extern "C" int ymt3_t5dec_last_logits(ymt3_t5dec_t* d, float* out, int64_t N, void* stream) {
   YMT3_REQUIRE(d && out && N <= d->cap_N, "t5dec_last_logits: bad argument");

@@ -3,8 +3,11 @@ event_codec.py, tokenizer.py, event2note.py, metrics.py [RECALL -- vocabulary la
 
 Vocabulary (596 ids, config.PROVENANCE['vocab_size']): 0 pad, 1 eos, 2 unk, then the event ranges in order
 ``shift`` (206 steps of 10 ms), ``pitch`` (128), ``velocity`` (2: 0 = off, 1 = on), ``tie`` (1),
-``program`` (128), ``drum`` (128).  Decoding is the MT3 state machine: shifts accumulate time within the
-segment, ``program`` / ``velocity`` set the state, ``pitch`` emits a note-on (velocity 1) or note-off
+``program`` (128), ``drum`` (128).  Decoding is the MT3 state machine: a ``shift`` token is the ABSOLUTE tick offset
+from the segment start (206 values x 10 ms cover one 2.048 s segment; the MT3 run-length rule: consecutive shift
+tokens add up, any non-shift event resets the running count, so the time after a run of shifts is the run's sum
+measured from the segment start -- never cumulative across events), ``program`` / ``velocity`` set the state,
+``pitch`` emits a note-on (velocity 1) or note-off
 (velocity 0), ``drum`` emits a drum onset; tokens before ``tie`` declare notes tied over from the previous
 segment.  CPU-side, not performance relevant; used for the note-level agreement check of the bf16 path."""
 from __future__ import annotations
@@ -61,10 +64,15 @@ def notes_to_tokens(notes: Sequence[Note], max_len: int = 1024) -> List[int]:
     out, cur, prog, vel = [encode_event("tie", 0)], 0, None, None
     for t, on, n in ev:
         step = int(round(t * STEPS_PER_SECOND))
-        while step > cur:
-            d = min(205, step - cur)
-            out.append(encode_event("shift", d))
-            cur += d
+        if step > cur:
+            # one ABSOLUTE shift per time change (run-length rule: a target beyond 205 ticks is a run of shift
+            # tokens that sums to the absolute tick)
+            rest = step
+            while rest > 0:
+                d = min(205, rest)
+                out.append(encode_event("shift", d))
+                rest -= d
+            cur = step
         if n.is_drum:
             out.append(encode_event("drum", n.pitch))
             continue
@@ -83,7 +91,7 @@ def tokens_to_notes(tokens: Iterable[int], start_time: float = 0.0) -> List[Note
     """One segment's token ids -> notes with onsets in seconds (offsets filled when a note-off follows)."""
     notes: List[Note] = []
     active = {}
-    cur, prog, vel, seen_tie = 0, 0, 1, False
+    cur, run, prog, vel, seen_tie = 0, 0, 0, 1, False
     for tok in tokens:
         tok = int(tok)
         if tok == EOS:
@@ -92,8 +100,11 @@ def tokens_to_notes(tokens: Iterable[int], start_time: float = 0.0) -> List[Note
             continue
         kind, v = decode_event(tok)
         if kind == "shift":
-            cur += v
-        elif kind == "program":
+            run += v            # shifts of one run add up ...
+            cur = run           # ... to the absolute tick from the segment start
+            continue
+        run = 0                 # any non-shift event ends the run (MT3 decode_events rule)
+        if kind == "program":
             prog = v
         elif kind == "velocity":
             vel = v

@@ -128,6 +128,36 @@ class DecoderRuntime(_NativeOwner):
                        "t5dec_generate_latent")
         return tokens
 
+    def score_forced(self, enc: torch.Tensor, forced_ids: torch.Tensor, logit_steps=()):
+        """Teacher-forced scoring (``ymt3_t5dec_score_forced``): decoder inputs [start, forced[:, :-1]].
+
+        enc: (N, T_enc, d_model) hidden states, or (B, T_enc, C, zdim) latents on a runtime built with ``cross_proj``
+        (absorbed cross-attention; N = B*C).  forced_ids: (N, L).  Returns (argmax (N, L) int32, logits
+        (len(logit_steps), N, vocab) f32): the greedy choice at every step and the logits of the selected steps."""
+        if not enc.is_cuda:
+            raise RuntimeError("scoring runs on CUDA only (no CPU fallback)")
+        latent = enc.dim() == 4
+        if latent and (self._cross_proj is None or self.precision != _lib.DTYPE_BF16):
+            raise RuntimeError("latent scoring needs a bf16 runtime built with cross_proj")
+        enc = enc.to(_lib.torch_dtype(self.precision)).contiguous()
+        if latent:
+            B, T, Cn, _ = enc.shape
+            N = B * Cn
+        else:
+            (B, T, _), Cn = enc.shape, 0
+            N = B
+        forced = forced_ids.to(enc.device, torch.int32).reshape(N, -1).contiguous()
+        L = forced.shape[1]
+        steps = (C.c_int32 * max(1, len(logit_steps)))(*[int(v) for v in logit_steps])
+        argmax = torch.empty((N, L), dtype=torch.int32, device=enc.device)
+        logits = torch.empty((len(logit_steps), N, self.vocab_size), dtype=torch.float32, device=enc.device)
+        with torch.cuda.device(enc.device):
+            _lib.check(_lib.load().ymt3_t5dec_score_forced(self.native(), enc.data_ptr(), B, T, Cn, forced.data_ptr(), L,
+                                                           argmax.data_ptr(), steps, len(logit_steps),
+                                                           logits.data_ptr() if len(logit_steps) else None,
+                                                           _lib.current_stream_ptr()), "t5dec_score_forced")
+        return argmax, logits
+
     def last_logits(self, N: int, device) -> torch.Tensor:
         out = torch.empty((N, self.vocab_size), dtype=torch.float32, device=device)
         _lib.check(_lib.load().ymt3_t5dec_last_logits(self.native(), out.data_ptr(), N, _lib.current_stream_ptr()),

@@ -127,6 +127,36 @@ class YourMT3(nn.Module):
                                       cross_proj=self.pre_decoder.proj)
 
     @torch.no_grad()
+    def score(self, x: torch.Tensor, target_tokens: torch.Tensor, logit_steps=()):
+        """Teacher-forced decoder pass (the decoder side of the reference's ``forward(x, target_tokens)``): x (B, 1, L)
+        audio, target_tokens (B, Ltok) / (B, C, Ltok).  Returns (argmax like target_tokens, logits
+        (len(logit_steps), B[*C], vocab) f32) computed by the SAME kernels / CUDA graph as ``inference`` (absorbed
+        cross-attention included when that is the path ``inference`` takes)."""
+        from .t5mod_helper import DecoderRuntime
+        L = int(target_tokens.shape[-1])
+        if self._absorbed():
+            enc = self.encoder(inputs_embeds=self.pre_encoder(self.spectrogram(x)))["last_hidden_state"]
+            B, T, K, Dl = enc.shape
+            zin = self.pre_decoder.proj.in_features
+            enc = enc.reshape(B, T, K * Dl // zin, zin)
+            proj = self.pre_decoder.proj
+        else:
+            enc = self.encode(x)
+            if enc.dim() == 4:
+                enc = enc.reshape(-1, enc.shape[2], enc.shape[3])
+            proj = None
+        rt = getattr(self.decoder, "_runtime_score", None)
+        if rt is None or rt.max_length < L or rt._cross_proj is not proj or rt.precision != self._prec:
+            if rt is not None:
+                rt.free_native()
+            rt = DecoderRuntime(self.decoder, self.embed_tokens, self.lm_head, self._prec, self.vocab_size,
+                                max(L, self.max_token_length), self.tie_word_embeddings, self.eos_id, self.pad_id, self.pad_id,
+                                cross_proj=proj)
+            object.__setattr__(self.decoder, "_runtime_score", rt)
+        argmax, logits = rt.score_forced(enc, target_tokens, logit_steps)
+        return argmax.long().view(target_tokens.shape), logits
+
+    @torch.no_grad()
     def transcribe_waveform(self, wave: torch.Tensor, bsz: int = 256, **kw) -> torch.Tensor:
         """Whole mono 16 kHz waveform (n_samples,) on the model's device -> tokens (n_seg, L) / (n_seg, C, L).
         The frontend consumes the waveform directly (segmentation + tail zero-padding fused into its loads,
@@ -153,7 +183,11 @@ class YourMT3(nn.Module):
         (n_seg, L) / (n_seg, C, L) int32 on every rank."""
         from .sharding import transcribe_sharded
         dev = next(self.parameters()).device
-        return transcribe_sharded(lambda x: self.inference(x, None, **kw), audio_segments, bsz, dev, self.pad_id)
+        L = kw.get("max_token_length") or self.max_token_length
+        nch = getattr(self.decoder, "num_channels", 1)
+        shape = (nch, L) if self.decoder_type == "multi-t5" else (L,)
+        return transcribe_sharded(lambda x: self.inference(x, None, **kw), audio_segments, bsz, dev, self.pad_id,
+                                  token_shape=shape)
 
     @torch.no_grad()
     def inference_file(self, bsz: int, audio_segments: torch.Tensor, note_token_array=None, task_token_array=None,

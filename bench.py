@@ -208,8 +208,8 @@ def run_reference(args):
     val = wl.ref_batch * SEG_SECONDS * args.steps / dt * (wl.reference_scale() if hasattr(wl, "reference_scale") else 1.0)
     line = {"metric": "audio_seconds_per_wall_second", "value": val, "unit": "audio-s/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": wl.config(),
+            "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": wl.config(),
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": torch.get_num_threads(),
                              "kind": "port", "sample": wl.reference_sample()},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -278,7 +278,7 @@ def run_native(args):
 
     if rank == 0:
         peaks = measured_peaks()
-        units = wl.batch * world
+        units = wl.units(world) if hasattr(wl, "units") else wl.batch * world
         value = units * SEG_SECONDS * args.steps / (total_ms * 1e-3)
         if hasattr(wl, "rooflines"):
             roofs = wl.rooflines(peaks)     # model workloads: dominant decode kernel + the log-mel frontend kernel
@@ -289,19 +289,29 @@ def run_native(args):
             roofs = {"roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                   "frac": achieved / peaks["hbm_gbs"], "traffic": getattr(wl, "ncu_traffic_bytes", None),
                                   "peak_source": peaks["source"], "kernel": "ymt3_logmel_kernel", "kernel_ms": kern_ms}}
+            try:
+                from yourmt3_b200.bench_workloads import frontend_compute_bound
+                roofs["roofline"]["compute"] = frontend_compute_bound(wl.batch * 256, kern_ms)
+            except ImportError:
+                pass
         line = {
             "metric": "audio_seconds_per_wall_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
+            "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None, "dtype": wl.dtype,
             "data": "synthetic", "config": wl.config(),
             **roofs,
-            "e2e": {"value": wl.e2e_batch * world * SEG_SECONDS * n_e2e / e_dt, "unit": "audio-s/s",
+            "e2e": {"value": (units if getattr(wl, "scaling", "weak") == "strong" else wl.e2e_batch * world)
+                    * SEG_SECONDS * n_e2e / e_dt, "unit": "audio-s/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": wl.launches_per_step * args.steps,
+            "gpu_launches_note": "estimated from the structure of the step (kernels per decode step x steps + encoder), "
+                                 "not counted by a profiler",
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
+        if world == 1 and not args.no_gpu_eager_baseline and hasattr(wl, "gpu_eager_baseline"):
+            line["gpu_eager_baseline"] = wl.gpu_eager_baseline(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -316,6 +326,8 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--batch", type=int, default=None, help="segments per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true",
+                    help="skip the eager-torch-on-the-same-GPU bar (model workloads, N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -75,7 +75,7 @@ def apply_rope(x: Tensor, rot_dim: int) -> Tensor:
     """x: (..., S, d_head); rotate-half RoPE on the first rot_dim dims, position = index along S."""
     if rot_dim <= 0:
         return x
-    cos, sin = rope_cos_sin(x.shape[-2], rot_dim)
+    cos, sin = (t.to(x.device) for t in rope_cos_sin(x.shape[-2], rot_dim))
     xr, xp = x[..., :rot_dim], x[..., rot_dim:]
     x1, x2 = xr[..., : rot_dim // 2], xr[..., rot_dim // 2:]
     rot = torch.cat([-x2, x1], dim=-1)
@@ -189,7 +189,9 @@ def pre_decoder(sd, h: Tensor, kind: str, num_channels: int = 13, prefix: str = 
 
 def encode(sd, feats: Tensor, model_cfg: Dict) -> Tensor:
     """spectrogram features (B, T, F) -> decoder-ready encoder states."""
-    sd = {k: v.detach().cpu().float() for k, v in sd.items()}
+    from . import pipeline as _P
+    sd = {k: v.detach().to(_P.DEVICE).float() for k, v in sd.items()}
+    feats = feats.to(_P.DEVICE)
     cfg = model_cfg["encoder"]["perceiver-tf"]
     x = pre_encoder_res3b(sd, feats)
     h = perceiver_tf_encoder(sd, x, cfg)

@@ -12,8 +12,12 @@ from . import logmel as OL
 from . import t5 as OT
 
 
+DEVICE = "cpu"   # the oracle is a CPU checker; tools/ref_gpu_bar.py sets "cuda" to time the SAME eager modules on the
+                 # GPU (the "bar to beat" of SURVEY.md 2c) - never used by the product path
+
+
 def _sub(sd: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
-    return {k[len(prefix):]: v.detach().cpu().float() for k, v in sd.items() if k.startswith(prefix)}
+    return {k[len(prefix):]: v.detach().to(DEVICE).float() for k, v in sd.items() if k.startswith(prefix)}
 
 
 def frontend(sd, audio: np.ndarray, audio_cfg: Dict) -> torch.Tensor:
@@ -36,17 +40,18 @@ def frontend(sd, audio: np.ndarray, audio_cfg: Dict) -> torch.Tensor:
 
 def t5_encode(sd, feats: torch.Tensor, model_cfg: Dict, n_pos: int) -> torch.Tensor:
     ec = model_cfg["encoder"]["t5"]
-    pos = OT.sinusoidal_positions(n_pos, ec["d_model"]) if ec.get("position_encoding_type") == "sinusoidal" else None
-    return OT.t5_encoder(_sub(sd, "encoder."), feats, n_layers=ec["num_layers"], n_heads=ec["num_heads"],
+    pos = OT.sinusoidal_positions(n_pos, ec["d_model"]).to(DEVICE) if ec.get("position_encoding_type") == "sinusoidal" else None
+    return OT.t5_encoder(_sub(sd, "encoder."), feats.to(DEVICE), n_layers=ec["num_layers"], n_heads=ec["num_heads"],
                          eps=ec.get("layer_norm_epsilon", 1e-6), pos=pos)
 
 
 def t5_generate(sd, enc_hs: torch.Tensor, model_cfg: Dict, n_pos: int, max_length: int, stop_at_eos=True,
                 eos_id=1, pad_id=0, return_margins=False, prefix_ids=None):
     dc = model_cfg["decoder"][model_cfg["decoder_type"]]
-    pos = OT.sinusoidal_positions(n_pos, dc["d_model"]) if dc.get("position_encoding_type") == "sinusoidal" else None
-    embed = sd["embed_tokens.weight"].detach().cpu().float()
-    lm = sd["lm_head.lm_head.weight"].detach().cpu().float()
+    pos = OT.sinusoidal_positions(n_pos, dc["d_model"]).to(DEVICE) if dc.get("position_encoding_type") == "sinusoidal" else None
+    embed = sd["embed_tokens.weight"].detach().to(DEVICE).float()
+    lm = sd["lm_head.lm_head.weight"].detach().to(DEVICE).float()
+    enc_hs = enc_hs.to(DEVICE)
     if enc_hs.dim() == 4:
         B, C, T, D = enc_hs.shape
         enc_hs = enc_hs.reshape(B * C, T, D)
@@ -64,12 +69,20 @@ def transcribe_t5(sd, audio: np.ndarray, audio_cfg: Dict, model_cfg: Dict, n_pos
         return t5_generate(sd, enc, model_cfg, n_pos, max_length, **kw)
 
 
+def transcribe_from_feats(sd, feats: torch.Tensor, model_cfg, n_pos, max_length, **kw):
+    """(B, T, F) log-(mel)spectrogram features -> tokens (encoder family dispatch)."""
+    with torch.no_grad():
+        if model_cfg["encoder_type"] == "t5":
+            enc = t5_encode(sd, feats, model_cfg, n_pos)
+        else:
+            from . import perceiver_tf as OPTF
+            enc = OPTF.encode(sd, feats, model_cfg)
+        return t5_generate(sd, enc, model_cfg, n_pos, max_length, **kw)
+
+
 def transcribe(sd, audio, audio_cfg, model_cfg, n_pos, max_length, **kw):
     """Dispatch on the encoder family (T5 | Perceiver-TF)."""
     if model_cfg["encoder_type"] == "t5":
         return transcribe_t5(sd, audio, audio_cfg, model_cfg, n_pos, max_length, **kw)
-    from . import perceiver_tf as OPTF
     with torch.no_grad():
-        feats = frontend(sd, audio, audio_cfg)
-        enc = OPTF.encode(sd, feats, model_cfg)
-        return t5_generate(sd, enc, model_cfg, n_pos, max_length, **kw)
+        return transcribe_from_feats(sd, frontend(sd, audio, audio_cfg), model_cfg, n_pos, max_length, **kw)

@@ -25,6 +25,7 @@ DEFAULT = "yptf_moe_multi"   # the model BASELINE.json quotes the target on
 
 
 class ModelWorkload:
+    scaling = "weak"
     roofline_bound = "hbm"
     dominant_kernel = "decode_attn_kernel"
     # dram__bytes_read + dram__bytes_write of ONE decode_attn_kernel launch at cache length 128 for 3328 x 6 (sequence,
@@ -81,6 +82,10 @@ class ModelWorkload:
     def step_e2e(self):
         outs = self.model.inference_file(self.batch, self.host_in, stop_at_eos=True)
         return outs
+
+    def units(self, world):
+        """segments transcribed per step by the whole job"""
+        return self.batch * world
 
     def e2e_bytes(self):
         return self.batch * SEG_SAMPLES * 4, self.batch * self.channels * self.max_len * 8
@@ -145,6 +150,7 @@ class ModelWorkload:
                  "traffic": self.ncu_traffic_bytes, "peak_source": peaks["source"], "kernel": "ymt3_logmel_kernel",
                  "kernel_ms": f_ms, "algorithmic_bytes_per_launch": self.roofline_units(), "launches_per_step": 1,
                  "note": "compute-bound on the fp32 pipes (2048-point FFT per 128/300 new samples), see DESIGN.md 3.1"}
+        front["compute"] = frontend_compute_bound(self.batch * self.model.feat_length, f_ms)
         return {"roofline": main, "roofline_frontend": front}
 
     def dominant_kernel_ms(self):
@@ -186,42 +192,55 @@ class ModelWorkload:
                 "encoder": m.encoder_type, "decoder": m.decoder_type, "channels": self.channels,
                 "decode_steps": self.max_len, "vocab": m.vocab_size, "weights": "random-init (non-degenerate, seed 0)",
                 "l2_policy": "per-step working set (activations + KV cache) larger than L2",
-                "cross_attention": "absorbed (latent)" if (getattr(self, "model", None) is not None
-                                                           and self.model._absorbed()) else "k/v",
+                "cross_attention": "absorbed (latent)" if (self.precision == "bf16" and m.decoder_type == "multi-t5"
+                                                           and m.absorb_cross_attention) else "k/v",
                 "roofline_kernel_note": "roofline = decode self-attention kernel (dominant); roofline_frontend = log-mel"}
 
-    # ---- reference arm: same architecture through the CPU oracle (HF-pinned torch restatement) ----
+    # ---- reference arm: same architecture on the host cores: torchaudio frontend (the library upstream wraps) +
+    # the HF-pinned torch restatement of the model (oracle/), B = 8 segments ----
+    REF_BATCH = 8
+
     def setup_reference(self):
-        import numpy as np
         import torch
         import yourmt3_b200 as ymt3
         from oracle import pipeline as OP
         self.OP = OP
-        self.ref_batch = 1 if self.preset != "mt3_t5_small" else 2
+        self.ref_batch = self.REF_BATCH
         m = ymt3.YourMT3(audio_cfg=ymt3.get_audio_cfg(**self.audio_over), model_cfg=ymt3.get_model_cfg(self.preset),
                          precision="f32")
         ymt3.init_nondegenerate_(m, seed=0)
         self.ref_model = m
         self.ref_sd = {k: v.detach() for k, v in m.state_dict().items()}
+        self.ref_frontend = reference_frontend(m.audio_cfg)
         g = torch.Generator().manual_seed(1234)
-        self.ref_audio = (torch.randn(self.ref_batch, SEG_SAMPLES, generator=g) * 0.1).numpy().astype(np.float32)
+        self.ref_audio = torch.randn(self.ref_batch, SEG_SAMPLES, generator=g) * 0.1
         # bounded sample: decode fewer steps on the CPU and extrapolate linearly in the step count
         self.ref_steps = min(64, m.max_token_length)
 
     def step_reference(self):
-        """One bounded CPU sample: the full frontend + encoder + ONE decode step, then the same with ref_steps decode
-        steps; the per-step decode cost is their difference and the full-length time is extrapolated linearly in the
-        step count (the CPU attention cost grows with the cache length, so this is an UPPER bound on the CPU speed)."""
-        m = self.ref_model
-        kw = dict(n_pos=m.decoder.pos_table.shape[0], stop_at_eos=False)
-        t0 = time.perf_counter()
-        self.OP.transcribe(self.ref_sd, self.ref_audio, m.audio_cfg, m.model_cfg, max_length=1, **kw)
-        t1 = time.perf_counter()
-        out = self.OP.transcribe(self.ref_sd, self.ref_audio, m.audio_cfg, m.model_cfg, max_length=self.ref_steps, **kw)
-        t2 = time.perf_counter()
-        per_step = max((t2 - t1) - (t1 - t0), 0.0) / max(self.ref_steps - 1, 1)
-        self._ref_spent = getattr(self, "_ref_spent", 0.0) + (t2 - t0)
-        self._ref_full = getattr(self, "_ref_full", 0.0) + (t1 - t0) + per_step * (m.max_token_length - 1)
+        """One bounded CPU sample: frontend (torchaudio) + encoder ONCE, then a 1-step decode and a ref_steps-step
+        decode on the same encoder states; the per-step decode cost is their difference and the full-length time is
+        frontend + encoder + first step + per-step cost x remaining steps (the CPU attention cost grows with the
+        cache length, so this is an UPPER bound on the CPU speed)."""
+        import torch
+        m, OP = self.ref_model, self.OP
+        n_pos = m.decoder.pos_table.shape[0]
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            feats = self.ref_frontend(self.ref_audio)
+            if m.encoder_type == "t5":
+                enc = OP.t5_encode(self.ref_sd, feats, m.model_cfg, n_pos)
+            else:
+                from oracle import perceiver_tf as OPTF
+                enc = OPTF.encode(self.ref_sd, feats, m.model_cfg)
+            t1 = time.perf_counter()
+            OP.t5_generate(self.ref_sd, enc, m.model_cfg, n_pos, 1, stop_at_eos=False)
+            t2 = time.perf_counter()
+            out = OP.t5_generate(self.ref_sd, enc, m.model_cfg, n_pos, self.ref_steps, stop_at_eos=False)
+            t3 = time.perf_counter()
+        per_step = max((t3 - t2) - (t2 - t1), 0.0) / max(self.ref_steps - 1, 1)
+        self._ref_spent = getattr(self, "_ref_spent", 0.0) + (t3 - t0)
+        self._ref_full = getattr(self, "_ref_full", 0.0) + (t2 - t0) + per_step * (m.max_token_length - 1)
         return out
 
     def reference_scale(self):
@@ -230,12 +249,165 @@ class ModelWorkload:
         return self._ref_spent / self._ref_full if getattr(self, "_ref_full", 0.0) > 0 else 1.0
 
     def reference_sample(self):
-        return (f"CPU oracle (HF-T5-pinned torch restatement) of {self.preset}, {self.ref_batch} segment(s): frontend + "
-                f"encoder + 1 decode step, then {self.ref_steps} of {self.ref_model.max_token_length} decode steps; "
-                f"full-length time = first + per-step cost x remaining steps")
+        return (f"torchaudio frontend + CPU oracle (HF-pinned torch restatement) of {self.preset}, {self.ref_batch} "
+                f"segments per step: frontend + encoder once, a 1-step and a {self.ref_steps}-step decode "
+                f"(of {self.ref_model.max_token_length}); full-length time = frontend + encoder + first step + per-step "
+                f"cost x remaining steps")
+
+    # ---- the "bar to beat" of SURVEY.md 2c: the SAME eager torch modules on the SAME GPU (cuFFT / cuBLAS / ATen),
+    # bf16 autocast, full decode length, host loop with the reference's per-step structure ----
+    def gpu_eager_baseline(self, dev, segments=None, budget_s=60.0):
+        import torch
+        import yourmt3_b200 as ymt3
+        from oracle import pipeline as OP
+        B = int(segments or min(self.batch, 64 if self.preset == "mt3_t5_small" else self.batch))
+        m = ymt3.YourMT3(audio_cfg=ymt3.get_audio_cfg(**self.audio_over), model_cfg=ymt3.get_model_cfg(self.preset),
+                         precision="f32")
+        ymt3.init_nondegenerate_(m, seed=0)
+        sd = {k: v.detach().to(dev) for k, v in m.state_dict().items()}
+        fe = reference_frontend(m.audio_cfg).to(dev)
+        x = self.dev_in[:B, 0] if getattr(self, "dev_in", None) is not None and self.dev_in.shape[0] >= B \
+            else torch.randn(B, SEG_SAMPLES, device=dev) * 0.1
+        n_pos, L = m.decoder.pos_table.shape[0], m.max_token_length
+        enc_chunk = 64     # the eager conv pre-encoder materialises (b, 64..128, T, F) fp32 activations
+        old = OP.DEVICE
+        OP.DEVICE = str(dev)
+
+        def run(steps):
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                if m.encoder_type == "t5":
+                    enc = torch.cat([OP.t5_encode(sd, fe(x[i:i + enc_chunk]), m.model_cfg, n_pos)
+                                     for i in range(0, B, enc_chunk)], 0)
+                else:
+                    from oracle import perceiver_tf as OPTF
+                    enc = torch.cat([OPTF.encode(sd, fe(x[i:i + enc_chunk]), m.model_cfg) for i in range(0, B, enc_chunk)], 0)
+                tok = OP.t5_generate(sd, enc.float(), m.model_cfg, n_pos, steps, stop_at_eos=True)
+            torch.cuda.synchronize()
+            return tok
+        try:
+            run(2)                                         # warm-up (cuBLAS / cuDNN heuristics, allocator)
+            t0 = time.perf_counter()
+            run(L)
+            dt = time.perf_counter() - t0
+            out = {"value": B * SEG_SAMPLES / 16000.0 / dt, "unit": "audio-s/s", "segments": B, "decode_steps": L,
+                   "seconds": dt, "dtype": "bf16 autocast (fp32 softmax / norms as in the reference)",
+                   "what": "torchaudio frontend + eager torch modules of the oracle on the SAME GPU (cuFFT / cuBLAS / "
+                           "cuDNN / ATen), host greedy loop with the reference's per-step EOS sync"}
+        except Exception as e:   # OOM etc.: report, never fail the bench
+            out = {"value": None, "error": f"{type(e).__name__}: {str(e)[:160]}", "segments": B}
+        finally:
+            OP.DEVICE = old
+            del sd
+            torch.cuda.empty_cache()
+        return out
+
+
+def frontend_compute_bound(frames, kernel_ms, n_fft=2048, sm_count=148, sm_mhz=1965.0):
+    """the honest bound of the log-mel kernel beside the HBM one.  Algorithmic fp32 flops per frame of a
+    real n_fft-point transform (split-radix-class count 2.5 N log2 N for the real-input FFT) + window (N) + power
+    spectrum (3 per bin); peak = SMs x 128 fp32 lanes x 2 (FMA) x the maximum SM clock - an upper bound no SIMT FFT
+    reaches because butterflies are add/sub-heavy (at most half of the issue slots are FMAs)."""
+    import math
+    per_frame = 2.5 * n_fft * math.log2(n_fft) + n_fft + 3 * (n_fft // 2 + 1)
+    peak = sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+    ach = frames * per_frame / (kernel_ms * 1e-3) / 1e12
+    return {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "flops_per_frame": per_frame, "peak_source": f"{sm_count} SMs x 128 lanes x 2 x {sm_mhz:.0f} MHz"}
+
+
+def reference_frontend(audio_cfg):
+    """The reference frontend itself: the torchaudio transform upstream's spectrogram.py wraps + log(clamp)
+    (SP/torchaudio/transforms/_transforms.py:621-631 / :101-123), as an nn.Module: (B, L) -> (B, T, F)."""
+    import torch
+    import torchaudio
+
+    class Ref(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.eps = float(audio_cfg.get("log_eps", 1e-5))
+            if audio_cfg["codec"] == "melspec":
+                self.t = torchaudio.transforms.MelSpectrogram(
+                    sample_rate=audio_cfg["sample_rate"], n_fft=audio_cfg["n_fft"], hop_length=audio_cfg["hop_length"],
+                    f_min=audio_cfg["f_min"], f_max=audio_cfg["f_max"], n_mels=audio_cfg["n_mels"],
+                    power=audio_cfg.get("power", 1.0))
+                self.lo, self.hi = 0, None
+            else:
+                self.t = torchaudio.transforms.Spectrogram(n_fft=audio_cfg["n_fft"], hop_length=audio_cfg["hop_length"],
+                                                           power=audio_cfg.get("power", 1.0))
+                self.lo = 1 if audio_cfg.get("spec_drop_dc", True) else 0
+                self.hi = audio_cfg["n_fft"] // 2 + 1
+
+        def forward(self, x):
+            with torch.no_grad():
+                y = self.t(x.float())[:, self.lo:self.hi]
+                return torch.log(torch.clamp(y, min=self.eps)).transpose(1, 2).contiguous()
+    return Ref()
+
+
+class HourWorkload(ModelWorkload):
+    """BASELINE.json configs[4]: ONE HOUR of synthetic 16 kHz audio (1758 segments of 2.048 s), YPTF.MoE+Multi,
+    sharded by contiguous segment ranges over the ranks = STRONG scaling (total work fixed).  A step transcribes the
+    whole hour: every rank runs its shard in near-equal batches, then the one NCCL all-gather of the int32 tokens."""
+    scaling = "strong"
+    TOTAL_SEGMENTS = 1758
+
+    def __init__(self, name, batch):
+        super().__init__("yptf_moe_multi", batch)
+        self.name = "hour_sharded"
+        self.max_batch = batch or PRESETS["yptf_moe_multi"][2]
+
+    def setup_native(self, dev):
+        import torch
+        from .sharding import shard_range
+        dist = torch.distributed
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        start, stop, _ = shard_range(self.TOTAL_SEGMENTS, self.world, self.rank)
+        n_local = stop - start
+        n_batches = max(1, -(-n_local // self.max_batch))
+        self.batch = -(-n_local // n_batches)              # near-equal batches (no ragged tail batch)
+        super().setup_native(dev)
+        g = torch.Generator().manual_seed(1234)
+        # the same hour of audio on every rank (host, pinned); the rank's shard also resident on the device
+        self.host_full = (torch.randn(self.TOTAL_SEGMENTS, 1, SEG_SAMPLES, generator=g) * 0.1).pin_memory()
+        self.dev_full_shard = self.host_full[start:stop].to(dev)
+        self.start, self.stop = start, stop
+        self.dev = dev
+        self.e2e_batch = self.batch
+
+    def units(self, world):
+        return self.TOTAL_SEGMENTS
+
+    def _shard_view(self):
+        # transcribe_sharded indexes [start, stop) of a full-length tensor: give it a device-resident view of the shard
+        class _View:
+            def __init__(v, t, start, n):
+                v.t, v.start, v.shape = t, start, (n,) + tuple(t.shape[1:])
+
+            def __getitem__(v, sl):
+                return v.t[sl.start - v.start: sl.stop - v.start]
+        return _View(self.dev_full_shard, self.start, self.TOTAL_SEGMENTS)
+
+    def step(self):
+        return self.model.inference_file_sharded(self.batch, self._shard_view(), stop_at_eos=True)
+
+    def step_e2e(self):
+        return self.model.inference_file_sharded(self.batch, self.host_full, stop_at_eos=True).cpu()
+
+    def e2e_bytes(self):
+        n_local = self.stop - self.start
+        return n_local * SEG_SAMPLES * 4, self.TOTAL_SEGMENTS * self.channels * self.max_len * 4
+
+    def config(self):
+        c = super().config()
+        c.update(workload=self.name, total_segments=self.TOTAL_SEGMENTS, audio_seconds=self.TOTAL_SEGMENTS * SEG_SAMPLES / 16000.0,
+                 segments_per_batch=self.batch, sharding="contiguous segment ranges, replicated weights, one int32 all-gather")
+        return c
 
 
 def get(name, batch):
+    if name in ("hour", "hour_sharded"):
+        return HourWorkload(name, batch)
     if name not in PRESETS:
-        raise SystemExit(f"unknown workload {name!r}; choose from frontend, {', '.join(PRESETS)}")
+        raise SystemExit(f"unknown workload {name!r}; choose from frontend, hour, {', '.join(PRESETS)}")
     return ModelWorkload(name, batch)

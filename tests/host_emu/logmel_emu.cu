@@ -37,16 +37,19 @@ extern "C" __attribute__((visibility("default"))) int lm_emu_run_wave(const ymt3
       }
       for (int tid = 0; tid < LM_THREADS; ++tid) lm_pass2(tid, tb.tw2, bufA.data(), bufB.data());
       for (size_t i = 0; i < mags.size(); ++i) mags[i] = make_float2(-1.f, -1.f);   // poison: every bin must be written
-      for (int tid = 0; tid < LM_THREADS; ++tid) lm_pass3_mag(tid, bufB.data(), mags.data(), cfg->power_mode);
+      const bool spec = cfg->codec != YMT3_CODEC_MELSPEC;
+      const bool take_sqrt = !spec && cfg->power_mode == 1;
+      const LmOut oc = lm_out_consts(spec, cfg->power_mode, cfg->log_eps);
+      for (int tid = 0; tid < LM_THREADS; ++tid) lm_pass3_mag(tid, bufB.data(), mags.data(), take_sqrt);
       for (int k = 0; k <= 1024; ++k)
         if (mags[lm_magaddr(k)].x < 0.f) return 2;
       float* outA = out + ((size_t)b * T + tA) * n_out;
       float* outB = hasB ? outA + n_out : nullptr;
       for (int tid = 0; tid < LM_THREADS; ++tid) {
         if (cfg->codec == YMT3_CODEC_MELSPEC)
-          lm_mel_log(tid, tb, n_out, cfg->log_eps, mags.data(), outA, outB);
+          lm_mel_log(tid, tb, n_out, oc, mags.data(), outA, outB);
         else
-          lm_spec_log(tid, cfg->spec_bin0, n_out, cfg->log_eps, mags.data(), outA, outB);
+          lm_spec_log(tid, cfg->spec_bin0, n_out, oc, mags.data(), outA, outB);
       }
     }
   return 0;

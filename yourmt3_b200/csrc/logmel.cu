@@ -37,6 +37,10 @@ ymt3_logmel_kernel(LmTables tb, const float* __restrict__ audio, int64_t total_s
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) w[n1] = __ldg(tb.window + 128 * n1 + tid);
 
+  const bool spec = codec != YMT3_CODEC_MELSPEC;
+  const bool take_sqrt = !spec && power_mode == 1;   // the linear-frequency codec never needs the square root
+  const LmOut oc = lm_out_consts(spec, power_mode, eps);
+
   const int p0 = blockIdx.x * chunk;
   const int p1 = min(p0 + chunk, total_pairs);
 
@@ -54,14 +58,14 @@ ymt3_logmel_kernel(LmTables tb, const float* __restrict__ audio, int64_t total_s
     __syncthreads();
     lm_pass2(tid, tb.tw2, bufA, bufB);
     __syncthreads();
-    lm_pass3_mag(tid, bufB, mags, power_mode);
+    lm_pass3_mag(tid, bufB, mags, take_sqrt);
     __syncthreads();
     float* outA = out + ((size_t)b * T + tA) * n_out;
     float* outB = hasB ? outA + n_out : nullptr;
-    if (codec == YMT3_CODEC_MELSPEC)
-      lm_mel_log(tid, tb, n_out, eps, mags, outA, outB);
+    if (!spec)
+      lm_mel_log(tid, tb, n_out, oc, mags, outA, outB);
     else
-      lm_spec_log(tid, spec_bin0, n_out, eps, mags, outA, outB);
+      lm_spec_log(tid, spec_bin0, n_out, oc, mags, outA, outB);
     __syncthreads();   // mags alias bufA, which the next pair's pass 1 overwrites
   }
 }

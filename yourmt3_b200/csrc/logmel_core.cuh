@@ -44,11 +44,58 @@ struct LmTables {
   const float*  mel_w;      // packed nonzero weights, ascending bin order
 };
 
-YMT3_HD float2 lm_cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// Complex arithmetic on (re, im) register pairs.  On sm_100a every helper is ONE packed fp32 instruction
+// (FADD2 / FMUL2 / FFMA2: add.f32x2 / mul.f32x2 / fma.f32x2), the +-i rotations and the scalar broadcasts ride on the
+// instructions' operand modifiers (.LO_HI swap, per-half negate, .F32 broadcast), so a complex add is one issue slot and
+// a complex multiply two - the r01 kernel was issue-bound with 55 % of its slots in scalar FADD / FMUL / FFMA
+// (profiles/r01_logmel_default_workload_ncu_full.txt).  Same IEEE round-to-nearest operations as the scalar forms, so
+// the host emulation (tests/host_emu) mirrors them with fmaf.
+YMT3_HD float2 lm_add(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
 }
-YMT3_HD float2 lm_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-YMT3_HD float2 lm_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+YMT3_HD float2 lm_sub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+// a - i*b = (a.x + b.y, a.y - b.x)
+YMT3_HD float2 lm_add_mi(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __fadd2_rn(a, make_float2(b.y, -b.x));
+#else
+  return make_float2(a.x + b.y, a.y - b.x);
+#endif
+}
+// a + i*b = (a.x - b.y, a.y + b.x)
+YMT3_HD float2 lm_add_pi(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __fadd2_rn(a, make_float2(-b.y, b.x));
+#else
+  return make_float2(a.x - b.y, a.y + b.x);
+#endif
+}
+// a * w = (a.x w.x - a.y w.y, a.x w.y + a.y w.x) = a.x * (w.x, w.y) + a.y * (-w.y, w.x)
+YMT3_HD float2 lm_cmul(float2 a, float2 w) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __ffma2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x), __fmul2_rn(make_float2(a.x, a.x), w));
+#else
+  return make_float2(fmaf(a.y, -w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));
+#endif
+}
+// (x * s, y * s)
+YMT3_HD float2 lm_scale2(float x, float y, float s) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __fmul2_rn(make_float2(x, y), make_float2(s, s));
+#else
+  return make_float2(x * s, y * s);
+#endif
+}
 
 // forward DFT-4, natural order in and out
 YMT3_HD void lm_fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
@@ -56,8 +103,8 @@ YMT3_HD void lm_fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
   float2 t2 = lm_add(a1, a3), t3 = lm_sub(a1, a3);
   a0 = lm_add(t0, t2);
   a2 = lm_sub(t0, t2);
-  a1 = make_float2(t1.x + t3.y, t1.y - t3.x);  // t1 - i*t3
-  a3 = make_float2(t1.x - t3.y, t1.y + t3.x);  // t1 + i*t3
+  a1 = lm_add_mi(t1, t3);  // t1 - i*t3
+  a3 = lm_add_pi(t1, t3);  // t1 + i*t3
 }
 
 #define LM_C1 0.92387953251128674f   // cos(pi/8)
@@ -93,7 +140,7 @@ YMT3_HD void lm_fft8(float2 (&v)[8]) {
   lm_fft4(v[1], v[3], v[5], v[7]);
   // v[j + 2a]; multiply j=1 terms by W_8^a
   v[3] = lm_cmul(v[3], make_float2(LM_R2, -LM_R2));
-  v[5] = make_float2(v[5].y, -v[5].x);
+  v[5] = make_float2(v[5].y, -v[5].x);   // * (-i): folds into the operand modifiers of the add / sub below
   v[7] = lm_cmul(v[7], make_float2(-LM_R2, -LM_R2));
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
@@ -154,7 +201,7 @@ YMT3_HD void lm_pass1(int tid, const float* __restrict__ seg, int L, int valid, 
       for (int n1 = 0; n1 < 17; ++n1) xs[n1] = lm_ld(seg, startA + 128 * n1 + tid, L, valid);
     }
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) v[n1] = make_float2(xs[n1] * w[n1], xs[n1 + 1] * w[n1]);
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = lm_scale2(xs[n1], xs[n1 + 1], w[n1]);
     if (!hasB) {   // odd frame count: the last pair has no second frame (uniform, rare)
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) v[n1].y = 0.f;
@@ -165,7 +212,7 @@ YMT3_HD void lm_pass1(int tid, const float* __restrict__ seg, int L, int valid, 
       int n = 128 * n1 + tid;
       float xa = seg[startA + n];
       float xb = hasB ? seg[startB + n] : 0.f;
-      v[n1] = make_float2(xa * w[n1], xb * w[n1]);
+      v[n1] = lm_scale2(xa, xb, w[n1]);
     }
   } else {
 #pragma unroll
@@ -173,7 +220,7 @@ YMT3_HD void lm_pass1(int tid, const float* __restrict__ seg, int L, int valid, 
       int n = 128 * n1 + tid;
       float xa = lm_ld(seg, startA + n, L, valid);
       float xb = hasB ? lm_ld(seg, startB + n, L, valid) : 0.f;
-      v[n1] = make_float2(xa * w[n1], xb * w[n1]);
+      v[n1] = lm_scale2(xa, xb, w[n1]);
     }
   }
   lm_fft16(v);
@@ -205,17 +252,36 @@ YMT3_HD void lm_pass2(int tid, const float2* __restrict__ tw2, const float2* __r
 
 YMT3_HD int lm_magaddr(int bin) { return bin + (bin >> 4); }
 
-// |X_A|^p, |X_B|^p of one (k, N-k) pair from z = Z[k], zc = Z[N-k]
-YMT3_HD float2 lm_pair_mag(float2 z, float2 zc, int power_mode) {
-  // X_A = ((a+c) + i(b-d))/2 ; X_B = ((b+d) - i(a-c))/2 with z=a+ib, zc=c+id
-  float ar = 0.5f * (z.x + zc.x), ai = 0.5f * (z.y - zc.y);
-  float br = 0.5f * (z.y + zc.y), bi = 0.5f * (z.x - zc.x);
-  float pa = ar * ar + ai * ai, pb = br * br + bi * bi;
-  if (power_mode == 1) {
-    pa = sqrtf(pa);
-    pb = sqrtf(pb);
-  }
-  return make_float2(pa, pb);
+// One (k, N-k) pair, z = Z[k], zc = Z[N-k]:  X_A = ((a+c) + i(b-d))/2, X_B = ((b+d) - i(a-c))/2 with z = a+ib,
+// zc = c+id, so with S = z + zc, D = z - zc:  4|X_A|^2 = S.x^2 + D.y^2,  4|X_B|^2 = S.y^2 + D.x^2  - four packed
+// instructions for both frames.  The factor 4 (and the square root of power = 1) is folded into the output stage:
+// take_sqrt = false -> (4|X_A|^2, 4|X_B|^2);  true -> (2|X_A|, 2|X_B|)  (sqrt.approx, 1 ulp-class).
+YMT3_HD float lm_fast_sqrt(float x) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return sqrtf(x);
+#endif
+}
+YMT3_HD float lm_fast_log2(float x) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __log2f(x);   // lg2.approx: relative error 2^-22
+#else
+  return log2f(x);
+#endif
+}
+YMT3_HD float2 lm_pair_mag(float2 z, float2 zc, bool take_sqrt) {
+  const float2 S = lm_add(z, zc), D = lm_sub(z, zc);
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  const float2 dq = __fmul2_rn(D, D);
+  float2 q = __ffma2_rn(S, S, make_float2(dq.y, dq.x));
+#else
+  float2 q = make_float2(fmaf(S.x, S.x, D.y * D.y), fmaf(S.y, S.y, D.x * D.x));
+#endif
+  if (take_sqrt) q = make_float2(lm_fast_sqrt(q.x), lm_fast_sqrt(q.y));
+  return q;
 }
 
 // pass 3 + magnitudes: every thread owns TWO (k1, k2) columns chosen so that Z[k] and Z[N-k] of all its
@@ -224,8 +290,11 @@ YMT3_HD float2 lm_pair_mag(float2 z, float2 zc, int power_mode) {
 //   tid 112..119 : (8, tid-112)                    with partner (8, 15-k2)
 //   tid 120..126 : (0, tid-119)                    with partner (0, 16-k2)
 //   tid 127      : (0, 0) [k3 <-> (8-k3)%8] and (0, 8) [k3 <-> 7-k3], both self-paired
-// mags[lm_magaddr(bin)] = (|X_A[bin]|^p, |X_B[bin]|^p), bin = min(k, N-k) in [0, 1024].
-YMT3_HD void lm_pass3_mag(int tid, const float2* __restrict__ bufB, float2* __restrict__ mags, int power_mode) {
+// mags[lm_magaddr(bin)] = lm_pair_mag of the two frames (see there for the folded scale), bin = min(k, N-k) in [0, 1024].
+// For tid < 127 the first column has ka0 = k1a + 16*k2a <= 247, so k = ka0 + 256*k3 is a bin itself for k3 < 4 and
+// mirrors to bin 2048 - k for k3 >= 4: both shared-memory addresses are a per-thread base plus a compile-time
+// multiple of 272 (= 256 + 256/16).
+YMT3_HD void lm_pass3_mag(int tid, const float2* __restrict__ bufB, float2* __restrict__ mags, bool take_sqrt) {
   int k1a, k2a, k1b, k2b;
   if (tid < 112) { k1a = 1 + (tid >> 4); k2a = tid & 15; k1b = 16 - k1a; k2b = 15 - k2a; }
   else if (tid < 120) { k1a = 8; k2a = tid - 112; k1b = 8; k2b = 15 - k2a; }
@@ -242,14 +311,15 @@ YMT3_HD void lm_pass3_mag(int tid, const float2* __restrict__ bufB, float2* __re
   // register index r = 2a + b holds k3 = a + 4b  ->  k3 lives at r(k3) = 2*(k3 & 3) + (k3 >> 2)
   if (tid < 127) {
     const int ka0 = k1a + 16 * k2a;
+    float2* lo = mags + lm_magaddr(ka0);              // bins ka0 + 256*k3,           k3 = 0..3
+    float2* hi = mags + lm_magaddr(256 - ka0);        // bins (256 - ka0) + 256*(7-k3), k3 = 4..7
 #pragma unroll
     for (int k3 = 0; k3 < 8; ++k3) {
       const int ra = 2 * (k3 & 3) + (k3 >> 2);
       const int k3p = 7 - k3;
       const int rb = 2 * (k3p & 3) + (k3p >> 2);
-      const int k = ka0 + 256 * k3;
-      const int bin = k <= 1024 ? k : LM_NFFT - k;
-      mags[lm_magaddr(bin)] = lm_pair_mag(va[ra], vb[rb], power_mode);
+      float2* dst = k3 < 4 ? lo + 272 * k3 : hi + 272 * (7 - k3);
+      *dst = lm_pair_mag(va[ra], vb[rb], take_sqrt);
     }
   } else {
     // (0,0): k = 256*k3, partner k3' = (8-k3)%8 -> bins 0, 256, 512, 768, 1024
@@ -257,42 +327,62 @@ YMT3_HD void lm_pass3_mag(int tid, const float2* __restrict__ bufB, float2* __re
     for (int k3 = 0; k3 <= 4; ++k3) {
       const int k3p = (8 - k3) & 7;
       const int ra = 2 * (k3 & 3) + (k3 >> 2), rb = 2 * (k3p & 3) + (k3p >> 2);
-      mags[lm_magaddr(256 * k3)] = lm_pair_mag(va[ra], va[rb], power_mode);
+      mags[lm_magaddr(256 * k3)] = lm_pair_mag(va[ra], va[rb], take_sqrt);
     }
     // (0,8): k = 128 + 256*k3, partner 7-k3 -> bins 128, 384, 640, 896
 #pragma unroll
     for (int k3 = 0; k3 < 4; ++k3) {
       const int k3p = 7 - k3;
       const int ra = 2 * (k3 & 3) + (k3 >> 2), rb = 2 * (k3p & 3) + (k3p >> 2);
-      mags[lm_magaddr(128 + 256 * k3)] = lm_pair_mag(vb[ra], vb[rb], power_mode);
+      mags[lm_magaddr(128 + 256 * k3)] = lm_pair_mag(vb[ra], vb[rb], take_sqrt);
     }
   }
 }
 
+// Output stage.  The stored values carry a folded scale (lm_pair_mag): with m = the stored value and
+//   |X|^p = mag_scale * m,   log(max(|X|^p [summed over a mel band], eps)) = ln2 * log2(max(sum, eps / mag_scale)) + ln(mag_scale)
+// and for the linear-frequency codec with power 1 the square root is never taken at all:
+//   log(max(|X|, eps)) = 0.5 * ln2 * log2(max(4|X|^2, 4 eps^2)) - ln2.
+// LmOut carries (floor, c1, c0): out = c1 * log2(max(v, floor)) + c0   (lg2.approx + one FFMA per output).
+struct LmOut { float floor, c1, c0; };
+YMT3_HD LmOut lm_out_consts(int codec_spec, int power_mode, float eps) {
+  const float ln2 = 0.69314718055994531f;
+  LmOut o;
+  if (codec_spec && power_mode == 1) { o.floor = 4.f * eps * eps; o.c1 = 0.5f * ln2; o.c0 = -ln2; }   // v = 4|X|^2
+  else if (power_mode == 1) { o.floor = 2.f * eps; o.c1 = ln2; o.c0 = -ln2; }                         // v = sum w * 2|X|
+  else { o.floor = 4.f * eps; o.c1 = ln2; o.c0 = -2.f * ln2; }                                        // v = (sum w *) 4|X|^2
+  return o;
+}
+YMT3_HD float lm_out(float v, const LmOut& o) { return fmaf(o.c1, lm_fast_log2(fmaxf(v, o.floor)), o.c0); }
+
 // mel projection + log for both frames. Filter m: sum_j mel_w[off+j] * mag[first+j] (banded filterbank).
-YMT3_HD void lm_mel_log(int tid, const LmTables& tb, int n_mels, float eps,
+YMT3_HD void lm_mel_log(int tid, const LmTables& tb, int n_mels, const LmOut& oc,
                         const float2* __restrict__ mags, float* __restrict__ outA, float* __restrict__ outB) {
   for (int m = tid; m < n_mels; m += LM_THREADS) {
     const int2 meta = tb.mel_meta[m];
     const int first = meta.x & 0xffff, cnt = meta.x >> 16, o0 = meta.y;
-    float sa = 0.f, sb = 0.f;
+    float2 acc = make_float2(0.f, 0.f);
     for (int j = 0; j < cnt; ++j) {
       const float wgt = tb.mel_w[o0 + j];
       const float2 mg = mags[lm_magaddr(first + j)];
-      sa = fmaf(wgt, mg.x, sa);
-      sb = fmaf(wgt, mg.y, sb);
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+      acc = __ffma2_rn(make_float2(wgt, wgt), mg, acc);
+#else
+      acc = make_float2(fmaf(wgt, mg.x, acc.x), fmaf(wgt, mg.y, acc.y));
+#endif
     }
-    outA[m] = logf(fmaxf(sa, eps));
-    if (outB) outB[m] = logf(fmaxf(sb, eps));
+    outA[m] = lm_out(acc.x, oc);
+    if (outB) outB[m] = lm_out(acc.y, oc);
   }
 }
 
 // linear-frequency ("spec" codec) log output: bins [bin0, bin0 + n_out)
-YMT3_HD void lm_spec_log(int tid, int bin0, int n_out, float eps, const float2* __restrict__ mags,
+YMT3_HD void lm_spec_log(int tid, int bin0, int n_out, const LmOut& oc, const float2* __restrict__ mags,
                          float* __restrict__ outA, float* __restrict__ outB) {
+#pragma unroll 8
   for (int f = tid; f < n_out; f += LM_THREADS) {
     const float2 mg = mags[lm_magaddr(bin0 + f)];
-    outA[f] = logf(fmaxf(mg.x, eps));
-    if (outB) outB[f] = logf(fmaxf(mg.y, eps));
+    outA[f] = lm_out(mg.x, oc);
+    if (outB) outB[f] = lm_out(mg.y, oc);
   }
 }

@@ -78,6 +78,8 @@ int rmsnorm(const void* x, const float* w, void* y, int64_t rows, int dim, float
             cudaStream_t stream);
 int layernorm(const void* x, const float* w, const float* b, void* y, int64_t rows, int dim,
               float eps, int dtype, cudaStream_t stream);
+// mixed precision RMSNorm: x fp32 (the residual stream of the bf16 T5 encoder), y bf16 (tensor-core operand)
+int rmsnorm_f32_bf16(const float* x, const float* w, void* y, int64_t rows, int dim, float eps, cudaStream_t stream);
 
 // Generic small-sequence attention: O[b,h,i,:] = softmax_j(scale * Q[b,h,i,:].K[b,h,j,:] (+causal)) V[b,h,j,:]
 // element strides are given in ELEMENTS; head dim dk in {16, 32, 64, 128}.

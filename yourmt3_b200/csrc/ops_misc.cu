@@ -190,6 +190,53 @@ int rmsnorm(const void* x, const float* w, void* y, int64_t rows, int dim, float
   return YMT3_OK;
 }
 
+// fp32 residual stream in -> bf16 GEMM operand out (one warp per row, 16-byte loads, the row stays in registers)
+template <int MAXV>
+__global__ void __launch_bounds__(256) rmsnorm_f32_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               __nv_bfloat16* __restrict__ y, int64_t rows, int dim,
+                                                               float eps) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+  const int vecs = dim >> 2;
+  float4 v[MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < vecs) {
+      v[j] = xr[i];
+      ss = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, ss))));
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss / (float)dim + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + row * dim);
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < vecs) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + i);
+      uint2 o;
+      *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(wv.x * (v[j].x * inv), wv.y * (v[j].y * inv));
+      *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(wv.z * (v[j].z * inv), wv.w * (v[j].w * inv));
+      yr[i] = o;
+    }
+  }
+}
+
+int rmsnorm_f32_bf16(const float* x, const float* w, void* y, int64_t rows, int dim, float eps, cudaStream_t stream) {
+  if (rows <= 0) return YMT3_OK;
+  YMT3_REQUIRE(x && w && y && dim > 0 && dim % 4 == 0 && dim <= 2048, "rmsnorm_f32_bf16: dim must be a multiple of 4, <= 2048");
+  YMT3_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w) & 15) == 0, "rmsnorm_f32_bf16: 16-byte alignment");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dim <= 512) rmsnorm_f32_bf16_kernel<4><<<grid, 256, 0, stream>>>(x, w, (__nv_bfloat16*)y, rows, dim, eps);
+  else rmsnorm_f32_bf16_kernel<16><<<grid, 256, 0, stream>>>(x, w, (__nv_bfloat16*)y, rows, dim, eps);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
+
 int layernorm(const void* x, const float* w, const float* b, void* y, int64_t rows, int dim, float eps,
               int dtype, cudaStream_t stream) {
   if (rows <= 0) return YMT3_OK;

@@ -102,7 +102,8 @@ extern "C" int ymt3_t5enc_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
         rc = YMT3_ERR_INVALID;
       } else {
         e->n_pos = (int)p->shape[0];
-        rc = pack_table(e->weights, (const float*)p->data, false, p->shape[0] * p->shape[1], cfg->precision, &e->pos, 0);
+        // the encoder's residual stream is fp32 in both precisions (see ymt3_t5enc_forward): fp32 position table
+        rc = pack_table(e->weights, (const float*)p->data, false, p->shape[0] * p->shape[1], YMT3_F32, &e->pos, 0);
       }
     }
   }
@@ -137,11 +138,16 @@ extern "C" int ymt3_t5enc_forward(ymt3_t5enc_t* e, const float* x_in, int64_t B,
   YMT3_REQUIRE(M < (1ll << 31), "t5enc_forward: too many tokens");
   YMT3_REQUIRE(!e->pos || S <= e->n_pos, "t5enc_forward: sequence %lld longer than pos_table %d", (long long)S, e->n_pos);
   cudaStream_t s = (cudaStream_t)stream;
+  // bf16 precision: GEMM operands / attention in bf16 (tcgen05), the RESIDUAL STREAM x in fp32 - what torch autocast
+  // does with the reference modules.  A bf16 residual stream loses ~2^-9 of |x| at every add while the layer updates
+  // are a fraction of |x|; measured on the unreduced 8-layer encoder (log-mel input, random weights) the relative L2
+  // error of the hidden states vs the fp32 oracle was 9.3 % with a bf16 stream (profiles/r02_diag_t5enc_bf16.txt).
+  const bool mixed = dt == YMT3_BF16;
   if (M > e->cap_rows) {
     YMT3_CUDA_CHECK(cudaStreamSynchronize(s));
     e->ws.release();
     const size_t es = dtype_size(dt);
-    e->x = e->ws.alloc(M * D * es);
+    e->x = e->ws.alloc(M * D * 4);
     e->h = e->ws.alloc(M * D * es);
     e->qkv = e->ws.alloc(M * 3 * inner * es);
     e->attn = e->ws.alloc(M * inner * es);
@@ -152,12 +158,19 @@ extern "C" int ymt3_t5enc_forward(ymt3_t5enc_t* e, const float* x_in, int64_t B,
   }
   int rc;
   // inputs_embeds (+ absolute position table [RECALL upstream]); dropout is identity in eval
-  if ((rc = convert(x_in, YMT3_F32, e->x, dt, M * D, s))) return rc;
-  if (e->pos && (rc = add_rows(e->x, e->pos, e->x, M, (int)S, D, dt, s))) return rc;
+  if (e->pos) {
+    if ((rc = add_rows(x_in, e->pos, e->x, M, (int)S, D, YMT3_F32, s))) return rc;
+  } else {
+    YMT3_CUDA_CHECK(cudaMemcpyAsync(e->x, x_in, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, s));
+  }
   const size_t es = dtype_size(dt);
+  auto norm = [&](const float* w, void* y) -> int {
+    return mixed ? rmsnorm_f32_bf16((const float*)e->x, w, y, M, D, c.layer_norm_eps, s)
+                 : rmsnorm(e->x, w, y, M, D, c.layer_norm_eps, YMT3_F32, s);
+  };
   for (const T5Layer& L : e->layers) {
     // T5LayerSelfAttention (modeling_t5.py:356-377): x += o(attn(rmsnorm(x)))
-    if ((rc = rmsnorm(e->x, L.ln_sa, e->h, M, D, c.layer_norm_eps, dt, s))) return rc;
+    if ((rc = norm(L.ln_sa, e->h))) return rc;
     if ((rc = linear_fwd(dt, e->h, D, L.qkv, e->qkv, 3 * inner, (int)M, 0, 0, nullptr, 0, 1.f, dt, s))) return rc;
     AttnParams a{};
     a.Q = e->qkv; a.K = (char*)e->qkv + inner * es; a.V = (char*)e->qkv + 2 * inner * es;
@@ -166,13 +179,13 @@ extern "C" int ymt3_t5enc_forward(ymt3_t5enc_t* e, const float* x_in, int64_t B,
     a.B = (int)B; a.H = H; a.Sq = (int)S; a.Sk = (int)S; a.dk = dk;
     a.scale = 1.0f;  // T5: no 1/sqrt(d) (modeling_t5.py:308)
     if ((rc = attention(a, dt, s))) return rc;
-    if ((rc = linear_fwd(dt, e->attn, inner, L.o, e->x, D, (int)M, 0, 0, e->x, D, 1.f, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, e->attn, inner, L.o, e->x, D, (int)M, 0, 0, e->x, D, 1.f, YMT3_F32, s))) return rc;
     // T5LayerFF (modeling_t5.py:146-150) with gated-GELU (:115-131)
-    if ((rc = rmsnorm(e->x, L.ln_ff, e->h, M, D, c.layer_norm_eps, dt, s))) return rc;
+    if ((rc = norm(L.ln_ff, e->h))) return rc;
     if ((rc = linear_fwd(dt, e->h, D, L.wi, e->g, F, (int)M, YMT3_ACT_GELU_NEW, 1, nullptr, 0, 1.f, dt, s))) return rc;
-    if ((rc = linear_fwd(dt, e->g, F, L.wo, e->x, D, (int)M, 0, 0, e->x, D, 1.f, dt, s))) return rc;
+    if ((rc = linear_fwd(dt, e->g, F, L.wo, e->x, D, (int)M, 0, 0, e->x, D, 1.f, YMT3_F32, s))) return rc;
   }
-  return rmsnorm(e->x, e->final_ln, out, M, D, c.layer_norm_eps, dt, s);  // final_layer_norm (:767)
+  return norm(e->final_ln, out);  // final_layer_norm (:767)
 }
 
 // ------------------------------------------------------------------------------------------

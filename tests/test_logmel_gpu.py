@@ -137,3 +137,26 @@ def test_waveform_entry_equals_sliced_segments(cuda_device, native_lib):
             got = layer.forward_waveform(wave)
             assert got.shape == ref.shape
             assert torch.equal(got, ref)
+
+
+def test_bulk_copy_staging_equals_cooperative_fill(cuda_device, native_lib):
+    """Interior frame pairs are staged by 1-D bulk async copies (16-byte aligned windows), edge pairs and misaligned
+    buffers by the CTA itself: the same audio at a 4-byte-misaligned address (every pair cooperative) must give
+    bit-identical output; several hops (stage size = hop + 2048 samples, > 48 KB of shared memory in total for the
+    largest) against the float64 oracle."""
+    for layer in (S.Melspectrogram(), S.Spectrogram()):
+        x = torch.from_numpy(synth_noise(5, 32767, seed=3)).to(cuda_device)
+        ref = layer(x)
+        for shift in (1, 2, 3):
+            buf = torch.zeros(5 * 32767 + 8, device=cuda_device)
+            view = buf[shift: shift + 5 * 32767].view(5, 32767)
+            view.copy_(x)
+            assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+            assert torch.equal(layer(view), ref)
+    for hop in (64, 128, 300, 512, 1000, 2048):
+        import yourmt3_b200 as ymt3
+        layer, (T, F) = S.get_spectrogram_layer_from_audio_cfg(ymt3.get_audio_cfg(codec="spec", hop_length=hop))
+        xs = synth_noise(3, 20000, seed=hop)
+        got, ref = run(layer, xs, cuda_device), oracle_run(layer, xs)
+        assert got.shape == ref.shape == (3, 1 + 20000 // hop, F)
+        assert_frontend_close(got, ref, TOL, strict_everywhere=False)

@@ -109,7 +109,8 @@ def test_moe_ff_bf16_flip_rate(cuda_device, native_lib):
     print(f"moe bf16: flip rate {rate:.4f} of {N} tokens ({float((~sure).float().mean()):.3f} within the bf16 "
           f"perturbation of a tie); max err of well-conditioned tokens {float(err[sure].max()):.4f}, median "
           f"{float(err.median()):.5f}")
-    assert float(err[sure].max()) < 2e-2           # bf16 accuracy (of the output range) where routing is unambiguous
+    # measured on B200 (round 2): flip rate 0.0023, max err of well-conditioned tokens 0.0057, median 0.0021
+    assert float(err[sure].max()) < 1e-2           # bf16 accuracy (of the output range) where routing is unambiguous
     assert float(err.median()) < 4e-3
     assert not bool(flipped[sure].any())
-    assert rate < 0.02                              # measured-rate + margin (printed above)
+    assert rate < 0.006                             # measured rate + margin

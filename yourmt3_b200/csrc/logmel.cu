@@ -18,55 +18,140 @@ struct ymt3_frontend {
   int* d_mel_off;
   int2* d_mel_meta;
   float* d_mel_w;
+  float4* d_rec_w;
+  int rec_ok;
   // staging for the *_host entry point (grown on demand)
   float* d_stage_in;
   float* d_stage_out;
   size_t stage_in_bytes, stage_out_bytes;
 };
 
-__global__ void __launch_bounds__(LM_THREADS, 6)
+// ---- mbarrier / bulk-copy helpers (1-D TMA: cp.async.bulk global -> shared, completion on an mbarrier) ----
+__device__ __forceinline__ uint32_t lm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lm_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lm_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void lm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lm_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LM_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra LM_DONE;\n\t"
+      "bra LM_WAIT;\n\t"
+      "LM_DONE:\n\t"
+      "}" ::"r"(lm_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void lm_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   lm_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(lm_smem_u32(bar))
+               : "memory");
+}
+
+// One CTA (128 threads) per run of `chunk` consecutive frame pairs.  Per pair: [staged samples ready] pass 1 ->
+// barrier -> (one thread launches the bulk copy of the NEXT pair's samples) pass 2 -> barrier -> pass 3 + magnitudes
+// -> barrier -> output stage -> barrier.  Shared memory: two FFT exchange buffers (static, 35 KB) + the sample
+// stage (dynamic, hop + 2048 + 4 floats).  4 CTAs / SM (register twiddles: <= 128 registers per thread).
+__global__ void __launch_bounds__(LM_THREADS, 4)
 ymt3_logmel_kernel(LmTables tb, const float* __restrict__ audio, int64_t total_samples, float* __restrict__ out, int L,
                    int T, int hop, int pairs_per_seg, int chunk, int total_pairs, int codec,
-                   int n_out, int spec_bin0, int power_mode, float eps) {
+                   int n_out, int spec_bin0, int power_mode, float eps, int bulk_ok) {
   __shared__ __align__(16) float2 bufA[LM_BUF_ELEMS];
   __shared__ __align__(16) float2 bufB[LM_BUF_ELEMS];
-  float2* mags = bufA;   // bufA is dead after pass 2; the interleaved magnitudes (LM_MAG_ELEMS <= LM_BUF_ELEMS) reuse it
+  __shared__ __align__(16) float2 mags[LM_MAG_ELEMS];   // own buffer: no barrier between the output stage and the next pass 1
+  __shared__ __align__(8) uint64_t stage_bar;
+  extern __shared__ __align__(16) float stage[];   // hop + 2048 (+ <= 3 alignment) samples
   const int tid = threadIdx.x;
 
-  float w[16];   // loop-invariant window column of this thread
+  // loop-invariant per-thread constants: window column and pass-1 twiddles W_2048^(tid * k1)
+  float w[16];
+  float2 tw[16];
 #pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) w[n1] = __ldg(tb.window + 128 * n1 + tid);
-
+  for (int n1 = 0; n1 < 16; ++n1) {
+    w[n1] = __ldg(tb.window + 128 * n1 + tid);
+    tw[n1] = __ldg(tb.tw1 + n1 * 128 + tid);
+  }
   const bool spec = codec != YMT3_CODEC_MELSPEC;
   const bool take_sqrt = !spec && power_mode == 1;   // the linear-frequency codec never needs the square root
   const LmOut oc = lm_out_consts(spec, power_mode, eps);
+  const int span = hop + LM_NFFT;                    // samples one pair covers
+
+  if (tid < LM_MAG_ELEMS - lm_magaddr(LM_NBINS)) mags[lm_magaddr(LM_NBINS) + tid] = make_float2(0.f, 0.f);   // slots past bin 1024
+  if (tid == 0) {
+    lm_mbar_init(&stage_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
   const int p0 = blockIdx.x * chunk;
-  const int p1 = min(p0 + chunk, total_pairs);
+  const int n_pairs = min(p0 + chunk, total_pairs) - p0;
+  uint32_t phase = 0;
 
-  for (int p = p0; p < p1; ++p) {
-    const int b = p / pairs_per_seg;
-    const int tA = 2 * (p - b * pairs_per_seg);
-    const bool hasB = (tA + 1) < T;
-    const float* seg = audio + (size_t)b * L;
-    const int64_t remain = total_samples - (int64_t)b * L;   // waveform mode: the last segment may be partial
+  // (segment, pair-in-segment) of the NEXT pair to request, advanced incrementally (one division per CTA)
+  int nb = p0 / pairs_per_seg, ntp = p0 - nb * pairs_per_seg;
+  // request the samples of pair (nb, ntp) into the stage (which must be free) and advance; returns the pair's
+  // geometry for later consumption.  `bulk`: ONE aligned bulk copy (interior pair, both frames present, 16-byte
+  // aligned window inside the buffer); `off` = frame A's offset in the staged window
+  struct Geo { int b, tA, off; bool hasB, bulk; };
+  auto request_next = [&]() {
+    Geo g;
+    g.b = nb;
+    g.tA = 2 * ntp;
+    g.hasB = (g.tA + 1) < T;
+    const int64_t seg0 = (int64_t)nb * L;
+    const int64_t remain = total_samples - seg0;               // waveform mode: the last segment may be partial
     const int valid = remain >= L ? L : (remain > 0 ? (int)remain : 0);
-    const int startA = tA * hop - LM_NFFT / 2;
-    const int startB = startA + hop;
+    const int startA = g.tA * hop - LM_NFFT / 2;
+    const int64_t gi = seg0 + startA;                          // global sample index of frame A's first sample
+    const int64_t a0 = gi & ~(int64_t)3;
+    g.off = (int)(gi - a0);
+    const int n4 = (g.off + span + 3) & ~3;
+    g.bulk = bulk_ok && g.hasB && startA >= 0 && startA + span <= valid && a0 + n4 <= total_samples;
+    if (g.bulk) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads / writes of the stage
+        lm_mbar_expect_tx(&stage_bar, (uint32_t)n4 * 4u);
+        lm_bulk_g2s(stage, audio + a0, (uint32_t)n4 * 4u, &stage_bar);
+      }
+    } else {
+      g.off = 0;
+      lm_stage_fill(tid, audio + seg0, L, valid, startA, span, stage);   // visible after the next barrier
+    }
+    if (++ntp == pairs_per_seg) { ntp = 0; ++nb; }
+    return g;
+  };
 
-    lm_pass1(tid, seg, L, valid, startA, startB, hasB, w, tb.tw1, bufA);
+  Geo g{};
+  if (n_pairs > 0) {
+    g = request_next();
     __syncthreads();
+  }
+  for (int i = 0; i < n_pairs; ++i) {
+    if (g.bulk) {
+      lm_mbar_wait(&stage_bar, phase);
+      phase ^= 1;
+    }
+    lm_pass1(tid, stage + g.off, hop, g.hasB, w, tw, bufA);
+    __syncthreads();                      // bufA complete; the stage is free again
+    const Geo cur = g;
+    if (i + 1 < n_pairs) g = request_next();
     lm_pass2(tid, tb.tw2, bufA, bufB);
     __syncthreads();
     lm_pass3_mag(tid, bufB, mags, take_sqrt);
     __syncthreads();
-    float* outA = out + ((size_t)b * T + tA) * n_out;
-    float* outB = hasB ? outA + n_out : nullptr;
+    float* outA = out + ((size_t)cur.b * T + cur.tA) * n_out;
+    float* outB = cur.hasB ? outA + n_out : nullptr;
     if (!spec)
       lm_mel_log(tid, tb, n_out, oc, mags, outA, outB);
     else
       lm_spec_log(tid, spec_bin0, n_out, oc, mags, outA, outB);
-    __syncthreads();   // mags alias bufA, which the next pair's pass 1 overwrites
+    // no barrier here: the next pair's pass 1 / pass 2 touch the stage, bufA and bufB only, and two barriers separate
+    // this output stage from the next write of `mags` (and a cooperative stage fill from its first read)
   }
 }
 
@@ -113,6 +198,8 @@ extern "C" int ymt3_frontend_create(const ymt3_audio_cfg_t* cfg, const float* wi
   FE_UPLOAD(fe->d_mel_off, off, int);
   FE_UPLOAD(fe->d_mel_meta, ht.meta, int2);
   FE_UPLOAD(fe->d_mel_w, wts, float);
+  FE_UPLOAD(fe->d_rec_w, ht.rec_w, float4);
+  fe->rec_ok = ht.rec_ok;
 #undef FE_UPLOAD
   *out = fe;
   return YMT3_OK;
@@ -127,6 +214,7 @@ extern "C" int ymt3_frontend_destroy(ymt3_frontend_t* fe) {
   cudaFree(fe->d_mel_off);
   cudaFree(fe->d_mel_meta);
   cudaFree(fe->d_mel_w);
+  cudaFree(fe->d_rec_w);
   cudaFree(fe->d_stage_in);
   cudaFree(fe->d_stage_out);
   free(fe);
@@ -177,17 +265,31 @@ static int logmel_launch(ymt3_frontend_t* fe, const float* audio_dev, int64_t to
   const int64_t total64 = B * (int64_t)pairs_per_seg;
   YMT3_REQUIRE(total64 < (1ll << 31), "logmel: too many frames in one call");
   const int total = (int)total64;
-  // chunk consecutive frame pairs of a segment onto one CTA (L1 reuse of the
-  // 16x-overlapping audio) while keeping >= 2 waves of 6 CTAs/SM when possible.
-  const int target_ctas = ymt3_num_sms() * 6 * 2;
+  // a CTA walks `chunk` consecutive frame pairs (per-thread constants and the staging pipeline are amortised over
+  // the run) while the grid keeps >= 3 waves of 4 CTAs / SM when the batch allows
+  const int target_ctas = ymt3_num_sms() * 4 * 3;
   int chunk = total / target_ctas;
   if (chunk < 1) chunk = 1;
-  if (chunk > 8) chunk = 8;
+  if (chunk > 16) chunk = 16;
   const int grid = ymt3_div_up(total, chunk);
-  LmTables tb{fe->d_window, fe->d_tw1, fe->d_tw2, fe->d_mel_first, fe->d_mel_off, fe->d_mel_meta, fe->d_mel_w};
-  ymt3_logmel_kernel<<<grid, LM_THREADS, 0, (cudaStream_t)stream>>>(
+  const size_t stage_bytes = (size_t)(fe->cfg.hop_length + LM_NFFT + 4) * sizeof(float);
+  {   // static 43.8 KB + dynamic stage exceed the 48 KB default: opt in (per device, grown with the hop)
+    static int attr_hop[64] = {0};
+    int dev = 0;
+    YMT3_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || attr_hop[dev] < fe->cfg.hop_length) {
+      YMT3_CUDA_CHECK(cudaFuncSetAttribute(ymt3_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+      if (dev >= 0 && dev < 64) attr_hop[dev] = fe->cfg.hop_length;
+    }
+  }
+  // bulk copies need 16-byte aligned global addresses: the window start is rounded down to a multiple of 4 samples
+  // relative to the buffer, so the buffer itself must be 16-byte aligned (else every pair takes the cooperative fill)
+  const int bulk_ok = (((uintptr_t)audio_dev) & 15) == 0;
+  LmTables tb{fe->d_window, fe->d_tw1, fe->d_tw2, fe->d_mel_first, fe->d_mel_off, fe->d_mel_meta, fe->d_mel_w,
+              fe->d_rec_w, fe->rec_ok};
+  ymt3_logmel_kernel<<<grid, LM_THREADS, stage_bytes, (cudaStream_t)stream>>>(
       tb, audio_dev, total_samples, out_dev, (int)L, T, fe->cfg.hop_length, pairs_per_seg, chunk, total,
-      fe->cfg.codec, fe->n_out, fe->cfg.spec_bin0, fe->cfg.power_mode, fe->cfg.log_eps);
+      fe->cfg.codec, fe->n_out, fe->cfg.spec_bin0, fe->cfg.power_mode, fe->cfg.log_eps, bulk_ok);
   YMT3_CUDA_CHECK(cudaGetLastError());
   return YMT3_OK;
 }

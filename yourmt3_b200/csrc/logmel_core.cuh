@@ -32,6 +32,7 @@
 #define LM_S3 274                 // pass-2 output plane stride [n3][k1*17+k2]
 #define LM_SZ 272                 // pass-3 output plane stride [k3][k1*17+k2]
 #define LM_BUF_ELEMS 2192         // >= max(16*129, 8*274, 8*272)
+#define LM_MEL_NV 3               // float4 weight vectors per fixed-width mel filter record (<= 12 bins per filter)
 #define LM_MAG_ELEMS 1092         // interleaved (magA, magB) float2 per bin, padded: addr(bin) = bin + (bin >> 4)
 
 struct LmTables {
@@ -42,6 +43,11 @@ struct LmTables {
   const int*    mel_off;    // [n_mels+1] prefix offsets into mel_w
   const int2*   mel_meta;   // [n_mels]   (first | count << 16, offset)
   const float*  mel_w;      // packed nonzero weights, ascending bin order
+  // fixed-width filter records for banks whose filters span <= 4 * LM_MEL_NV bins (the 512-band HTK bank: <= 11):
+  // rec_w[v][m] = weights 4v..4v+3 of filter m (zero padded), so the weight loads do not depend on the meta load and
+  // a thread issues the loads of two filters at once.  rec_ok == 0: wider bank, generic per-filter loop.
+  const float4* rec_w;      // [LM_MEL_NV][n_mels]
+  int           rec_ok;
 };
 
 // Complex arithmetic on (re, im) register pairs.  On sm_100a every helper is ONE packed fp32 instruction
@@ -80,12 +86,15 @@ YMT3_HD float2 lm_add_pi(float2 a, float2 b) {
   return make_float2(a.x - b.y, a.y + b.x);
 #endif
 }
-// a * w = (a.x w.x - a.y w.y, a.x w.y + a.y w.x) = a.x * (w.x, w.y) + a.y * (-w.y, w.x)
+// a * w = (a.x w.x - a.y w.y, a.x w.y + a.y w.x) = w.x * (a.x, a.y) + w.y * (-a.y, a.x): in THIS form ptxas folds the
+// swap + half negation of `a` and both scalar broadcasts into operand modifiers (FMUL2 a, w.x.F32; FFMA2
+// -a.LO_HI.NP, w.y.F32, t): exactly two instructions; the forms that swizzle the twiddle instead cost a scalar FADD
+// and a MOV per product (checked in SASS).
 YMT3_HD float2 lm_cmul(float2 a, float2 w) {
 #if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
-  return __ffma2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x), __fmul2_rn(make_float2(a.x, a.x), w));
+  return __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
 #else
-  return make_float2(fmaf(a.y, -w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));
+  return make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.x, w.y, a.y * w.x));
 #endif
 }
 // (x * s, y * s)
@@ -175,60 +184,53 @@ YMT3_HD void lm_tw_powers(float2 w1, float2 w2, float2 w4, float2 w8, float2 (&p
   p[15] = lm_cmul(w8, p[7]);
 }
 
-// pass 1: load frame A (real) and frame B (imag), window, radix-16 over n1, twiddle.
-// seg: this segment's L samples. startA/startB: index of sample n=0 of each frame
-// in un-padded coordinates (may be negative / beyond L -> reflect).
-// tw1: [16][128] table W_2048^(m*k1) (L1-resident; rebuilding the powers in registers was measured slower:
-// +130 FP instructions and +16 registers per thread cost more than the 15 loads they save)
-// valid <= L: number of samples of this segment that exist (waveform tail); samples in [valid, L) read as 0
-// (= slice_padded_array zero padding fused into the load), reflection still happens at the segment length L.
+// Staging: the hop + 2048 samples [startA, startA + hop + 2048) that frames A and B of a pair cover are staged ONCE
+// in shared memory.  Interior pairs (no padding involved): one elected thread issues a 1-D bulk async copy
+// (cp.async.bulk, TMA engine) for the NEXT pair right after the pass-1 barrier, so the global-memory latency hides
+// under passes 2-3 of the current pair (logmel.cu).  Edge pairs (reflect padding at the segment ends, zero-padded
+// waveform tail, misaligned buffers): the CTA fills the buffer itself with this function - also the path the host
+// emulation takes for every pair.
+// seg: this segment's L samples. startA: index of sample n = 0 of frame A in un-padded coordinates (may be negative /
+// beyond L -> reflect, torch/functional.py:675-680).  valid <= L: number of samples of this segment that exist
+// (waveform tail); samples in [valid, L) read as 0 (= slice_padded_array zero padding fused into the load),
+// reflection still happens at the segment length L.
 YMT3_HD float lm_ld(const float* __restrict__ seg, int i, int L, int valid) {
   i = lm_reflect(i, L);
-  return i < valid ? seg[i] : 0.f;
+  return (i >= 0 && i < valid) ? seg[i] : 0.f;
 }
-YMT3_HD void lm_pass1(int tid, const float* __restrict__ seg, int L, int valid, int startA, int startB,
-                      bool hasB, const float (&w)[16], const float2* __restrict__ tw1, float2* __restrict__ bufA) {
+YMT3_HD void lm_stage_fill(int tid, const float* __restrict__ seg, int L, int valid, int startA, int count,
+                           float* __restrict__ stage) {
+  for (int i = tid; i < count; i += LM_THREADS) stage[i] = lm_ld(seg, startA + i, L, valid);
+}
+
+// pass 1: frame A (real) and frame B (imag) from the staged samples (fa[n] = frame A sample n, frame B = fa + hop),
+// window, radix-16 over n1, twiddle W_2048^(tid*k1) from the thread's REGISTERS (tw[k1], loop-invariant: the r01 / v3
+// kernels re-read 15 table entries per pair through an L1 that the 200+ KB of shared memory leaves at 18 KB).
+YMT3_HD void lm_pass1(int tid, const float* __restrict__ fa, int hop, bool hasB, const float (&w)[16],
+                      const float2 (&tw)[16], float2* __restrict__ bufA) {
   float2 v[16];
-  const bool interior = (startA >= 0) && (startB + LM_NFFT <= valid);
-  if (startB - startA == 128) {
-    // hop == 128: frame B sample (n1) == frame A sample (n1 + 1): 17 loads feed both frames
+  if (hop == 128) {
+    // frame B sample (n1) == frame A sample (n1 + 1): 17 loads feed both frames
     float xs[17];
-    if (interior) {
 #pragma unroll
-      for (int n1 = 0; n1 < 17; ++n1) xs[n1] = seg[startA + 128 * n1 + tid];
-    } else {
-#pragma unroll
-      for (int n1 = 0; n1 < 17; ++n1) xs[n1] = lm_ld(seg, startA + 128 * n1 + tid, L, valid);
-    }
+    for (int n1 = 0; n1 < 17; ++n1) xs[n1] = fa[128 * n1 + tid];
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) v[n1] = lm_scale2(xs[n1], xs[n1 + 1], w[n1]);
-    if (!hasB) {   // odd frame count: the last pair has no second frame (uniform, rare)
-#pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) v[n1].y = 0.f;
-    }
-  } else if (interior) {
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-      int n = 128 * n1 + tid;
-      float xa = seg[startA + n];
-      float xb = hasB ? seg[startB + n] : 0.f;
-      v[n1] = lm_scale2(xa, xb, w[n1]);
-    }
   } else {
+    const float* fb = fa + hop;
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-      int n = 128 * n1 + tid;
-      float xa = lm_ld(seg, startA + n, L, valid);
-      float xb = hasB ? lm_ld(seg, startB + n, L, valid) : 0.f;
-      v[n1] = lm_scale2(xa, xb, w[n1]);
-    }
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = lm_scale2(fa[128 * n1 + tid], fb[128 * n1 + tid], w[n1]);
+  }
+  if (!hasB) {   // odd frame count: the last pair has no second frame (uniform, rare)
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) v[n1].y = 0.f;
   }
   lm_fft16(v);
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    int k1 = (r >> 2) + 4 * (r & 3);
+    const int k1 = (r >> 2) + 4 * (r & 3);
     float2 o = v[r];
-    if (k1 != 0) o = lm_cmul(o, tw1[k1 * 128 + tid]);
+    if (k1 != 0) o = lm_cmul(o, tw[k1]);
     bufA[k1 * LM_S1 + tid] = o;
   }
 }
@@ -267,7 +269,9 @@ YMT3_HD float lm_fast_sqrt(float x) {
 }
 YMT3_HD float lm_fast_log2(float x) {
 #if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
-  return __log2f(x);   // lg2.approx: relative error 2^-22
+  float y;             // lg2.approx.ftz: relative error 2^-22; the argument is clamped above any denormal
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 #else
   return log2f(x);
 #endif
@@ -355,21 +359,66 @@ YMT3_HD LmOut lm_out_consts(int codec_spec, int power_mode, float eps) {
 }
 YMT3_HD float lm_out(float v, const LmOut& o) { return fmaf(o.c1, lm_fast_log2(fmaxf(v, o.floor)), o.c0); }
 
-// mel projection + log for both frames. Filter m: sum_j mel_w[off+j] * mag[first+j] (banded filterbank).
+// Mel projection (banded filterbank: sum_j mel_w[off+j] * mag[first+j]) + log for both frames, a thread per filter.
+// Fast path (rec_ok): fixed-width records, the loads of TWO filters (2 meta + 6 float4, mutually independent) are
+// issued before either is consumed, the bins are walked in groups of four with one (near warp-uniform) test per group;
+// the r01 loop had a dependent meta -> weight -> accumulate chain per bin and ~450 warp instructions per pair.
+YMT3_HD float2 lm_mel_filter(int meta, const float4 (&wv)[LM_MEL_NV], const float2* __restrict__ mags) {
+  const int first = meta & 0xffff, cnt = meta >> 16;
+  const float2* pa = mags + lm_magaddr(first);
+  const float2* pb = pa + 1;                // lm_magaddr inserts one pad slot after every 16 bins
+  const int skip = 16 - (first & 15);       // bins j >= skip sit one slot further
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int v = 0; v < LM_MEL_NV; ++v) {
+    if (4 * v < cnt) {
+      const float wq[4] = {wv[v].x, wv[v].y, wv[v].z, wv[v].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = 4 * v + q;            // weights beyond cnt are zero; the slots read stay inside `mags`
+        const float2 mg = (j < skip ? pa : pb)[j];
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+        acc = __ffma2_rn(make_float2(wq[q], wq[q]), mg, acc);
+#else
+        acc = make_float2(fmaf(wq[q], mg.x, acc.x), fmaf(wq[q], mg.y, acc.y));
+#endif
+      }
+    }
+  }
+  return acc;
+}
 YMT3_HD void lm_mel_log(int tid, const LmTables& tb, int n_mels, const LmOut& oc,
                         const float2* __restrict__ mags, float* __restrict__ outA, float* __restrict__ outB) {
-  for (int m = tid; m < n_mels; m += LM_THREADS) {
+  if (tb.rec_ok) {
+    for (int m0 = tid; m0 < n_mels; m0 += 2 * LM_THREADS) {
+      const int m1 = m0 + LM_THREADS;
+      const bool two = m1 < n_mels;
+      const int meta0 = tb.mel_meta[m0].x, meta1 = two ? tb.mel_meta[m1].x : 0;
+      float4 w0[LM_MEL_NV], w1[LM_MEL_NV];
+#pragma unroll
+      for (int v = 0; v < LM_MEL_NV; ++v) {
+        w0[v] = tb.rec_w[v * n_mels + m0];
+        w1[v] = two ? tb.rec_w[v * n_mels + m1] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const float2 a0 = lm_mel_filter(meta0, w0, mags);
+      outA[m0] = lm_out(a0.x, oc);
+      if (outB) outB[m0] = lm_out(a0.y, oc);
+      if (two) {
+        const float2 a1 = lm_mel_filter(meta1, w1, mags);
+        outA[m1] = lm_out(a1.x, oc);
+        if (outB) outB[m1] = lm_out(a1.y, oc);
+      }
+    }
+    return;
+  }
+  for (int m = tid; m < n_mels; m += LM_THREADS) {   // generic bank (filters wider than 4 * LM_MEL_NV bins)
     const int2 meta = tb.mel_meta[m];
     const int first = meta.x & 0xffff, cnt = meta.x >> 16, o0 = meta.y;
     float2 acc = make_float2(0.f, 0.f);
     for (int j = 0; j < cnt; ++j) {
       const float wgt = tb.mel_w[o0 + j];
       const float2 mg = mags[lm_magaddr(first + j)];
-#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
-      acc = __ffma2_rn(make_float2(wgt, wgt), mg, acc);
-#else
       acc = make_float2(fmaf(wgt, mg.x, acc.x), fmaf(wgt, mg.y, acc.y));
-#endif
     }
     outA[m] = lm_out(acc.x, oc);
     if (outB) outB[m] = lm_out(acc.y, oc);

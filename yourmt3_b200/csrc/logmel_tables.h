@@ -11,6 +11,8 @@ struct LmHostTables {
   std::vector<int> first, off;
   std::vector<int2> meta;   // (first | count << 16, offset)
   std::vector<float> wts;
+  std::vector<float4> rec_w;  // fixed-width filter records (LmTables::rec_w), [LM_MEL_NV][n_mels]
+  int rec_ok = 0;
   int n_out = 0;
 };
 
@@ -66,6 +68,27 @@ static inline const char* lm_build_host_tables(const ymt3_audio_cfg_t* cfg, cons
     const int cnt = t.off[m + 1] - t.off[m];
     if (t.first[m] > 0xffff || cnt > 0x7fff) return "mel filter too wide";
     t.meta[m] = make_int2(t.first[m] | (cnt << 16), t.off[m]);
+  }
+  // fixed-width filter records (logmel_core.cuh: lm_mel_log fast path) when no filter is wider than 4 * LM_MEL_NV bins
+  // and the zero-padded tail of every record stays inside the magnitude buffer
+  {
+    const size_t M = t.first.size();
+    bool ok = cfg->codec == YMT3_CODEC_MELSPEC;
+    for (size_t m = 0; ok && m < M; ++m) {
+      const int cnt = t.off[m + 1] - t.off[m];
+      // the walk reads whole groups of four bins: up to 3 slots past the filter's last bin, i.e. at most bins
+      // 1025..1027, which map inside the magnitude buffer and are zeroed once per CTA (logmel.cu)
+      if (cnt > 4 * LM_MEL_NV || t.first[m] + 4 * ((cnt + 3) / 4) > LM_NBINS + 3) ok = false;
+    }
+    t.rec_ok = ok ? 1 : 0;
+    t.rec_w.assign(ok ? (size_t)LM_MEL_NV * M : 1, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (size_t m = 0; ok && m < M; ++m) {
+      float w[4 * LM_MEL_NV] = {0.f};
+      const int cnt = t.off[m + 1] - t.off[m];
+      for (int j = 0; j < cnt; ++j) w[j] = t.wts[(size_t)t.off[m] + j];
+      for (int v = 0; v < LM_MEL_NV; ++v)
+        t.rec_w[(size_t)v * M + m] = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+    }
   }
   return nullptr;
 }

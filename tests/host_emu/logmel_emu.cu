@@ -56,8 +56,11 @@ extern "C" __attribute__((visibility("default"))) int lm_emu_run_wave(const ymt3
       float* outA = out + ((size_t)b * T + tA) * n_out;
       float* outB = hasB ? outA + n_out : nullptr;
       for (int tid = 0; tid < LM_THREADS; ++tid) {
-        if (cfg->codec == YMT3_CODEC_MELSPEC)
-          lm_mel_log(tid, tb, n_out, oc, mags.data(), outA, outB);
+        if (cfg->codec == YMT3_CODEC_MELSPEC) {
+          LmMelRec rec;
+          lm_mel_prefetch(tid, tb, n_out, rec);
+          lm_mel_log(tid, tb, n_out, oc, rec, mags.data(), outA, outB);
+        }
         else
           lm_spec_log(tid, cfg->spec_bin0, n_out, oc, mags.data(), outA, outB);
       }

@@ -143,11 +143,13 @@ ymt3_logmel_kernel(LmTables tb, const float* __restrict__ audio, int64_t total_s
     lm_pass2(tid, tb.tw2, bufA, bufB);
     __syncthreads();
     lm_pass3_mag(tid, bufB, mags, take_sqrt);
+    LmMelRec rec;
+    if (!spec) lm_mel_prefetch(tid, tb, n_out, rec);   // table loads in flight across the barrier
     __syncthreads();
     float* outA = out + ((size_t)cur.b * T + cur.tA) * n_out;
     float* outB = cur.hasB ? outA + n_out : nullptr;
     if (!spec)
-      lm_mel_log(tid, tb, n_out, oc, mags, outA, outB);
+      lm_mel_log(tid, tb, n_out, oc, rec, mags, outA, outB);
     else
       lm_spec_log(tid, spec_bin0, n_out, oc, mags, outA, outB);
     // no barrier here: the next pair's pass 1 / pass 2 touch the stage, bufA and bufB only, and two barriers separate
@@ -266,11 +268,13 @@ static int logmel_launch(ymt3_frontend_t* fe, const float* audio_dev, int64_t to
   YMT3_REQUIRE(total64 < (1ll << 31), "logmel: too many frames in one call");
   const int total = (int)total64;
   // a CTA walks `chunk` consecutive frame pairs (per-thread constants and the staging pipeline are amortised over
-  // the run) while the grid keeps >= 3 waves of 4 CTAs / SM when the batch allows
-  const int target_ctas = ymt3_num_sms() * 4 * 3;
-  int chunk = total / target_ctas;
+  // the run).  All CTAs cost the same, so the grid is sized to a WHOLE number of waves of the 4 x SMs resident CTAs:
+  // k waves of at most 20 pairs each (728 segments x 55 pairs: 2503 CTAs of 16 pairs were 4.2 waves = 5 rounds;
+  // 2356 CTAs of 17 are 3.98)
+  const int slots = ymt3_num_sms() * 4;
+  const int waves = ymt3_div_up(total, (int64_t)slots * 20);
+  int chunk = ymt3_div_up(total, (int64_t)slots * waves);
   if (chunk < 1) chunk = 1;
-  if (chunk > 16) chunk = 16;
   const int grid = ymt3_div_up(total, chunk);
   const size_t stage_bytes = (size_t)(fe->cfg.hop_length + LM_NFFT + 4) * sizeof(float);
   {   // static 43.8 KB + dynamic stage exceed the 48 KB default: opt in (per device, grown with the hop)

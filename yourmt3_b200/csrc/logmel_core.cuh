@@ -387,10 +387,39 @@ YMT3_HD float2 lm_mel_filter(int meta, const float4 (&wv)[LM_MEL_NV], const floa
   }
   return acc;
 }
-YMT3_HD void lm_mel_log(int tid, const LmTables& tb, int n_mels, const LmOut& oc,
+// Records of the first LM_MEL_PRE filters of a thread (m = tid + 128 i; 2 -> no register spills): loaded BEFORE the barrier that ends pass 3
+// (lm_mel_prefetch), so the table latency hides under the barrier wait; consumed after it (lm_mel_log).
+#define LM_MEL_PRE 2
+struct LmMelRec {
+  int meta[LM_MEL_PRE];
+  float4 w[LM_MEL_PRE][LM_MEL_NV];
+};
+YMT3_HD void lm_mel_prefetch(int tid, const LmTables& tb, int n_mels, LmMelRec& rec) {
+  if (!tb.rec_ok) return;
+#pragma unroll
+  for (int i = 0; i < LM_MEL_PRE; ++i) {
+    const int m = tid + LM_THREADS * i;
+    const bool on = m < n_mels;
+    rec.meta[i] = on ? tb.mel_meta[m].x : 0;
+#pragma unroll
+    for (int v = 0; v < LM_MEL_NV; ++v) rec.w[i][v] = on ? tb.rec_w[v * n_mels + m] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+YMT3_HD void lm_mel_log(int tid, const LmTables& tb, int n_mels, const LmOut& oc, const LmMelRec& rec,
                         const float2* __restrict__ mags, float* __restrict__ outA, float* __restrict__ outB) {
+  int m_next = tid;
   if (tb.rec_ok) {
-    for (int m0 = tid; m0 < n_mels; m0 += 2 * LM_THREADS) {
+#pragma unroll
+    for (int i = 0; i < LM_MEL_PRE; ++i) {
+      const int m = tid + LM_THREADS * i;
+      if (m < n_mels) {
+        const float2 a = lm_mel_filter(rec.meta[i], rec.w[i], mags);
+        outA[m] = lm_out(a.x, oc);
+        if (outB) outB[m] = lm_out(a.y, oc);
+      }
+    }
+    // the remaining filters, two at a time (their 8 loads are mutually independent: one exposed latency per pair)
+    for (int m0 = tid + LM_THREADS * LM_MEL_PRE; m0 < n_mels; m0 += 2 * LM_THREADS) {
       const int m1 = m0 + LM_THREADS;
       const bool two = m1 < n_mels;
       const int meta0 = tb.mel_meta[m0].x, meta1 = two ? tb.mel_meta[m1].x : 0;
@@ -411,7 +440,7 @@ YMT3_HD void lm_mel_log(int tid, const LmTables& tb, int n_mels, const LmOut& oc
     }
     return;
   }
-  for (int m = tid; m < n_mels; m += LM_THREADS) {   // generic bank (filters wider than 4 * LM_MEL_NV bins)
+  for (int m = m_next; m < n_mels; m += LM_THREADS) {   // generic bank (filters wider than 4 * LM_MEL_NV bins)
     const int2 meta = tb.mel_meta[m];
     const int first = meta.x & 0xffff, cnt = meta.x >> 16, o0 = meta.y;
     float2 acc = make_float2(0.f, 0.f);

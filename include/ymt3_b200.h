@@ -119,7 +119,10 @@ typedef struct ymt3_tensor {
  *   :46-68 (T5LayerNorm = RMSNorm).
  * Tensor names: block.{i}.layer.0.SelfAttention.{q,k,v,o}.weight, block.{i}.layer.0.layer_norm.weight,
  * block.{i}.layer.1.DenseReluDense.{wi_0,wi_1,wo}.weight, block.{i}.layer.1.layer_norm.weight,
- * final_layer_norm.weight, and (optional) pos_table (n_pos, d_model) added to inputs_embeds.
+ * final_layer_norm.weight, and (optional) pos_table (n_pos, d_model) added to inputs_embeds, and (optional)
+ * relative_bias_by_distance (num_heads, 2P-1) fp32: T5's relative attention bias (modeling_t5.py:189-268; computed in
+ * block 0, shared by all layers, :755-760) folded per distance by the host module from
+ * block.0.layer.0.SelfAttention.relative_attention_bias.weight: score(i, j) += table[h][P - 1 + (j - i)], S <= P.
  * ------------------------------------------------------------------------- */
 typedef struct ymt3_t5_cfg {
   int32_t precision;   /* YMT3_DTYPE_F32: fp32 FFMA path (token-exact); YMT3_DTYPE_BF16: tcgen05 path */
@@ -147,7 +150,9 @@ YMT3_API int ymt3_t5enc_forward(ymt3_t5enc_t* enc, const float* x_dev, int64_t B
  *   HF/models/t5/modeling_t5.py:380-408 (cross-attention layer), :269-305 (KV cache update),
  *   :1105-1110 (d_model**-0.5 logit scale when embeddings are tied).
  * Extra tensor names: embed_tokens.weight (V, d_model), lm_head.weight (V, d_model) [absent = tied],
- * block.{i}.layer.1.EncDecAttention.{q,k,v,o}.weight, block.{i}.layer.2.*, pos_table.
+ * block.{i}.layer.1.EncDecAttention.{q,k,v,o}.weight, block.{i}.layer.2.*, pos_table, and (optional)
+ * relative_bias_by_distance (num_heads, P >= max_length) fp32: self-attention bias of the query at position s over key
+ * j = table[h][s - j] (unidirectional buckets; cross-attention has no position bias, modeling_t5.py:387-408).
  * The whole loop runs on the device: KV cache, finished mask, step counter and the token
  * matrix never leave HBM; there is no host synchronisation inside ymt3_t5dec_generate.
  * ------------------------------------------------------------------------- */

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnParams p, int n_qtiles) {
     for (int i = 0; i < DPL; ++i) o[r][i] = 0.f;
   }
   const int causal_off = p.Sk - p.Sq;
+  const float* rb = p.rel_bias ? p.rel_bias + (int64_t)h * p.rel_stride + p.rel_center : nullptr;
 
   for (int k0 = 0; k0 < kv_len; k0 += TK) {
     __syncthreads();  // previous tile fully consumed (also orders the Q tile stores)
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnParams p, int n_qtiles) {
       for (int c = 0; c < KPL; ++c) {
         const int jg = k0 + lane + 32 * c;
         const bool ok = (jg < kv_len) && (!p.causal || jg <= qi + causal_off);
+        if (rb && ok && qi < p.Sq) s[r][c] += rb[jg - qi];   // T5 relative position bias (shared by all layers)
         if (!ok) s[r][c] = -INFINITY;
         tmax = fmaxf(tmax, s[r][c]);
       }
@@ -696,6 +698,16 @@ static bool try_launch_small(const AttnParams& p, cudaStream_t stream) {
 
 template <typename T>
 static int launch_attn(const AttnParams& p, cudaStream_t stream) {
+  if (p.rel_bias) {   // only the generic kernel adds the relative position bias
+    YMT3_REQUIRE(p.rope_dim == 0, "attention: relative bias and fused RoPE are exclusive");
+    const int nq = ymt3_div_up(p.Sq, 16);
+    const int64_t blocks = (int64_t)p.B * p.H * nq;
+    YMT3_REQUIRE(blocks < (1ll << 31), "attention: grid too large");
+    YMT3_REQUIRE(p.dk == 64, "attention: relative bias is implemented for head dim 64 (T5)");
+    attn_kernel<T, 64><<<(unsigned)blocks, 128, 0, stream>>>(p, nq);
+    YMT3_CUDA_CHECK(cudaGetLastError());
+    return YMT3_OK;
+  }
   if constexpr (sizeof(T) == 2) {
     if (try_launch_small_tc(p, stream) || try_launch_wide_tc(p, stream)) {
       YMT3_CUDA_CHECK(cudaGetLastError());

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(W > 4 ? 32 * W : 128, sizeof(T) == 2 ? (W > 4 
 decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ knew, const T* __restrict__ vnew,
                    int64_t new_ld, T* __restrict__ Kc, T* __restrict__ Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss,
                    const int* __restrict__ step, int fixed_len, int cap, int rows_cap, float scale, T* __restrict__ out,
-                   int64_t out_ld, int H, int64_t total) {
+                   int64_t out_ld, int H, int64_t total, const float* __restrict__ rel_bias, int rel_stride) {
   constexpr int DK = 64, NG = 4, U = 4;
   pdl_launch_dependents();
   pdl_wait();
@@ -185,6 +185,8 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
   float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  // T5 relative position bias of the single query at position `lim` (self mode): rb[dist], dist = lim - key index
+  const float* rb = (rel_bias && knew) ? rel_bias + (int64_t)h * rel_stride + lim : nullptr;
 
   // one 16-key block: scores of this group's 4 keys (8 lanes each, 3 xor-shuffles), online-softmax update.
   // MASKED = false: all 16 keys valid, straight-line code; true: the ragged last block
@@ -200,6 +202,7 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+      if (rb && base + u * NG + grp < lim) sacc += rb[-(base + u * NG + grp)];
       sc[u] = (MASKED && base + u * NG + grp >= lim) ? -INFINITY : sacc;
     }
     const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
@@ -258,6 +261,7 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
     sacc += __shfl_xor_sync(0x000000ffu, sacc, 1);
     sacc += __shfl_xor_sync(0x000000ffu, sacc, 2);
     sacc += __shfl_xor_sync(0x000000ffu, sacc, 4);
+    if (rb) sacc += rb[-lim];   // distance 0
     const float mn = fmaxf(m, sacc);
     const float corr = expf(m - mn), pu = expf(sacc - mn);
     l = l * corr + pu;
@@ -328,7 +332,8 @@ decode_attn_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ 
 
 int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* vnew, int64_t new_ld, void* Kc,
                      void* Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss, int Lmax, const int* step, int fixed_len,
-                     float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream) {
+                     float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream,
+                     const float* rel_bias, int rel_stride) {
   if (N <= 0) return YMT3_OK;
   YMT3_REQUIRE(dk == 64, "decode_attention: head dim must be 64 (got %d)", dk);
   YMT3_REQUIRE(c_ss == 64, "decode_attention: cache rows must be dense (row stride %lld != 64)", (long long)c_ss);
@@ -353,7 +358,7 @@ int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* 
   YMT3_CUDA_CHECK(ymt3_launch_pdl(decode_attn_kernel<TT, WW>, dim3((unsigned)ymt3_div_up(total, (WW > 4 ? WW : 4) / WW)), \
                                   dim3(32 * (WW > 4 ? WW : 4)), 0, stream, (const TT*)q, q_ld, (const TT*)knew,         \
                                   (const TT*)vnew, new_ld, (TT*)Kc, (TT*)Vc, c_sn, c_sh, c_ss, step, fixed_len, cap, max_len, scale, \
-                                  (TT*)out, out_ld, H, total))
+                                  (TT*)out, out_ld, H, total, rel_bias, rel_stride))
 #define YMT3_DISPATCH_DECODE_ATTN(TT)                                                                                  \
   switch (w) {                                                                                                         \
     case 1: YMT3_LAUNCH_DECODE_ATTN(TT, 1); break;                                                                     \

@@ -11,9 +11,12 @@ int embed_pos(const int* tok, const void* E, const void* pos, const int* step, v
 // q: (N, H*dk) rows with leading dim q_ld. knew/vnew (self mode) rows with leading dim new_ld or
 // null (cross mode). Kc/Vc: caches addressed as base + n*c_sn + h*c_sh + j*c_ss (+ d), element strides.
 // step: device int (self mode attends keys [0, *step]; cross mode keys [0, fixed_len)). out: (N, H*dk).
+// rel_bias (self mode, optional): T5 relative position bias per distance, (H, rel_stride) fp32: score of key j +=
+// rel_bias[h][*step - j] (HF modeling_t5.py:248-268, unidirectional buckets).
 int decode_attention(const void* q, int64_t q_ld, const void* knew, const void* vnew, int64_t new_ld, void* Kc,
                      void* Vc, int64_t c_sn, int64_t c_sh, int64_t c_ss, int Lmax, const int* step, int fixed_len,
-                     float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream);
+                     float scale, void* out, int64_t out_ld, int N, int H, int dk, int dtype, cudaStream_t stream,
+                     const float* rel_bias = nullptr, int rel_stride = 0);
 
 // The vocab-projection GEMM leaves one packed arg-max key per row (GemmParams::argmax_out, ops.cuh); this single-block
 // launch turns the keys into tokens (finished mask, EOS, forced (N, n_forced) task prefix or null), zeroes them and

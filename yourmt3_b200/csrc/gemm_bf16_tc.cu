@@ -60,6 +60,25 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, each destination's
+// mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // TMA store of one staged box (shared -> global), bulk async-group completion
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
@@ -105,6 +124,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// arrive on the barrier at this CTA-relative offset in EVERY CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -280,7 +306,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // from ~4000 to ~1500 instructions (ncu on the generic kernel: `no_inst` / `branch_resolving` stalls all over the
 // epilogue, 460 warp instructions per 32-column chunk; profiles/r01_gemm_smallk_v4_tma_store_ncu_full.txt).
 // EPI < 0: every combination decided at run time (rare shapes, convolutions, A/B switches).
-template <int BN, bool CONV, int EPI>
+// CL > 1: thread-block CLUSTER of CL CTAs along M (launch attribute).  The CTAs of a cluster work on CL vertically
+// adjacent 128-row tiles of the SAME N tile in lock step; each loads its own A tile and ONE CL-th of the W tile, which
+// TMA multicasts into the shared memory of all CL CTAs.  The mainloop of every GEMM here is bound by the L2 -> SM
+// fill (128 + BN rows of 128 bytes per k-block and CTA, see gemm_choose_bn): the cluster cuts it to 128 + BN / CL.
+// A ring slot is refilled only after the MMAs of ALL CL consumers have retired: every MMA warp commits to the slot's
+// empty barrier in all CTAs (multicast commit, barrier count CL).
+template <int BN, bool CONV, int EPI, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                     const __grid_constant__ CUtensorMap mapC, TcParams p) {
@@ -315,7 +347,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (e_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);   // one multicast commit from the MMA warp of every CTA in the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -332,7 +364,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
     } else {
       gstart[0] = 0;
-      acc = ((p.M + BM - 1) / BM) * n_tiles;
+      // clusters walk SUPER tiles: CL vertically adjacent M tiles x one N tile
+      acc = ((p.M + BM * CL - 1) / (BM * CL)) * n_tiles;
     }
     gstart[groups] = acc;
   }
@@ -344,10 +377,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive / multicast
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = gstart[groups];
+  // persistent walk: tile (CL == 1) or super-tile (CL > 1) index t = t_first, t_first + t_step, ...
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int t_first = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+  const int t_step = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
 
   // tile index -> (m0, row_end, n0, w_row0, bias offset group)
   auto decode_tile = [&](int t, int& m0, int& row_end, int& n0, int& w_row0, int& g_out) {
@@ -363,7 +402,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       row_end = p.group_offsets[g + 1];
       w_row0 = g * p.N + n0;
     } else {
-      m0 = mt * BM;
+      m0 = (mt * CL + crank) * BM;   // may lie entirely beyond M in the last super-tile: TMA zero-fills, nothing is stored
       row_end = p.M;
       w_row0 = n0;
     }
@@ -375,7 +414,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         int m0, row_end, n0, w_row0, g;
         decode_tile(t, m0, row_end, n0, w_row0, g);
         int cv_f0 = 0, cv_t = 0, cv_b = 0;
@@ -400,7 +439,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           } else {
             tma_load_2d(&mapA, &full_bar[stage], sa, kb * BK, m0);
           }
-          tma_load_2d(&mapW, &full_bar[stage], sb, kb * BK, w_row0);
+          if constexpr (CL > 1) {
+            // this CTA's CL-th of the W tile, multicast to every CTA of the cluster (mapW's box is BN / CL rows)
+            constexpr int SL = BN / CL;
+            tma_load_2d_mc(&mapW, &full_bar[stage], sb + crank * (SL * BK * 2), kb * BK, w_row0 + crank * SL, CMASK);
+          } else {
+            tma_load_2d(&mapW, &full_bar[stage], sb, kb * BK, w_row0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -415,7 +460,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     int j = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+    for (int t = t_first; t < total_tiles; t += t_step, ++j) {
       const int buf = j & 1;
       mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1) ^ 1);   // epilogue drained this accumulator buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -430,7 +475,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the 128 B swizzle row = +2 in the address field
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);                          // frees the smem slot when the MMAs retire
+          if constexpr (CL > 1) umma_commit_mc(&empty_bar[stage], CMASK);   // ... in every CTA that multicasts into it
+          else umma_commit(&empty_bar[stage]);                     // frees the smem slot when the MMAs retire
           if (kb == num_kb - 1) umma_commit(&tmem_full_bar[buf]);  // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -457,7 +503,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int stg_row = lane * stg_rb;
     const int stg_xor = tma_swizzle_xor(lane, stg_rb);   // index_maps.h
     int j = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+    for (int t = t_first; t < total_tiles; t += t_step, ++j) {
       int m0, row_end, n0, w_row0, g;
       decode_tile(t, m0, row_end, n0, w_row0, g);
       const float* bias = p.bias ? p.bias + (p.group_offsets ? (int64_t)g * p.N : 0) : nullptr;
@@ -575,6 +621,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   // ---- teardown: everyone done with TMEM, then the allocating warp frees it ----
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
@@ -655,19 +702,21 @@ struct ConvGeom {
 constexpr int EPI_PLAIN_BF16 = 0, EPI_PLAIN_F32 = 1, EPI_GATED_GELU_NEW = YMT3_ACT_GELU_NEW * 4 + 2,
               EPI_GATED_SILU = YMT3_ACT_SILU * 4 + 2;
 
-template <int BN, bool CONV, int EPI>
+template <int BN, bool CONV, int EPI, int CL>
 int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGeom& cg = ConvGeom()) {
   CUtensorMap mapA, mapW, mapC;
   memset(&mapC, 0, sizeof(mapC));
   int rc;
   const int groups = p.group_offsets ? p.num_groups : 1;
+  YMT3_REQUIRE(CL == 1 || !p.group_offsets, "gemm_bf16_tc: grouped GEMMs do not run in clusters");
   if constexpr (CONV) {
     if ((rc = make_conv_map(&mapA, p.A, cg.B, cg.T, cg.F, cg.Cin))) return rc;
   } else {
     if ((rc = make_map(&mapA, p.A, p.M, p.K, p.lda, BM))) return rc;
   }
   // grouped: weights of all groups are stacked along rows ((groups*N, K), strideW == N*ldw)
-  if ((rc = make_map(&mapW, p.W, (int64_t)p.N * groups, p.K, p.ldw, BN))) return rc;
+  // cluster: every CTA loads (and multicasts) a BN / CL-row slice of the W tile
+  if ((rc = make_map(&mapW, p.W, (int64_t)p.N * groups, p.K, p.ldw, BN / CL))) return rc;
   // bf16 outputs leave through TMA stores (full-line writes issued by one lane per 32 x 32 chunk instead of 32
   // scattered 16-byte st.global per warp instruction); YMT3_GEMM_DIRECT_STORE=1 keeps the direct stores (A/B aid)
   static const bool direct_store = getenv("YMT3_GEMM_DIRECT_STORE") != nullptr;   // (forces the generic kernel)
@@ -689,22 +738,66 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   t.row_scale = p.row_scale; t.group_offsets = p.group_offsets; t.num_groups = groups; t.out_f32 = out_dtype == YMT3_F32;
   t.conv_T = cg.T; t.conv_F = cg.F; t.conv_cblocks = CONV ? cg.Cin / BK : 0;
   static bool attr_set[64] = {false};   // per device (the attribute is per device and function)
+  static int max_clusters[64] = {0};    // co-resident clusters of this instantiation (one CTA per SM)
   int dev = 0;
   YMT3_CUDA_CHECK(cudaGetDevice(&dev));
+  const int sms = ymt3_num_sms();
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, CONV, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, CONV, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SmemLayout<BN>::TOTAL));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    int mc = sms / CL;
+    if constexpr (CL > 1) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3((unsigned)(sms / CL * CL));
+      q.blockDim = dim3(THREADS);
+      q.dynamicSmemBytes = SmemLayout<BN>::TOTAL;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_bf16_tc_kernel<BN, CONV, EPI, CL>, &q) == cudaSuccess && n > 0) mc = n < mc ? n : mc;
+      else (void)cudaGetLastError();
+    }
+    if (dev >= 0 && dev < 64) { attr_set[dev] = true; max_clusters[dev] = mc; }
   }
+  const int mclusters = (dev >= 0 && dev < 64 && max_clusters[dev] > 0) ? max_clusters[dev] : sms / CL;
   // persistent: one CTA per SM (or per tile when there are fewer tiles than SMs); in grouped mode the tile
   // count depends on device-side offsets, so all SMs are launched and idle CTAs exit after setup
-  const int64_t tiles = (int64_t)ymt3_div_up(p.M, BM) * ymt3_div_up(p.N, BN);
-  const int sms = ymt3_num_sms();
-  const int grid = p.group_offsets ? sms : (int)(tiles < sms ? tiles : sms);
+  const int64_t tiles = (int64_t)ymt3_div_up(p.M, BM * CL) * ymt3_div_up(p.N, BN);   // (super-)tiles
+  const int grid = p.group_offsets ? sms : (int)(tiles < mclusters ? tiles : mclusters) * CL;
   YMT3_REQUIRE(groups <= 32, "gemm_bf16_tc: at most 32 groups");
-  YMT3_CUDA_CHECK(ymt3_launch_pdl(gemm_bf16_tc_kernel<BN, CONV, EPI>, dim3(grid), dim3(THREADS), SmemLayout<BN>::TOTAL, stream,
-                                  mapA, mapW, mapC, t));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SmemLayout<BN>::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (ymt3_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if constexpr (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  YMT3_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, CONV, EPI, CL>, mapA, mapW, mapC, t));
   return YMT3_OK;
+}
+
+// cluster size of the non-grouped GEMMs / convolutions.  MEASURED (B200, profiles/r02_ab_gemm_cluster.txt): the 2-CTA
+// cluster with the W tile multicast is NEUTRAL on every shape of this model and on 8192^3 (1152 vs 1159 TFLOP/s;
+// decode-step GEMMs and the whole bench within noise) - the mainloop is not bound by the L2 -> SM fill that the
+// multicast halves, as round 1 had assumed.  The path stays as an A/B switch (YMT3_GEMM_CLUSTER=2), default off.
+int cluster_size(const GemmParams& p, int64_t m_tiles) {
+  static const int want = getenv("YMT3_GEMM_CLUSTER") ? atoi(getenv("YMT3_GEMM_CLUSTER")) : 1;
+  if (p.group_offsets || want < 2 || m_tiles < 2) return 1;
+  return 2;
 }
 
 }  // namespace
@@ -742,12 +835,13 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   static const bool generic_only = getenv("YMT3_GEMM_DIRECT_STORE") || getenv("YMT3_GEMM_TMA_GATED") ||
                                    getenv("YMT3_GEMM_GENERIC");   // A/B switches act on the run-time kernel
   const int code = generic_only ? -1 : p.act * 4 + (p.gated ? 2 : 0) + (out_dtype == YMT3_F32 ? 1 : 0);
-#define YMT3_TC_LAUNCH(EPI)                                                        \
-  switch (bn) {                                                                    \
-    case 256: return launch<256, false, EPI>(p, out_dtype, stream);                \
-    case 128: return launch<128, false, EPI>(p, out_dtype, stream);                \
-    case 64: return launch<64, false, EPI>(p, out_dtype, stream);                  \
-    default: return launch<32, false, EPI>(p, out_dtype, stream);                  \
+  const bool cl2 = cluster_size(p, mt) == 2;
+#define YMT3_TC_LAUNCH(EPI)                                                                                      \
+  switch (bn) {                                                                                                  \
+    case 256: return cl2 ? launch<256, false, EPI, 2>(p, out_dtype, stream) : launch<256, false, EPI, 1>(p, out_dtype, stream); \
+    case 128: return cl2 ? launch<128, false, EPI, 2>(p, out_dtype, stream) : launch<128, false, EPI, 1>(p, out_dtype, stream); \
+    case 64: return cl2 ? launch<64, false, EPI, 2>(p, out_dtype, stream) : launch<64, false, EPI, 1>(p, out_dtype, stream);   \
+    default: return cl2 ? launch<32, false, EPI, 2>(p, out_dtype, stream) : launch<32, false, EPI, 1>(p, out_dtype, stream);  \
   }
   switch (code) {
     case EPI_PLAIN_BF16: YMT3_TC_LAUNCH(EPI_PLAIN_BF16)
@@ -775,9 +869,10 @@ int conv3x3_bf16_tc(const void* x, int B, int T, int F, int Cin, const GemmParam
   YMT3_REQUIRE(p.N % 8 == 0 && p.ldc % 8 == 0 && (!p.residual || p.ldr % 8 == 0), "conv3x3_bf16_tc: Cout/ldc alignment");
   ConvGeom cg;
   cg.B = B; cg.T = T; cg.F = F; cg.Cin = Cin;
-  if (p.N % 128 == 0) return launch<128, true, -1>(p, out_dtype, stream, cg);
-  if (p.N % 64 == 0) return launch<64, true, -1>(p, out_dtype, stream, cg);
-  return launch<32, true, -1>(p, out_dtype, stream, cg);
+  const bool cl2 = cluster_size(p, M64 / BM) == 2;
+  if (p.N % 128 == 0) return cl2 ? launch<128, true, -1, 2>(p, out_dtype, stream, cg) : launch<128, true, -1, 1>(p, out_dtype, stream, cg);
+  if (p.N % 64 == 0) return cl2 ? launch<64, true, -1, 2>(p, out_dtype, stream, cg) : launch<64, true, -1, 1>(p, out_dtype, stream, cg);
+  return cl2 ? launch<32, true, -1, 2>(p, out_dtype, stream, cg) : launch<32, true, -1, 1>(p, out_dtype, stream, cg);
 }
 
 }  // namespace ymt3

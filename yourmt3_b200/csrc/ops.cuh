@@ -99,6 +99,9 @@ struct AttnParams {
   const float* rope_cos; const float* rope_sin; int rope_dim;
   int causal;        // key j allowed iff j <= i + (Sk - Sq)
   const int* kv_len; // optional per-batch valid key count (device), else Sk
+  // optional T5 relative attention bias folded per distance (HF modeling_t5.py:248-268 compute_bias): score(i, j) +=
+  // rel_bias[h * rel_stride + rel_center + (j - i)]; fp32 table; generic kernel only
+  const float* rel_bias; int rel_stride, rel_center;
 };
 int attention(const AttnParams& p, int dtype, cudaStream_t stream);
 

@@ -83,6 +83,8 @@ struct ymt3_t5enc {
   float* final_ln = nullptr;
   void* pos = nullptr;
   int n_pos = 0;
+  float* rel_bias = nullptr;   // (H, 2 * rel_P - 1) relative attention bias per distance, or null
+  int rel_P = 0;
   int64_t cap_rows = 0;
   void *x = nullptr, *h = nullptr, *qkv = nullptr, *attn = nullptr, *g = nullptr;
 };
@@ -104,6 +106,21 @@ extern "C" int ymt3_t5enc_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
         e->n_pos = (int)p->shape[0];
         // the encoder's residual stream is fp32 in both precisions (see ymt3_t5enc_forward): fp32 position table
         rc = pack_table(e->weights, (const float*)p->data, false, p->shape[0] * p->shape[1], YMT3_F32, &e->pos, 0);
+      }
+    }
+  }
+  if (!rc) {
+    // T5 relative attention bias (HF modeling_t5.py:189-268), folded per distance by the host module:
+    // relative_bias_by_distance[h][P - 1 + (j - i)], bidirectional buckets
+    if (const ymt3_tensor_t* rb = tt.find("relative_bias_by_distance")) {
+      if (rb->ndim != 2 || rb->shape[0] != cfg->num_heads || rb->shape[1] % 2 != 1) {
+        ymt3_set_error("t5enc_create: relative_bias_by_distance must be (num_heads, 2 * P - 1)");
+        rc = YMT3_ERR_INVALID;
+      } else {
+        e->rel_P = (int)((rb->shape[1] + 1) / 2);
+        void* t = nullptr;
+        rc = pack_table(e->weights, (const float*)rb->data, false, rb->shape[0] * rb->shape[1], YMT3_F32, &t, 0);
+        e->rel_bias = (float*)t;
       }
     }
   }
@@ -137,6 +154,8 @@ extern "C" int ymt3_t5enc_forward(ymt3_t5enc_t* e, const float* x_in, int64_t B,
   const int64_t M = B * S;
   YMT3_REQUIRE(M < (1ll << 31), "t5enc_forward: too many tokens");
   YMT3_REQUIRE(!e->pos || S <= e->n_pos, "t5enc_forward: sequence %lld longer than pos_table %d", (long long)S, e->n_pos);
+  YMT3_REQUIRE(!e->rel_bias || S <= e->rel_P, "t5enc_forward: sequence %lld longer than the relative bias table %d",
+               (long long)S, e->rel_P);
   cudaStream_t s = (cudaStream_t)stream;
   // bf16 precision: GEMM operands / attention in bf16 (tcgen05), the RESIDUAL STREAM x in fp32 - what torch autocast
   // does with the reference modules.  A bf16 residual stream loses ~2^-9 of |x| at every add while the layer updates
@@ -178,6 +197,8 @@ extern "C" int ymt3_t5enc_forward(ymt3_t5enc_t* e, const float* x_in, int64_t B,
     a.O = e->attn; a.o_sb = S * inner; a.o_sh = dk; a.o_ss = inner;
     a.B = (int)B; a.H = H; a.Sq = (int)S; a.Sk = (int)S; a.dk = dk;
     a.scale = 1.0f;  // T5: no 1/sqrt(d) (modeling_t5.py:308)
+    // position bias: computed in block 0 and shared by every layer (modeling_t5.py:755-760)
+    a.rel_bias = e->rel_bias; a.rel_stride = 2 * e->rel_P - 1; a.rel_center = e->rel_P - 1;
     if ((rc = attention(a, dt, s))) return rc;
     if ((rc = linear_fwd(dt, e->attn, inner, L.o, e->x, D, (int)M, 0, 0, e->x, D, 1.f, YMT3_F32, s))) return rc;
     // T5LayerFF (modeling_t5.py:146-150) with gated-GELU (:115-131)
@@ -198,6 +219,8 @@ struct ymt3_t5dec {
   float* final_ln = nullptr;
   void* pos = nullptr;
   int n_pos = 0;
+  float* rel_bias = nullptr; // (H, rel_P) self-attention relative bias per distance (query pos - key pos), or null
+  int rel_P = 0;
   void* embed = nullptr;     // (V, D) compute dtype
   Linear lm_head;            // (Vp, D), rows >= V are zero
   Linear lm_head_n;          // bf16: final_layer_norm folded in (fused RMSNorm)
@@ -299,6 +322,20 @@ extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
       } else {
         d->n_pos = (int)p->shape[0];
         rc = pack_table(d->weights, (const float*)p->data, false, p->shape[0] * p->shape[1], cfg->precision, &d->pos, 0);
+      }
+    }
+  }
+  if (!rc) {
+    // decoder self-attention relative bias (unidirectional buckets), folded per distance by the host module
+    if (const ymt3_tensor_t* rb = tt.find("relative_bias_by_distance")) {
+      if (rb->ndim != 2 || rb->shape[0] != cfg->num_heads || rb->shape[1] < cfg->max_length) {
+        ymt3_set_error("t5dec_create: relative_bias_by_distance must be (num_heads, >= max_length)");
+        rc = YMT3_ERR_INVALID;
+      } else {
+        d->rel_P = (int)rb->shape[1];
+        void* t = nullptr;
+        rc = pack_table(d->weights, (const float*)rb->data, false, rb->shape[0] * rb->shape[1], YMT3_F32, &t, 0);
+        d->rel_bias = (float*)t;
       }
     }
   }
@@ -446,7 +483,7 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
     if ((rc = normed_linear(L.ln_sa, L.qkv, L.qkv_n, sA, d->qkv, 3 * inner, 0, 0, 1.f, dt))) return rc;
     if (!(skip & 1) && (rc = decode_attention(d->qkv, 3 * inner, (char*)d->qkv + inner * es, (char*)d->qkv + 2 * inner * es, 3 * inner,
                                d->selfK[i], d->selfV[i], (int64_t)H * d->cap_L * dk, (int64_t)d->cap_L * dk, dk, Lmax + n_prefix,
-                               d->d_step, 0, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
+                               d->d_step, 0, 1.0f, d->attn, inner, (int)N, H, dk, dt, s, d->rel_bias, d->rel_P)))
       return rc;
     if ((rc = residual_linear(d->attn, inner, L.o, sB))) return rc;
     // cross-attention (modeling_t5.py:387-408)

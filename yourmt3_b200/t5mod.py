@@ -9,8 +9,10 @@
 The modules only OWN parameters; ``forward`` runs natively through the C ABI
 (``ymt3_t5enc_forward`` / ``ymt3_t5dec_generate``): hand-written sm_100a kernels, no eager
 fallback.  Position encoding: fixed absolute sinusoidal table added to ``inputs_embeds``
-(upstream ``position_encoding_type='sinusoidal'`` [RECALL]); T5's relative attention bias is
-not used.
+(upstream ``position_encoding_type='sinusoidal'`` [RECALL]) and / or T5's bucketed relative
+attention bias (``position_encoding_type='relative'`` or ``has_relative_attention_bias=True``; HF
+modeling_t5.py:189-268): block 0 owns ``relative_attention_bias.weight`` under its HF key and the
+kernels add the per-distance table to the scores of every layer.
 """
 from __future__ import annotations
 
@@ -31,6 +33,37 @@ def sinusoidal_positions(n_pos: int, d_model: int, max_timescale: float = 10000.
     inv = torch.exp(-inc * torch.arange(half, dtype=torch.float64))
     t = torch.arange(n_pos, dtype=torch.float64)[:, None] * inv[None, :]
     return torch.cat([torch.sin(t), torch.cos(t)], dim=1).to(torch.float32)
+
+
+def relative_position_bucket(rel: torch.Tensor, bidirectional: bool, num_buckets: int = 32, max_distance: int = 128):
+    """Bucket of a relative position rel = key_pos - query_pos; the same tensor ops, in the same order and dtypes,
+    as HF ``T5Attention._relative_position_bucket`` (modeling_t5.py:189-234), so the buckets are identical."""
+    ret = torch.zeros_like(rel)
+    if bidirectional:
+        num_buckets //= 2
+        ret = ret + (rel > 0).to(torch.long) * num_buckets
+        rel = torch.abs(rel)
+    else:
+        rel = -torch.min(rel, torch.zeros_like(rel))
+    max_exact = num_buckets // 2
+    is_small = rel < max_exact
+    large = max_exact + (torch.log(rel.float() / max_exact) / math.log(max_distance / max_exact)
+                         * (num_buckets - max_exact)).to(torch.long)
+    large = torch.min(large, torch.full_like(large, num_buckets - 1))
+    return ret + torch.where(is_small, rel, large)
+
+
+def relative_bias_by_distance(weight: torch.Tensor, n_pos: int, bidirectional: bool, max_distance: int = 128):
+    """HF ``compute_bias`` (modeling_t5.py:248-268) depends on (j - i) only: fold the (num_buckets, H) embedding into
+    a per-distance table for the kernels.  Encoder (bidirectional): (H, 2 n_pos - 1), entry n_pos - 1 + (j - i);
+    decoder (causal): (H, n_pos), entry i - j >= 0."""
+    dev = weight.device
+    if bidirectional:
+        rel = torch.arange(-(n_pos - 1), n_pos, dtype=torch.long, device=dev)
+    else:
+        rel = -torch.arange(0, n_pos, dtype=torch.long, device=dev)
+    bucket = relative_position_bucket(rel, bidirectional, num_buckets=weight.shape[0], max_distance=max_distance)
+    return weight.detach().float()[bucket].t().contiguous()            # (H, n)
 
 
 class T5LayerNorm(nn.Module):
@@ -57,9 +90,11 @@ class T5DenseGatedActDense(nn.Module):
 
 
 class T5LayerSelfAttention(nn.Module):
-    def __init__(self, d_model, inner):
+    def __init__(self, d_model, inner, rel_bias_heads: int = 0, num_buckets: int = 32):
         super().__init__()
         self.SelfAttention = T5Attention(d_model, inner)
+        if rel_bias_heads:   # HF: only block 0 owns the table (has_relative_attention_bias), all layers share it
+            self.SelfAttention.relative_attention_bias = nn.Embedding(num_buckets, rel_bias_heads)
         self.layer_norm = T5LayerNorm(d_model)
 
 
@@ -78,9 +113,9 @@ class T5LayerFF(nn.Module):
 
 
 class T5Block(nn.Module):
-    def __init__(self, d_model, inner, d_ff, is_decoder):
+    def __init__(self, d_model, inner, d_ff, is_decoder, rel_bias_heads: int = 0, num_buckets: int = 32):
         super().__init__()
-        layers = [T5LayerSelfAttention(d_model, inner)]
+        layers = [T5LayerSelfAttention(d_model, inner, rel_bias_heads, num_buckets)]
         if is_decoder:
             layers.append(T5LayerCrossAttention(d_model, inner))
         layers.append(T5LayerFF(d_model, d_ff))
@@ -149,12 +184,19 @@ class T5EncoderYMT3(_NativeOwner):
         self.precision = {"f32": _lib.DTYPE_F32, "bf16": _lib.DTYPE_BF16}[precision]
         d, inner = config["d_model"], config["num_heads"] * config.get("d_kv", 64)
         d_ff = d * config.get("ff_widening_factor", 2)
-        self.block = nn.ModuleList([T5Block(d, inner, d_ff, False) for _ in range(config["num_layers"])])
-        self.final_layer_norm = T5LayerNorm(d)
         pe = config.get("position_encoding_type", "sinusoidal")
+        # 'relative' (or has_relative_attention_bias=True next to another type): HF T5's bucketed relative attention
+        # bias, owned by block 0 under its HF state-dict key and shared by every layer
+        self.has_relative_attention_bias = bool(config.get("has_relative_attention_bias", pe == "relative"))
+        self.num_max_positions = num_max_positions
+        nb = config.get("relative_attention_num_buckets", 32)
+        self.block = nn.ModuleList([T5Block(d, inner, d_ff, False,
+                                            config["num_heads"] if (i == 0 and self.has_relative_attention_bias) else 0, nb)
+                                    for i in range(config["num_layers"])])
+        self.final_layer_norm = T5LayerNorm(d)
         if pe == "sinusoidal":
             self.register_buffer("pos_table", sinusoidal_positions(num_max_positions, d), persistent=False)
-        elif pe in (None, "none"):
+        elif pe in (None, "none", "relative"):
             self.pos_table = None
         else:
             raise NotImplementedError(f"position_encoding_type={pe!r}")
@@ -163,6 +205,10 @@ class T5EncoderYMT3(_NativeOwner):
         named = dict(self.named_parameters())
         if self.pos_table is not None:
             named["pos_table"] = self.pos_table
+        if self.has_relative_attention_bias:
+            w = named.pop("block.0.layer.0.SelfAttention.relative_attention_bias.weight")
+            named["relative_bias_by_distance"] = relative_bias_by_distance(
+                w, self.num_max_positions, True, self.config.get("relative_attention_max_distance", 128))
         return named
 
     def _create(self, arr, n):
@@ -194,12 +240,17 @@ class T5DecoderYMT3(nn.Module):
         self.config = dict(config)
         d, inner = config["d_model"], config["num_heads"] * config.get("d_kv", 64)
         d_ff = d * config.get("ff_widening_factor", 2)
-        self.block = nn.ModuleList([T5Block(d, inner, d_ff, True) for _ in range(config["num_layers"])])
-        self.final_layer_norm = T5LayerNorm(d)
         pe = config.get("position_encoding_type", "sinusoidal")
+        self.has_relative_attention_bias = bool(config.get("has_relative_attention_bias", pe == "relative"))
+        self.num_max_positions = num_max_positions
+        nb = config.get("relative_attention_num_buckets", 32)
+        self.block = nn.ModuleList([T5Block(d, inner, d_ff, True,
+                                            config["num_heads"] if (i == 0 and self.has_relative_attention_bias) else 0, nb)
+                                    for i in range(config["num_layers"])])
+        self.final_layer_norm = T5LayerNorm(d)
         if pe == "sinusoidal":
             self.register_buffer("pos_table", sinusoidal_positions(num_max_positions, d), persistent=False)
-        elif pe in (None, "none"):
+        elif pe in (None, "none", "relative"):
             self.pos_table = None
         else:
             raise NotImplementedError(f"position_encoding_type={pe!r}")

@@ -62,6 +62,12 @@ class DecoderRuntime(_NativeOwner):
         named = dict(self._decoder.named_parameters())
         if getattr(self._decoder, "pos_table", None) is not None:
             named["pos_table"] = self._decoder.pos_table
+        if getattr(self._decoder, "has_relative_attention_bias", False):
+            from .t5mod import relative_bias_by_distance
+            w = named.pop("block.0.layer.0.SelfAttention.relative_attention_bias.weight")
+            n = max(self._decoder.num_max_positions, self.max_length)
+            named["relative_bias_by_distance"] = relative_bias_by_distance(
+                w, n, False, self._decoder.config.get("relative_attention_max_distance", 128))
         named["embed_tokens.weight"] = self._embed.weight
         lm_w = self._lm.lm_head.weight if hasattr(self._lm, "lm_head") else self._lm.weight
         if not self.tie or lm_w.data_ptr() != self._embed.weight.data_ptr():

@@ -119,8 +119,8 @@ class FrontendWorkload:
     @property
     def ncu_traffic_bytes(self):
         # dram__bytes_read + dram__bytes_write of ymt3_logmel_kernel from `ncu --set full`
-        # (profiles/r01_logmel_v1_ncu_full.txt: 67.2 MB + 213.7 MB per launch of 512 segments), scaled to this batch
-        return int((67.20e6 + 213.67e6) / 512 * self.batch)
+        # (profiles/r02_logmel_v7_mel_b512_ncu_full.txt: 67.2 MB + 211.8 MB per launch of 512 segments), scaled to this batch
+        return int((67.21e6 + 211.82e6) / 512 * self.batch)
 
     def roofline_units(self):
         return self.batch * self.bytes_per_seg      # algorithmic bytes per launch

@@ -89,3 +89,26 @@ def test_empty_and_short_inputs():
     # silence clamps to log(eps)
     y = O.log_melspectrogram(np.zeros((1, 2049), np.float32))
     assert np.allclose(y, np.log(np.float32(1e-5)))
+
+
+def test_reference_fp32_itself_misses_1e4_on_quiet_linear_bins():
+    """Why the `spec` codec's 1e-4 bar is applied to bins within 40 dB of the frame peak (tests/util.py
+    assert_frontend_close, strict_everywhere=False): the REFERENCE'S OWN fp32 path (torchaudio Spectrogram + log on
+    CPU) differs from the float64 oracle by more than 1e-4 on isolated bins 40+ dB under the peak of harmonic audio -
+    fp32 FFT round-off amplified by the log - while it holds 1e-5 on every bin inside the 40 dB window.  Any fp32
+    implementation shares that floor; the GPU tests therefore bound the quiet bins in the LINEAR domain (2e-6 of the
+    frame peak) and apply the 1e-4 log-domain bar where the reference itself meets it."""
+    import torch
+    import torchaudio
+    from tests.util import synth_multitrack
+    x = synth_multitrack(4, seed=2)
+    sp = torchaudio.transforms.Spectrogram(n_fft=2048, hop_length=300, power=1.0)
+    ta = torch.log(torch.clamp(sp(torch.from_numpy(x))[:, 1:1025], min=1e-5)).transpose(1, 2).numpy().astype(np.float64)
+    ref = O.log_spectrogram(x, hop_length=300, window=torch.hann_window(2048).numpy(), bin0=1, n_bins=1024).astype(np.float64)
+    d = np.abs(ta - ref) / np.maximum(np.abs(ref), 1.0)
+    peak = np.exp(ref).max(axis=-1, keepdims=True)
+    big = np.exp(ref) >= 1e-2 * peak
+    lin = np.abs(np.exp(ta) - np.exp(ref)) / peak
+    assert d[big].max() < 1e-5                     # inside the window the reference is 10x better than the bar
+    assert d.max() > 1e-4                          # outside it the reference itself is beyond the bar ...
+    assert d.max() < 1e-3 and lin.max() < 2e-6     # ... by a bounded amount: the linear-domain error is tiny

@@ -39,40 +39,56 @@ def test_res3b_pre_encoder(cuda_device, native_lib, precision, tol):
     assert _err(got, ref) < tol
 
 
+def _encoder_oracle(m, x, cfg):
+    """oracle hidden states + the conditioning of every MoE routing decision it took (oracle.perceiver_tf.ROUTER_TRACE)"""
+    OPTF.ROUTER_TRACE = []
+    try:
+        with torch.no_grad():
+            ref = OPTF.perceiver_tf_encoder({k: v.cpu().float() for k, v in m.state_dict().items()}, x, cfg)
+        gaps = torch.cat([g for _, g in OPTF.ROUTER_TRACE]) if OPTF.ROUTER_TRACE else None
+    finally:
+        OPTF.ROUTER_TRACE = None
+    return ref, gaps
+
+
 @pytest.mark.parametrize("preset", ["yptf", "yptf_moe_multi"])
 def test_perceiver_tf_encoder_f32(cuda_device, native_lib, preset):
+    """fp32 path, 2 blocks.  MoE: a routing decision can only differ from the oracle's where the oracle's own gap
+    between the last selected and the first rejected expert is at fp32 round-off level; the instance (seed) is chosen
+    so that no decision is closer than 5e-6 (asserted), and then EVERY token must match to fp32 accuracy - no
+    blanket allowance for flipped tokens."""
     m = small_model(preset, "f32", blocks=2).to(cuda_device)
     cfg = m.model_cfg["encoder"]["perceiver-tf"]
     x = torch.randn(2, 7, 128, 128, generator=torch.Generator().manual_seed(2))
     got = m.encoder(inputs_embeds=x.to(cuda_device))["last_hidden_state"].cpu()
-    with torch.no_grad():
-        ref = OPTF.perceiver_tf_encoder({k: v.cpu().float() for k, v in m.state_dict().items()}, x, cfg)
+    ref, gaps = _encoder_oracle(m, x, cfg)
     assert got.shape == ref.shape == (2, 7, cfg["num_latents"], 128)
     d = (got - ref).abs() / max(1.0, float(ref.abs().max()))
     if cfg["ff_layer_type"] == "moe":
-        # a router near-tie (top-2 vs top-3 probability gap at fp32 round-off) may legitimately route one
-        # token differently; everything else must match to fp32 accuracy
-        bad_tokens = (d.amax(-1) > 5e-5).float().mean()
-        assert bad_tokens < 0.01, f"{float(bad_tokens):.4f} of tokens differ"
-        assert float(d.median()) < 1e-6
-    else:
-        assert float(d.max()) < 5e-5
+        print(f"{preset} f32: {gaps.numel()} routing decisions, min relative gap {float(gaps.min()):.2e}; max err {float(d.max()):.2e}")
+        assert float(gaps.min()) > 5e-6, "ill-conditioned routing instance: pick another seed"
+    assert float(d.max()) < 5e-6        # measured 7.3e-7 (MoE, min routing gap 3.1e-5) on B200
 
 
 def test_perceiver_tf_encoder_bf16(cuda_device, native_lib):
+    """bf16 path, 1 block (5 MoE layers).  Stated tolerances = measured on B200 (round 2, profiles/r02_ptf_tolerances.txt)
+    + margin: median element error 0.0019 of the output range (gate 0.004); a token counts as re-routed when its
+    error exceeds 0.1 of the range: measured 6.0 % of the tokens, next to 6.4 % of the oracle's routing decisions lying
+    within the bf16 perturbation (relative logit gap < 2e-2) of a tie (gate 10 %; round 1 allowed 25 %); max 0.485 of
+    the range (gate 0.6)."""
     m = small_model("yptf_moe_multi", "bf16", blocks=1).to(cuda_device)
     cfg = m.model_cfg["encoder"]["perceiver-tf"]
     x = torch.randn(2, 7, 128, 128, generator=torch.Generator().manual_seed(2))
     got = m.encoder(inputs_embeds=x.to(cuda_device))["last_hidden_state"].float().cpu()
-    with torch.no_grad():
-        ref = OPTF.perceiver_tf_encoder({k: v.cpu().float() for k, v in m.state_dict().items()}, x, cfg)
+    ref, gaps = _encoder_oracle(m, x, cfg)
     d = (got - ref).abs() / max(1.0, float(ref.abs().max()))
-    # stated bf16 tolerance: median element error < 1% of the output range; tokens whose top-k routing flips
-    # under the bf16 perturbation (router probability gaps < ~1e-2 are common with 8 near-uniform experts)
-    # legitimately differ -- they must stay a minority (< 25%) and bounded (< 0.5 of the range)
-    assert float(d.median()) < 1e-2
-    assert float((d.amax(-1) > 0.1).float().mean()) < 0.25
-    assert float(d.max()) < 0.5
+    flipped = float((d.amax(-1) > 0.1).float().mean())
+    near = float((gaps < 2e-2).float().mean())
+    print(f"yptf_moe_multi bf16 encoder: median err {float(d.median()):.4f}, max {float(d.max()):.3f}, tokens beyond 0.1 of "
+          f"the range {flipped:.4f}; routing decisions within the bf16 perturbation of a tie {near:.4f}")
+    assert float(d.median()) < 4e-3
+    assert flipped < 0.10 and flipped < 2.0 * near + 0.02      # re-routed tokens track the near-tie decisions
+    assert float(d.max()) < 0.6
 
 
 @pytest.mark.parametrize("preset", ["yptf", "yptf_moe_multi"])
@@ -140,6 +156,9 @@ def test_perceiver_tf_bf16_tensor_core_attention_matches_simt(cuda_device, nativ
     finally:
         os.environ.pop("YMT3_NO_TC_ATTN", None)
     d = (a - b).abs() / max(1.0, float(b.abs().max()))
-    # same stated bf16 tolerance as test_perceiver_tf_encoder_bf16: tiny median, MoE routing flips a bounded minority
+    flipped = float((d.amax(-1) > 0.1).float().mean())
+    print(f"tensor-core vs SIMT attention (bf16 encoder): median diff {float(d.median()):.4f}, tokens beyond 0.1: {flipped:.4f}")
+    # two bf16 evaluations of the same encoder re-route independently: measured median 0.0024, 9.3 % of the tokens
+    # beyond 0.1 of the range (about 1.5x the single-path rate of test_perceiver_tf_encoder_bf16); gates = + margin
     assert float(d.median()) < 5e-3
-    assert float((d.amax(-1) > 0.1).float().mean()) < 0.15
+    assert flipped < 0.14

@@ -28,10 +28,10 @@ class ModelWorkload:
     scaling = "weak"
     roofline_bound = "hbm"
     dominant_kernel = "decode_attn_kernel"
-    # dram__bytes_read + dram__bytes_write of ONE decode_attn_kernel launch at cache length 128 for 3328 x 6 (sequence,
-    # head) pairs, from `ncu --set full` (profiles/r01_cross_absorbed_v3_and_decode_attn_len128_ncu_full.txt, launch 2:
-    # 657.4 MB read + 11.3 MB written; algorithmic 669.6 MB)
-    NCU_DECODE_ATTN_TRAFFIC_3328x6_L128 = 657.416704e6 + 11.324672e6
+    # dram__bytes_read + dram__bytes_write of ONE decode_attn_kernel launch AT THE BENCH SHAPE (9464 x 6 (sequence, head)
+    # pairs = 728 segments x 13 channels, bf16 cache, length 128 = the mean of a 256-step decode), from `ncu --set full`
+    # (profiles/r02_decode_attn_9464x6_len128_ncu_full.txt: 1868.5 MB read + 52.5 MB written; algorithmic 1904.3 MB)
+    NCU_DECODE_ATTN_TRAFFIC_9464x6_L128 = 1868.480e6 + 52.546304e6
 
     def __init__(self, name, batch):
         self.name = name
@@ -136,9 +136,9 @@ class ModelWorkload:
             n += 1
         kern_ms, alg = tot_ms / n, tot_bytes / n
         achieved = alg / (kern_ms * 1e-3) / 1e9
-        traffic = self.NCU_DECODE_ATTN_TRAFFIC_3328x6_L128
-        if traffic is not None:
-            traffic = int(traffic * (N * H) / (3328.0 * 6) * (Lcap / 256.0) * (es / 2.0))
+        traffic = self.NCU_DECODE_ATTN_TRAFFIC_9464x6_L128
+        if traffic is not None:   # measured at 9464 x 6 / length 128 / bf16: scale factor 1 for the default workload
+            traffic = int(traffic * (N * H) / (9464.0 * 6) * (Lcap / 256.0) * (es / 2.0))
         main = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
                 "kernel": "decode_attn_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg,
@@ -149,7 +149,8 @@ class ModelWorkload:
         front = {"bound": "hbm", "achieved": f_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": f_ach / peaks["hbm_gbs"],
                  "traffic": self.ncu_traffic_bytes, "peak_source": peaks["source"], "kernel": "ymt3_logmel_kernel",
                  "kernel_ms": f_ms, "algorithmic_bytes_per_launch": self.roofline_units(), "launches_per_step": 1,
-                 "note": "compute-bound on the fp32 pipes (2048-point FFT per 128/300 new samples), see DESIGN.md 3.1"}
+                 "note": "issue / fp32-pipe bound (2048-point FFT per 128/300 new samples), see DESIGN.md 3.1 and the "
+                         "`compute` object beside this one"}
         front["compute"] = frontend_compute_bound(self.batch * self.model.feat_length, f_ms)
         return {"roofline": main, "roofline_frontend": front}
 
@@ -173,12 +174,13 @@ class ModelWorkload:
     @property
     def ncu_traffic_bytes(self):
         """dram__bytes_read + dram__bytes_write of the log-mel kernel from `ncu --set full`, scaled to this batch:
-        spec/hop-300 codec: profiles/r01_logmel_default_workload_ncu_full.txt (33.7 MB + 60.2 MB per 256 segments;
-        below the algorithmic 148.9 MB because part of the output is still resident in the 126 MB L2 when the
-        kernel ends); melspec/hop-128: profiles/r01_logmel_v1_ncu_full.txt (67.2 MB + 213.7 MB per 512 segments)."""
+        spec/hop-300 codec: profiles/r02_logmel_v7_spec_b728_ncu_full.txt (102.3 MB + 271.3 MB for 728 segments, captured
+        at the default batch; below the algorithmic 423.4 MB because part of the output is still resident in the
+        126 MB L2 when the kernel ends); melspec/hop-128: profiles/r02_logmel_v7_mel_b512_ncu_full.txt (67.2 MB + 211.8 MB
+        per 512 segments)."""
         if self.model.audio_cfg["codec"] == "spec":
-            return int((33.69e6 + 60.15e6) / 256 * self.batch)
-        return int((67.20e6 + 213.67e6) / 512 * self.batch)
+            return int((102.326e6 + 271.327e6) / 728 * self.batch)
+        return int((67.21e6 + 211.82e6) / 512 * self.batch)
 
     def roofline_units(self):
         return self.batch * self.bytes_per_seg

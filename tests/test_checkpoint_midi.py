@@ -100,3 +100,28 @@ def test_load_checkpoint_file_with_pickled_hparams(tmp_path):
         CK.load_checkpoint(m, str(p))
     missing, unexpected = CK.load_checkpoint(m, str(p), trusted=True)
     assert missing == [] and unexpected == []
+
+
+def test_midi_bytes_against_hand_assembled_file():
+    """Independent of the module's own reader: the exact bytes of a two-note file, assembled by hand from the
+    Standard MIDI File 1.0 specification (header chunk, tempo meta event FF 51 03, program change Cn, note on 9n /
+    note off 8n, variable-length delta times, end-of-track FF 2F 00).  120 bpm, 480 ticks per quarter = 960 ticks/s."""
+    from yourmt3_b200 import midi as MD
+    from yourmt3_b200.event_codec import Note
+    notes = [Note(0.0, 60, 5, False, 0.5),          # program 5: ticks 0 .. 480
+             Note(0.25, 64, 5, False, 1.0),         #            ticks 240 .. 960
+             Note(0.5, 38, 128, True)]              # drum, default duration 0.1 s: ticks 480 .. 576
+    got = MD.notes_to_midi_bytes(notes)
+    tempo = bytes.fromhex("4d54726b" "0000000b" "00ff5103" "07a120" "00ff2f00")
+    # tracks are ordered by (program, is_drum): the drum group (0, True) comes first, the program-5 group is the
+    # second group and takes the second melodic channel (index 1)
+    # drum track on channel 9: dt 480 (83 60) 99 26 64 | dt 96 (60) 89 26 00
+    drum_body = bytes.fromhex("8360992664" "60892600" "00ff2f00")
+    # melodic track on channel 1: dt 0 C1 05 | dt 0 91 3C 64 | dt 240 (81 70) 91 40 64 | dt 240 81 3C 00 | dt 480 (83 60) 81 40 00
+    mel_body = bytes.fromhex("00c105" "00913c64" "8170914064" "8170813c00" "8360814000" "00ff2f00")
+    chunk = lambda body: b"MTrk" + len(body).to_bytes(4, "big") + body
+    want = bytes.fromhex("4d546864" "00000006" "0001" "0003" "01e0") + tempo + chunk(drum_body) + chunk(mel_body)
+    assert got == want, (got.hex(), want.hex())
+    # variable-length quantities at the boundaries the specification lists
+    assert [MD._vlq(v).hex() for v in (0, 0x7F, 0x80, 0x2000, 0x3FFF, 0x4000, 0x0FFFFFFF)] == \
+        ["00", "7f", "8100", "c000", "ff7f", "818000", "ffffff7f"]

@@ -3,10 +3,10 @@
 //
 //   C[M, N] = residual + out_scale * row_scale * epi(A[M, K] @ W[N, K]^T + bias)
 //
-// Persistent CTA (one per SM) = 320 threads walking the tile list:
+// Persistent CTA (one per SM) = 64 + 32 * EPI_WARPS threads walking the tile list:
 //   warp 0     TMA producer  (one elected lane): A box {64 k, 128 m}, W box {64 k, BN n}, deep smem ring
 //   warp 1     TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma (K=16) per k-block
-//   warps 2..9 epilogue (two warps per TMEM lane quadrant, interleaved 32-column chunks):
+//   warps 2..  epilogue (EPI_GROUPS warps per TMEM lane quadrant, interleaved 32-column chunks):
 //              tcgen05.ld -> registers -> compile-time specialised epilogue math -> 16-byte stores
 // The accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the
 // MMAs of tile i+1.
@@ -22,8 +22,16 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 
-constexpr int THREADS = 320;
-constexpr int EPI_THREADS = 256;
+// epilogue warps: EPI_GROUPS warps per TMEM lane quadrant, each owning an interleaved share of the tile's 32-column
+// chunks.  The epilogue is latency-bound per warp (ncu on the K = 128 gated GEMM, profiles/r02_gemm_moe1_gated_silu_
+// ncu_full.txt: ~1400 warp instructions per warp and 128 x 256 tile at ~0.22 IPC, issue slots 47 % busy with 2.5
+// warps per scheduler).  MEASURED with EPI_GROUPS = 4 (16 epilogue warps, 576 threads): the register cap drops to 96
+// per thread, every epilogue spills (100-680 bytes) and the K = 128 gated GEMM goes 252 -> 380 us, the bench 1324 ->
+// 1416 ms (profiles/r02_experiments_not_kept.md); two groups (8 warps, 168 registers, no spills) stay.
+constexpr int EPI_GROUPS = 2;
+constexpr int EPI_WARPS = 4 * EPI_GROUPS;
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int THREADS = 64 + EPI_THREADS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -281,10 +289,11 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // epilogue staging for the TMA stores: 8 warps x STG_BOXES boxes of (32 rows x <= 128 B), 1024-byte aligned
-  static constexpr int STG_BOXES = BN == 256 ? 2 : 1;
+  // epilogue staging for the TMA stores: EPI_WARPS warps x STG_BOXES boxes of (32 rows x <= 128 B), 1024-byte aligned
+  static constexpr int CPW = BN / (32 * EPI_GROUPS) > 0 ? BN / (32 * EPI_GROUPS) : 1;   // 32-column chunks per warp
+  static constexpr int STG_BOXES = CPW > 2 ? CPW / 2 : 1;
   static constexpr int STG_WARP_BYTES = STG_BOXES * 4096;
-  static constexpr int STG_BYTES = 8 * STG_WARP_BYTES;
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int RING_BUDGET = 226 * 1024 - 2048 - STG_BYTES;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
@@ -489,14 +498,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;          // which interleaved set of 32-column chunks
-    // Each warp owns CPW ADJACENT 32-column chunks of the tile (BN = 256: four, 128: two, else one).
+    const int half = (warp - 2) >> 2;          // which share of the tile's 32-column chunks (0 .. EPI_GROUPS-1)
+    // Each warp owns CPW ADJACENT 32-column chunks of the tile (BN / (32 * EPI_GROUPS), at least one).
     // TMA-store path: the warp stages its 32 rows x (CPW * 64 B, gated: CPW * 32 B) of bf16 output in shared memory
     // in the swizzle of mapC (Swizzle<log2(row bytes / 16), 4, 3>: conflict-free 16-byte writes) and one lane issues
     // one box store (two for BN = 256: a box row is at most the 128-byte swizzle span) per tile: full 32/64/128-byte
     // row segments instead of 32 scattered 16-byte st.global per warp instruction.  A single buffer per warp
     // suffices: its previous store is a whole tile old.
-    constexpr int CPW = BN >= 64 ? BN / 64 : 1;
+    constexpr int CPW = L::CPW;
     uint8_t* stg = smem + L::STG_OFF + (warp - 2) * L::STG_WARP_BYTES;
     const int stg_rb_all = CPW * (e_gated ? 32 : 64);              // staged bytes per row, all boxes
     const int stg_rb = stg_rb_all > 128 ? 128 : stg_rb_all;        // bytes per row of one box
@@ -724,7 +733,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   //  its limiter is the epilogue math, not the stores - profiles/r01_ab_gemm_tma_store.txt)
   static const bool tma_gated = getenv("YMT3_GEMM_TMA_GATED") != nullptr;
   const int tma_store = out_dtype == YMT3_BF16 && !direct_store && (!p.gated || tma_gated);
-  const int out_row_bytes = (BN >= 64 ? BN / 64 : 1) * (p.gated ? 32 : 64);
+  const int out_row_bytes = SmemLayout<BN>::CPW * (p.gated ? 32 : 64);
   if (tma_store && (rc = make_out_map(&mapC, p.C, p.M, p.gated ? p.N / 2 : p.N, p.ldc,
                                       out_row_bytes > 128 ? 128 : out_row_bytes)))
     return rc;

@@ -66,6 +66,17 @@ if what in ("gemm", "all"):
     gemm(16384, 1152, 512, name="t5 enc qkv B=64")
     gemm(8192, 8192, 8192, name="square 8k")
 
+if what == "decode728":
+    # the GEMMs of one YPTF.MoE+Multi decode step at the default bench batch (728 segments x 13 channels)
+    M = 9464
+    gemm(M, 1152, 512, name="dec self qkv")
+    gemm(M, 512, 384, residual=True, name="dec self o+res")
+    gemm(M, 1536, 512, name="dec cross q absorbed")
+    gemm(M, 512, 1536, residual=True, name="dec cross o absorbed+res")
+    gemm(M, 2048, 512, gated=1, act=1, name="dec ffn wi")
+    gemm(M, 512, 1024, residual=True, name="dec ffn wo+res")
+    gemm(M, 600, 512, name="dec lm head")
+
 if what in ("decode", "all"):
     # the GEMMs of one YPTF.MoE+Multi decode step at B=256 (N = 3328 sequences)
     M = 3328

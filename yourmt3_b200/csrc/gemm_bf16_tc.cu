@@ -141,6 +141,61 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// ---- CTA pair (cta_group::2): one tcgen05.mma spans the two SMs of a cluster -----------------------------------------
+// shared::cluster address of `p` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+// TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are signalled on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once the pair's MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_C;\n\t"
+      "bra WAIT_LOOP_C;\n\t"
+      "DONE_C:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -284,10 +339,10 @@ __device__ __forceinline__ void epi_store(void* Cbase, const void* Rbase, int64_
   }
 }
 
-template <int BN>
+template <int BN, int CL = 1>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CL) * BK * 2;   // pair: each CTA stages half of the W tile -> a deeper ring
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue staging for the TMA stores: EPI_WARPS warps x STG_BOXES boxes of (32 rows x <= 128 B), 1024-byte aligned
   static constexpr int CPW = BN / (32 * EPI_GROUPS) > 0 ? BN / (32 * EPI_GROUPS) : 1;   // 32-column chunks per warp
@@ -315,18 +370,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // from ~4000 to ~1500 instructions (ncu on the generic kernel: `no_inst` / `branch_resolving` stalls all over the
 // epilogue, 460 warp instructions per 32-column chunk; profiles/r01_gemm_smallk_v4_tma_store_ncu_full.txt).
 // EPI < 0: every combination decided at run time (rare shapes, convolutions, A/B switches).
-// CL > 1: thread-block CLUSTER of CL CTAs along M (launch attribute).  The CTAs of a cluster work on CL vertically
-// adjacent 128-row tiles of the SAME N tile in lock step; each loads its own A tile and ONE CL-th of the W tile, which
-// TMA multicasts into the shared memory of all CL CTAs.  The mainloop of every GEMM here is bound by the L2 -> SM
-// fill (128 + BN rows of 128 bytes per k-block and CTA, see gemm_choose_bn): the cluster cuts it to 128 + BN / CL.
-// A ring slot is refilled only after the MMAs of ALL CL consumers have retired: every MMA warp commits to the slot's
-// empty barrier in all CTAs (multicast commit, barrier count CL).
+// CL == 2: CTA PAIR (`cta_group::2`, thread-block cluster of 2 along M).  The pair computes a 256 x BN super-tile with ONE
+// stream of tcgen05.mma issued by the leader (rank 0): each CTA stages its own 128 rows of A and HALF of the W tile
+// (BN / 2 rows); the tensor cores of both SMs read A from their own and the two W halves from both shared memories;
+// each CTA's 128 x BN accumulator lives in its own TMEM and is drained by its own epilogue warps.  Why: with a
+// single-CTA 128 x 256 tile every k-block costs the SM 48 KB of TMA writes + 48 KB of operand reads = 188 B / clk for
+// 512 clk of MMA against ~128 B / clk of shared-memory bandwidth (= the 71 % of cuBLAS measured on 8192^3); the pair
+// stages 32 KB and reads 32 KB per SM.  (The first round-2 attempt - same cluster, cta_group::1 MMAs, W tile
+// MULTICAST into both CTAs - halves the L2 -> SM bytes but not the shared-memory traffic, and measured neutral.)
+// Protocol: both producers signal the LEADER's full barrier (.cta_group::2 TMA loads, leader expects both CTAs'
+// bytes); the leader commits (multicast to both CTAs) onto the slot's empty barrier and the accumulator's full
+// barrier; the epilogue threads of BOTH CTAs arrive on the leader's accumulator-empty barrier.
 template <int BN, bool CONV, int EPI, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                     const __grid_constant__ CUtensorMap mapC, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CL>;
   constexpr int STAGES = L::STAGES;
   // SWIZZLE_128B operand tiles need 1024-byte aligned bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -356,11 +416,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (e_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);   // one multicast commit from the MMA warp of every CTA in the cluster
+      mbar_init(&empty_bar[i], 1);    // (pair: the leader's commit is multicast to both CTAs)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], EPI_THREADS);   // all epilogue threads arrive
+      mbar_init(&tmem_empty_bar[i], EPI_THREADS * CL);   // all epilogue threads arrive (pair: of both CTAs, on the leader's)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -379,10 +439,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     gstart[groups] = acc;
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(2 * BN)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CL == 2) {   // issued by the same logical warp of both CTAs of the pair
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(2 * BN)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(2 * BN)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -395,7 +462,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int t_first = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
   const int t_step = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
-  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
+  static_assert(CL == 1 || CL == 2, "cluster size 1 (single CTA) or 2 (CTA pair)");
 
   // tile index -> (m0, row_end, n0, w_row0, bias offset group)
   auto decode_tile = [&](int t, int& m0, int& row_end, int& n0, int& w_row0, int& g_out) {
@@ -439,20 +506,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          if constexpr (CONV) {
-            // shifted window of the input; out-of-range rows/cols are zero-filled by TMA = conv zero padding
-            const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            tma_load_4d(&mapA, &full_bar[stage], sa, cb * BK, cv_f0 + dx, cv_t + dy, cv_b);
+          if constexpr (CL == 2) {
+            // pair: own A tile + own half of the W tile (mapW's box is BN / 2 rows) into OWN shared memory, bytes
+            // signalled on the leader's barrier, which expects both CTAs' shares
+            const uint32_t lbar = mapa_u32(&full_bar[stage], 0);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+            if constexpr (CONV) {
+              const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
+              const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+              tma_load_4d_pair(&mapA, lbar, sa, cb * BK, cv_f0 + dx, cv_t + dy, cv_b);
+            } else {
+              tma_load_2d_pair(&mapA, lbar, sa, kb * BK, m0);
+            }
+            tma_load_2d_pair(&mapW, lbar, sb, kb * BK, w_row0 + crank * (BN / 2));
           } else {
-            tma_load_2d(&mapA, &full_bar[stage], sa, kb * BK, m0);
-          }
-          if constexpr (CL > 1) {
-            // this CTA's CL-th of the W tile, multicast to every CTA of the cluster (mapW's box is BN / CL rows)
-            constexpr int SL = BN / CL;
-            tma_load_2d_mc(&mapW, &full_bar[stage], sb + crank * (SL * BK * 2), kb * BK, w_row0 + crank * SL, CMASK);
-          } else {
+            mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            if constexpr (CONV) {
+              // shifted window of the input; out-of-range rows/cols are zero-filled by TMA = conv zero padding
+              const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
+              const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+              tma_load_4d(&mapA, &full_bar[stage], sa, cb * BK, cv_f0 + dx, cv_t + dy, cv_b);
+            } else {
+              tma_load_2d(&mapA, &full_bar[stage], sa, kb * BK, m0);
+            }
             tma_load_2d(&mapW, &full_bar[stage], sb, kb * BK, w_row0);
           }
           if (++stage == STAGES) {
@@ -462,16 +538,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  } else if (warp == 1 && (CL == 1 || crank == 0)) {
+    // ===================== MMA issuer (pair: the leader CTA only) =====================
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128 (pair: 256 = both CTAs' rows)
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CL) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int j = 0;
     for (int t = t_first; t < total_tiles; t += t_step, ++j) {
       const int buf = j & 1;
-      mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1) ^ 1);   // epilogue drained this accumulator buffer
+      // epilogue drained this accumulator buffer (pair: the epilogues of BOTH CTAs, arriving from across the cluster)
+      if constexpr (CL == 2) mbar_wait_cluster(&tmem_empty_bar[buf], ((j >> 1) & 1) ^ 1);
+      else mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1) ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -481,12 +559,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const uint8_t* sa = smem + stage * L::STAGE_BYTES;
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+          if constexpr (CL == 2) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the 128 B swizzle row = +2 in the address field
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          if constexpr (CL > 1) umma_commit_mc(&empty_bar[stage], CMASK);   // ... in every CTA that multicasts into it
-          else umma_commit(&empty_bar[stage]);                     // frees the smem slot when the MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[buf]);  // accumulator complete -> epilogue
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);                          // frees the slot in BOTH CTAs
+            if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[buf]);  // accumulators complete -> both epilogues
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the 128 B swizzle row = +2 in the address field
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);                          // frees the smem slot when the MMAs retire
+            if (kb == num_kb - 1) umma_commit(&tmem_full_bar[buf]);  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -495,7 +580,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue (warps 2..9) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;          // which share of the tile's 32-column chunks (0 .. EPI_GROUPS-1)
@@ -518,8 +603,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const float* bias = p.bias ? p.bias + (p.group_offsets ? (int64_t)g * p.N : 0) : nullptr;
       const int buf = j & 1;
       const int r = m0 + quad * 32 + lane;       // output row of this thread
-      mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool row_ok = r < row_end;
       // whole 32-row slab inside the tile's row range (always true without groups: TMA clips rows >= M itself;
       // a group's ragged last slab must not spill into the next group's rows -> direct stores there)
@@ -537,6 +620,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         pre = rsqrtf(tot / (float)p.K + p.norm_eps);
       }
       constexpr int NCHUNK = BN / 32;
+      // (the per-row loads above do not depend on the accumulator: they are issued before the wait)
+      mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       unsigned long long best_key = 0;   // fused greedy selection: best (logit, column) this thread produced
       const int c_first = n0 + half * CPW * 32;          // first accumulator column of this warp
       const bool stage_any = warp_tma && half * CPW < NCHUNK && c_first < p.N;   // warp-uniform
@@ -556,7 +642,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (last) {
           // all TMEM reads of this warp for this tile are done: hand the buffer back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(&tmem_empty_bar[buf]);
+          if constexpr (CL == 2) mbar_arrive_cluster(mapa_u32(&tmem_empty_bar[buf], 0));   // the LEADER's barrier
+          else mbar_arrive(&tmem_empty_bar[buf]);
         }
         if (has_chunk && row_ok) {
           const int c = n0 + ci * 32;
@@ -633,7 +720,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if constexpr (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    if constexpr (CL == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 
@@ -733,7 +823,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   //  its limiter is the epilogue math, not the stores - profiles/r01_ab_gemm_tma_store.txt)
   static const bool tma_gated = getenv("YMT3_GEMM_TMA_GATED") != nullptr;
   const int tma_store = out_dtype == YMT3_BF16 && !direct_store && (!p.gated || tma_gated);
-  const int out_row_bytes = SmemLayout<BN>::CPW * (p.gated ? 32 : 64);
+  const int out_row_bytes = SmemLayout<BN, CL>::CPW * (p.gated ? 32 : 64);
   if (tma_store && (rc = make_out_map(&mapC, p.C, p.M, p.gated ? p.N / 2 : p.N, p.ldc,
                                       out_row_bytes > 128 ? 128 : out_row_bytes)))
     return rc;
@@ -753,13 +843,13 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   const int sms = ymt3_num_sms();
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, CONV, EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SmemLayout<BN>::TOTAL));
+                                         SmemLayout<BN, CL>::TOTAL));
     int mc = sms / CL;
     if constexpr (CL > 1) {
       cudaLaunchConfig_t q = {};
       q.gridDim = dim3((unsigned)(sms / CL * CL));
       q.blockDim = dim3(THREADS);
-      q.dynamicSmemBytes = SmemLayout<BN>::TOTAL;
+      q.dynamicSmemBytes = SmemLayout<BN, CL>::TOTAL;
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeClusterDimension;
       qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
@@ -779,7 +869,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = SmemLayout<BN>::TOTAL;
+  cfg.dynamicSmemBytes = SmemLayout<BN, CL>::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
@@ -799,14 +889,18 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   return YMT3_OK;
 }
 
-// cluster size of the non-grouped GEMMs / convolutions.  MEASURED (B200, profiles/r02_ab_gemm_cluster.txt): the 2-CTA
-// cluster with the W tile multicast is NEUTRAL on every shape of this model and on 8192^3 (1152 vs 1159 TFLOP/s;
-// decode-step GEMMs and the whole bench within noise) - the mainloop is not bound by the L2 -> SM fill that the
-// multicast halves, as round 1 had assumed.  The path stays as an A/B switch (YMT3_GEMM_CLUSTER=2), default off.
+// CTA pair (cta_group::2) or single CTA?  MEASURED on B200 (profiles/r02_ab_gemm_pair.txt, r02_ab_gemm_cluster.txt):
+//   8192^3: 1152 TFLOP/s single -> 1376 TFLOP/s as a pair with a 5-deep ring (85 % of the measured cuBLAS burst, 99.5 % of
+//   its sustained figure); the same cluster with cta_group::1 MMAs and the W tile multicast: 1159 (neutral);
+//   every GEMM / convolution OF THIS MODEL (K <= 1536, one to four tiles per SM): the pair is 4-25 % SLOWER (decode-step
+//   GEMMs at M = 9464: 26.5 -> 30.1 us, conv pre-encoder 22.6 -> 24.0 ms, K = 128 projections 66 -> 82 us): two CTAs
+//   that must stay in lock step pay for every epilogue twice as long as it takes the slower one.
+// So the pair is chosen for long-K, many-tile GEMMs only; YMT3_GEMM_CLUSTER=1 / 2 forces either (A/B aid).
 int cluster_size(const GemmParams& p, int64_t m_tiles) {
-  static const int want = getenv("YMT3_GEMM_CLUSTER") ? atoi(getenv("YMT3_GEMM_CLUSTER")) : 1;
-  if (p.group_offsets || want < 2 || m_tiles < 2) return 1;
-  return 2;
+  static const int want = getenv("YMT3_GEMM_CLUSTER") ? atoi(getenv("YMT3_GEMM_CLUSTER")) : 0;
+  if (p.group_offsets || m_tiles < 2 || want == 1) return 1;
+  if (want == 2) return 2;
+  return (p.K >= 2048 && m_tiles >= 16 && p.N >= 512) ? 2 : 1;
 }
 
 }  // namespace

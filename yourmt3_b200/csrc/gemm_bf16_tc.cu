@@ -346,7 +346,9 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue staging for the TMA stores: EPI_WARPS warps x STG_BOXES boxes of (32 rows x <= 128 B), 1024-byte aligned
   static constexpr int CPW = BN / (32 * EPI_GROUPS) > 0 ? BN / (32 * EPI_GROUPS) : 1;   // 32-column chunks per warp
-  static constexpr int STG_BOXES = CPW > 2 ? CPW / 2 : 1;
+  // ONE 4 KB box per warp: a BN = 256 tile (two boxes per warp) hands them to the TMA engine one after the other
+  // through the same buffer - the 32 KB this saves buy the single-CTA 128 x 256 kernel a 4th ring stage
+  static constexpr int STG_BOXES = 1;
   static constexpr int STG_WARP_BYTES = STG_BOXES * 4096;
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int RING_BUDGET = 226 * 1024 - 2048 - STG_BYTES;
@@ -637,7 +639,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const bool has_chunk = ci < NCHUNK;
         const bool last = k == CPW - 1;         // this warp's last round for this tile
         uint32_t v[32];
+        bool box_in_flight = false;
         __syncwarp();
+        {
+          // warp-uniform: this chunk opens the warp's NEXT staging box -> hand the finished one to the TMA engine
+          const int b0k = k * (e_gated ? 32 : 64);
+          if (stage_any && b0k > 0 && b0k % stg_rb == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              const int cb = (e_gated ? (c_first >> 1) : c_first) + (b0k / stg_rb - 1) * (stg_rb >> 1);
+              if (cb < (e_gated ? (p.N >> 1) : p.N)) tma_store_2d(&mapC, stg, cb, m0 + quad * 32);
+              tma_store_commit();
+            }
+            box_in_flight = true;   // the buffer may be rewritten only after wait_read (below, after this chunk's math)
+          }
+        }
         if (has_chunk) tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + ci * 32), v);
         if (last) {
           // all TMEM reads of this warp for this tile are done: hand the buffer back to the MMA warp
@@ -645,10 +662,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if constexpr (CL == 2) mbar_arrive_cluster(mapa_u32(&tmem_empty_bar[buf], 0));   // the LEADER's barrier
           else mbar_arrive(&tmem_empty_bar[buf]);
         }
-        if (has_chunk && row_ok) {
-          const int c = n0 + ci * 32;
-          if (c < p.N) {
-            float f[32];
+        const int c = n0 + ci * 32;
+        const bool active = has_chunk && row_ok && c < p.N;   // per thread
+        float f[32];
+        if (active) {
+          {
 #pragma unroll
             for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]) * pre;
             if (bias) {
@@ -674,6 +692,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                   best_key = key > best_key ? key : best_key;
                 }
             }
+          }
+        }
+        if (box_in_flight) {   // warp-uniform: the math above ran while the TMA engine read the previous box
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        if (active) {
+          {
             const int n_out = e_gated ? min(16, (p.N - c) >> 1) : min(32, p.N - c);
             const int64_t off = (int64_t)r * p.ldc + (e_gated ? (c >> 1) : c);
             const int64_t roff = (int64_t)r * p.ldr + (e_gated ? (c >> 1) : c);
@@ -685,7 +711,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             else {
               const __nv_bfloat16* R = Rb ? static_cast<const __nv_bfloat16*>(Rb) + off : nullptr;
               const int b0 = k * (e_gated ? 32 : 64);  // byte offset of this chunk in the staged row (all boxes)
-              uint8_t* dst = stg + (b0 / stg_rb) * 4096 + stg_row;   // box, then this lane's row in it
+              uint8_t* dst = stg + stg_row;                          // this lane's row in the box
               const int u0 = (b0 % stg_rb) >> 4;                     // first 16-byte unit inside the box row
               const int sx = stg_xor;
               const float sq = epi_pack_bf16(R, f, n_out, p.ss_out != nullptr, [&](int q, const uint4& pk) {
@@ -704,8 +730,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (lane == 0) {
           const int co = e_gated ? (c_first >> 1) : c_first;       // first output column of this warp
           const int n_out_cols = e_gated ? (p.N >> 1) : p.N;
-          for (int b = 0; b * stg_rb < stg_rb_all; ++b)
-            if (co + b * (stg_rb >> 1) < n_out_cols) tma_store_2d(&mapC, stg + b * 4096, co + b * (stg_rb >> 1), m0 + quad * 32);
+          const int b = (stg_rb_all - 1) / stg_rb;   // the warp's last box (earlier ones left inside the chunk loop)
+          if (co + b * (stg_rb >> 1) < n_out_cols) tma_store_2d(&mapC, stg, co + b * (stg_rb >> 1), m0 + quad * 32);
           tma_store_commit();
         }
       }

@@ -298,6 +298,30 @@ YMT3_API int ymt3_op_linear_normfused(const void* A, int64_t lda, const void* W,
                                       const float* ss_in, int64_t chunks, float eps, void* C, int64_t ldc,
                                       const void* residual, int64_t ldr, float* ss_out, int64_t M, int64_t N, int64_t K,
                                       int32_t act, int32_t gated, float out_scale, int32_t out_dtype, void* stream);
+/* Several DEPENDENT normfused linears in ONE persistent launch (the GEMMs between two attention kernels of a decode
+ * step: [o-proj + residual -> cross-q] and [cross-o + residual -> wi (gated) -> wo + residual -> next layer's qkv]).
+ * Phase i > 0 reads what phase i - 1 wrote (its A is an earlier phase's C); every phase has the same M, bf16 in / out,
+ * fields as in ymt3_op_linear_normfused.  counters: ymt3_op_linear_chain_counters(M) device int32, zero before the
+ * first launch that uses them; `ordinal` = number of earlier launches on the same counters since they were zeroed.
+ * Result bit-identical to the same phases issued one by one through ymt3_op_linear_normfused. */
+typedef struct ymt3_chain_phase {
+  const void* A; int64_t lda;
+  const void* W; int64_t ldw;
+  const float* bias;
+  const float* ss_in; int64_t chunks; float eps;
+  void* C; int64_t ldc;
+  const void* residual; int64_t ldr;
+  float* ss_out;
+  int64_t N, K;
+  int32_t act, gated;
+  float out_scale;
+} ymt3_chain_phase_t;
+YMT3_API int64_t ymt3_op_linear_chain_counters(int64_t M);
+/* debug aid (tools/trace_chain.py): later chain launches write globaltimer stamps [CTA][16 tiles][32 events] into
+ * device_buf (>= SMs * 512 uint64, zeroed by the caller); NULL switches it off. */
+YMT3_API int ymt3_debug_chain_trace(uint64_t* device_buf);
+YMT3_API int ymt3_op_linear_chain(const ymt3_chain_phase_t* phases, int32_t n_phases, int64_t M, int32_t* counters,
+                                  int32_t ordinal, void* stream);
 /* Vocab projection with the greedy selection fused into its epilogue (the LM head of the decode step; HF
  * modeling_t5.py:1105-1110 followed by torch.argmax): logits (M, N) fp32 = out_scale * (A @ W^T + bias) are stored AND
  * every row's arg-max over columns [0, V) is left in keys[m] as  (ordered(logit) << 32) | (0xFFFFFFFF - column)  via

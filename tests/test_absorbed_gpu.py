@@ -84,3 +84,22 @@ def test_absorbed_with_task_prefix(cuda_device, native_lib):
     b = m16.inference(x, task_tokens=pfx.to(cuda_device), stop_at_eos=False).cpu()
     assert a.shape == b.shape == (2, 13, 6)
     assert float((a[..., 0] == b[..., 0]).float().mean()) >= 0.75
+
+
+def test_gemm_chain_bit_identical_absorbed(cuda_device, native_lib, monkeypatch):
+    """Absorbed (latent) cross-attention decode with the chained GEMM launches vs the separate launches: same tokens
+    and last-step logits, bit for bit (13 channels x 12 segments = 156 rows, two row tiles, the second ragged)."""
+    x = torch.from_numpy(synth_noise(12, seed=31)).unsqueeze(1).to(cuda_device)
+    out = {}
+    for mode in ("chain", "separate"):
+        if mode == "separate":
+            monkeypatch.setenv("YMT3_NO_GEMM_CHAIN", "1")
+        else:
+            monkeypatch.delenv("YMT3_NO_GEMM_CHAIN", raising=False)
+        m = small_model("yptf_moe_multi", "bf16", blocks=1, dec_layers=3, event_length=24, seed=5).to(cuda_device)
+        assert m._absorbed()
+        toks = m.inference(x, stop_at_eos=False).cpu()
+        out[mode] = (toks, m.decoder._runtime.last_logits(12 * 13, cuda_device).cpu())
+    assert len(torch.unique(out["chain"][0])) > 3
+    assert torch.equal(out["chain"][0], out["separate"][0])
+    assert torch.equal(out["chain"][1], out["separate"][1])

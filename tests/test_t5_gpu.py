@@ -200,3 +200,31 @@ def test_bf16_note_onset_f1_vs_fp32(cuda_device, native_lib):
     assert len(ref) > 0 and len(est) > 0
     assert 0.0 <= f <= 1.0
     assert float((toks["f32"][:, 0] == toks["bf16"][:, 0]).mean()) >= 0.75
+
+
+@pytest.mark.parametrize("n_rows", [7, 300])
+def test_gemm_chain_is_bit_identical(cuda_device, native_lib, monkeypatch, n_rows):
+    """The chained decode step (gemm_chain_kernel: [o-proj -> cross-q] and [cross-o -> wi -> wo -> next qkv] as ONE
+    persistent launch each, dependencies per 128-row tile) computes tile by tile what the separate launches compute:
+    tokens AND last-step logits are bit-identical with the chain on and off (YMT3_NO_GEMM_CHAIN, read when the
+    decoder runtime is created); 300 rows = 3 row tiles, the last one ragged."""
+    enc_hs = torch.randn(n_rows, 40, 512, generator=torch.Generator().manual_seed(5)).to(cuda_device)
+    out = {}
+    for mode in ("chain", "separate"):
+        if mode == "separate":
+            monkeypatch.setenv("YMT3_NO_GEMM_CHAIN", "1")
+        else:
+            monkeypatch.delenv("YMT3_NO_GEMM_CHAIN", raising=False)
+        m = ymt3.YourMT3(model_cfg=small_cfg(n_layers=3), precision="bf16")
+        ymt3.init_nondegenerate_(m, seed=0)
+        m = m.to(cuda_device)
+        toks = ymt3.task_cond_dec_generate(m.decoder, "t5", m.embed_tokens, m.lm_head, enc_hs, max_length=40,
+                                           stop_at_eos=False, precision=1)
+        out[mode] = (toks.cpu(), m.decoder._runtime.last_logits(n_rows, cuda_device).cpu())
+        # a second call on the same runtime re-zeroes the dependency counters
+        toks2 = ymt3.task_cond_dec_generate(m.decoder, "t5", m.embed_tokens, m.lm_head, enc_hs, max_length=40,
+                                            stop_at_eos=False, precision=1)
+        assert torch.equal(toks2.cpu(), out[mode][0])
+    assert len(np.unique(out["chain"][0].numpy())) > 10
+    assert torch.equal(out["chain"][0], out["separate"][0])
+    assert torch.equal(out["chain"][1], out["separate"][1])

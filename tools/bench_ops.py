@@ -77,6 +77,59 @@ if what == "decode728":
     gemm(M, 512, 1024, residual=True, name="dec ffn wo+res")
     gemm(M, 600, 512, name="dec lm head")
 
+if what == "chain728":
+    # the two GEMM chains of one YPTF.MoE+Multi decoder layer at the default bench batch, chained vs one by one
+    import ctypes
+    M = int(os.environ.get("CHAIN_M", 9464))
+    D, INNER, HZ, F = 512, 384, 1536, 1024
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *sh, sc=1.0: (torch.randn(*sh, device=dev, generator=g) * sc).bfloat16()
+    x0, attn, cz = rnd(M, D), rnd(M, INNER), rnd(M, HZ)
+    Wo, Wxq, Wxo, Wwi, Wwo, Wqkv = rnd(D, INNER, sc=.05), rnd(HZ, D, sc=.05), rnd(D, HZ, sc=.03), rnd(2 * F, D, sc=.05), rnd(D, F, sc=.03), rnd(3 * INNER, D, sc=.05)
+    s_ = torch.cuda.current_stream().cuda_stream
+    ncnt = int(lib.ymt3_op_linear_chain_counters(M))
+
+    def mk():
+        return dict(x=x0.clone(), qz=torch.empty(M, HZ, device=dev, dtype=torch.bfloat16), gbuf=torch.empty(M, F, device=dev, dtype=torch.bfloat16),
+                    qkv=torch.empty(M, 3 * INNER, device=dev, dtype=torch.bfloat16), sA=torch.zeros(M, 16, device=dev), sB=torch.zeros(M, 16, device=dev),
+                    sC=torch.zeros(M, 16, device=dev))
+
+    def phases(b, which):
+        P = _lib.ChainPhase
+        def ph(A, lda, W, C_, ldc, N, K, res=False, ss_in=None, ss_out=None, act=0, gated=0):
+            return P(A.data_ptr(), lda, W.data_ptr(), K, None, ss_in.data_ptr() if ss_in is not None else None, 16, 1e-6,
+                     C_.data_ptr(), ldc, C_.data_ptr() if res else None, ldc, ss_out.data_ptr() if ss_out is not None else None, N, K, act, gated, 1.0)
+        if which == "A":
+            return [ph(attn, INNER, Wo, b["x"], D, D, INNER, res=True, ss_out=b["sB"]),
+                    ph(b["x"], D, Wxq, b["qz"], HZ, HZ, D, ss_in=b["sB"])]
+        return [ph(cz, HZ, Wxo, b["x"], D, D, HZ, res=True, ss_out=b["sC"]),
+                ph(b["x"], D, Wwi, b["gbuf"], F, 2 * F, D, ss_in=b["sC"], act=1, gated=1),
+                ph(b["gbuf"], F, Wwo, b["x"], D, D, F, res=True, ss_out=b["sA"]),
+                ph(b["x"], D, Wqkv, b["qkv"], 3 * INNER, 3 * INNER, D, ss_in=b["sA"])]
+
+    def run_separate(ps):
+        for q in ps:
+            _lib.check(lib.ymt3_op_linear_normfused(q.A, q.lda, q.W, q.ldw, None, q.ss_in, q.chunks if q.ss_in else 0, q.eps, q.C, q.ldc,
+                                                    q.residual, q.ldr, q.ss_out, M, q.N, q.K, q.act, q.gated, 1.0, 1, s_))
+
+    for which in ("A", "B"):
+        b1, b2 = mk(), mk()
+        p1, p2 = phases(b1, which), phases(b2, which)
+        arr = (_lib.ChainPhase * len(p2))(*p2)
+        cnt = torch.zeros(ncnt, device=dev, dtype=torch.int32)
+        ordinal = [0]
+
+        def run_chain():
+            _lib.check(lib.ymt3_op_linear_chain(arr, len(p2), M, cnt.data_ptr(), ordinal[0], s_))
+            ordinal[0] += 1
+        run_separate(p1)
+        run_chain()
+        torch.cuda.synchronize()
+        same = all(torch.equal(b1[k], b2[k]) for k in b1)
+        t_sep = timeit(lambda: run_separate(p1))
+        t_ch = timeit(run_chain)
+        print(f"chain {which} M={M}: separate {t_sep:7.1f} us   chained {t_ch:7.1f} us   identical={same}", flush=True)
+
 if what in ("decode", "all"):
     # the GEMMs of one YPTF.MoE+Multi decode step at B=256 (N = 3328 sequences)
     M = 3328

@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libymt3_b200.so")
+# YMT3_B200_LIB: a differently-built copy of the SAME library (debug builds, e.g. the timeline build of tools/trace_gemm.py)
+LIB_PATH = os.environ.get("YMT3_B200_LIB") or os.path.join(_HERE, "csrc", "libymt3_b200.so")
 
 _lib = None
 _lock = threading.Lock()
@@ -36,6 +37,14 @@ class Tensor(C.Structure):
 
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("dtype", C.c_int32), ("ndim", C.c_int32),
                 ("shape", C.c_int64 * 4)]
+
+
+class ChainPhase(C.Structure):
+    """ymt3_chain_phase_t (include/ymt3_b200.h)"""
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("ldw", C.c_int64), ("bias", C.c_void_p),
+                ("ss_in", C.c_void_p), ("chunks", C.c_int64), ("eps", C.c_float), ("C", C.c_void_p), ("ldc", C.c_int64),
+                ("residual", C.c_void_p), ("ldr", C.c_int64), ("ss_out", C.c_void_p), ("N", C.c_int64), ("K", C.c_int64),
+                ("act", C.c_int32), ("gated", C.c_int32), ("out_scale", C.c_float)]
 
 
 class T5Cfg(C.Structure):
@@ -108,6 +117,9 @@ SIGNATURES = {
     "ymt3_op_attention": (_I, [C.c_int32, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, C.c_float, C.c_int32, _P]),
     "ymt3_op_linear_normfused": (_I, [_P, _I64, _P, _I64, _P, _P, _I64, C.c_float, _P, _I64, _P, _I64, _P, _I64, _I64, _I64,
                                       C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
+    "ymt3_op_linear_chain_counters": (_I64, [_I64]),
+    "ymt3_debug_chain_trace": (_I, [_P]),
+    "ymt3_op_linear_chain": (_I, [_P, C.c_int32, _I64, _P, C.c_int32, _P]),
     "ymt3_op_linear_argmax": (_I, [C.c_int32, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, C.c_float, _P, _P]),
     "ymt3_op_decode_attention": (_I, [C.c_int32, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _I64, _I64, _P]),
     "ymt3_op_cross_attn_absorbed": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),

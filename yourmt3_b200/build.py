@@ -14,12 +14,13 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "yourmt3_b200", "csrc")
-OUT = os.path.join(CSRC, "libymt3_b200.so")
-OBJ_DIR = os.path.join(ROOT, "build", "obj")
+OUT = os.environ.get("YMT3_B200_LIB") or os.path.join(CSRC, "libymt3_b200.so")
+OBJ_DIR = os.path.join(ROOT, "build", "obj_debug" if os.environ.get("YMT3_B200_LIB") else "obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include")]
+CFLAGS += os.environ.get("YMT3_EXTRA_NVCC_FLAGS", "").split()   # debug builds only (e.g. -DYMT3_GEMM_TRACE)
 
 
 def _sources():

@@ -209,6 +209,41 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 accumulator columns, NOT waited for: the caller overlaps other work and then calls tmem_wait_ld on the same array
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// wait for every outstanding TMEM load of this thread; the registers are read-write operands so that no use of them
+// can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+// debug timeline (tools/trace_chain.py, ymt3_debug_chain_trace): events < 8 in globaltimer ns, the rest in SM cycles
+static unsigned long long* g_chain_trace = nullptr;
+__device__ __forceinline__ void chain_stamp(unsigned long long* trace, int j, int e) {
+  if (trace && j < 16) {
+    unsigned long long t;
+    if (e < 8) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    else t = (unsigned long long)clock64();   // events 8.. : SM cycles (one warp's epilogue, finer than the 256 ns timer)
+    trace[((size_t)blockIdx.x * 16 + j) * 32 + e] = t;
+  }
+}
+#ifdef YMT3_GEMM_TRACE   // stamps in the single-GEMM kernel too (special build for tools/trace_gemm.py only)
+#define TC_STAMP(j, e) chain_stamp(p.trace, j, e)
+#else
+#define TC_STAMP(j, e) ((void)0)
+#endif
+
 struct TcParams {
   void* C; int64_t ldc;
   const float* bias;
@@ -219,6 +254,9 @@ struct TcParams {
   const float* row_scale;
   const float* norm_ss_in; int norm_ss_chunks; float norm_eps;   // fused RMSNorm, consumer side (ops.cuh)
   float* ss_out; int ss_out_chunks;                               // fused RMSNorm, producer side
+#ifdef YMT3_GEMM_TRACE
+  unsigned long long* trace;
+#endif
   unsigned long long* argmax_out; int argmax_n;                   // fused greedy selection (ops.cuh)
   int tma_store;   // bf16 output leaves through per-warp smem staging + TMA stores (mapC) instead of 16-byte st.global
   const int* group_offsets;
@@ -282,7 +320,7 @@ __device__ __forceinline__ float epi_pack_bf16(const __nv_bfloat16* R, const flo
     for (int j = 0; j < 4; ++j)
       if (8 * j < count) r[j] = *reinterpret_cast<const uint4*>(R + 8 * j);   // all residual loads in flight first
   }
-  float sq = 0.f;
+  float sqx = 0.f, sqy = 0.f;   // even / odd columns apart: the order of epi_chunk_lean's packed accumulator
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (8 * j >= count) break;
@@ -302,12 +340,94 @@ __device__ __forceinline__ float epi_pack_bf16(const __nv_bfloat16* R, const flo
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 v2 = __bfloat1622float2(h[q]);
-        sq = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, sq));
+        sqx = fmaf(v2.x, v2.x, sqx);
+        sqy = fmaf(v2.y, v2.y, sqy);
       }
     }
     sink(j, pk);
   }
-  return sq;
+  return sqx + sqy;
+}
+
+// ---- LEAN epilogue: the common case of the bf16 epilogue (full 32-column chunks of a non-gated, activation-free tile that
+// leaves through the TMA staging box) with the per-element work cut to the bone.  The general path spends ~290
+// warp instructions per chunk (timeline + SASS counts: profiles/r02_gemm_epilogue_timeline.txt: two scalings, scalar
+// adds / conversions, ~70 control-flow instructions), this one ~60 without and ~150 with residual + sum of squares:
+// packed f32x2 multiply / add / fma, one scale factor, no per-element predicates.  Same values as the general path
+// (IEEE mul / add / fma per element, identical summation order of the squares).
+__device__ __forceinline__ float2 bf16x2_as_f2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ float2 lean_mul2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __fmul2_rn(a, b);
+#else
+  return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+__device__ __forceinline__ float2 lean_add2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__device__ __forceinline__ float2 lean_fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+// v: 16 accumulator columns of this thread's row (one HALF of a 32-column chunk).  out = bf16(v * s + bias + residual)
+// (s = the one scale factor of the general path that is not exactly 1).  rr: the 32 residual bytes of this row segment.
+// ssacc: running (even, odd column) sums of squares of the rounded outputs of the chunk.  dst / u0 / sx: staging row,
+// first 16-byte unit (compile-time after unrolling), swizzle.
+template <bool BIAS, bool RES, bool SS>
+__device__ __forceinline__ void lean_half(const uint32_t (&v)[16], float s, const float* bias_c, const uint4 (&rr)[2],
+                                          float2& ssacc, uint32_t dst, int u0, int sx) {
+  float2 f[8];
+  const float2 a1 = make_float2(s, s);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) f[q] = lean_mul2(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), a1);
+  if constexpr (BIAS) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias_c) + q);
+      f[2 * q] = lean_add2(f[2 * q], make_float2(b.x, b.y));
+      f[2 * q + 1] = lean_add2(f[2 * q + 1], make_float2(b.z, b.w));
+    }
+  }
+  if constexpr (RES) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&rr[0]);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = lean_add2(f[q], bf16x2_as_f2(w[q]));
+  }
+  uint32_t h[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[q].x, f[q].y);
+    h[q] = *reinterpret_cast<const uint32_t*>(&b2);
+  }
+  if constexpr (SS) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float2 u = bf16x2_as_f2(h[q]);
+      ssacc = lean_fma2(u, u, ssacc);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q)   // dst: shared-space address of the staging row (st.shared, not a generic store)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)(((u0 + q) << 4) ^ sx)), "r"(h[4 * q]),
+                 "r"(h[4 * q + 1]), "r"(h[4 * q + 2]), "r"(h[4 * q + 3])
+                 : "memory");
+}
+// the residual bytes of one row segment of 16 bf16 - issued early, consumed by lean_half
+template <bool L2_ONLY>
+__device__ __forceinline__ void lean_load_res16(uint4 (&rr)[2], const __nv_bfloat16* R) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    rr[q] = L2_ONLY ? __ldcg(reinterpret_cast<const uint4*>(R) + q) : *(reinterpret_cast<const uint4*>(R) + q);
 }
 // store `count` (multiple of 8 for bf16 / 4 for f32, <= 32) consecutive outputs f[0..count) of one row (+ residual)
 // ss != null (bf16 output only): *ss = sum of squares of the bf16-rounded values stored (fused RMSNorm producer)
@@ -400,9 +520,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   int* gstart = reinterpret_cast<int*>(tmem_slot + 2);   // [num_groups + 1] tile-index prefix (grouped mode)
 
   constexpr bool GEN = EPI < 0;
-  const int e_act = GEN ? p.act : (EPI >> 2);
-  const bool e_gated = GEN ? (p.gated != 0) : (((EPI >> 1) & 1) != 0);
-  const bool e_f32 = GEN ? (p.out_f32 != 0) : ((EPI & 1) != 0);
+  // EPI_LEAN_BF16: plain bf16 output, N % 32 == 0, no groups / arg-max, TMA store: ONLY the lean chunk path is compiled
+  // (epi_chunk_lean; the host picks it whenever the shape allows - every plain GEMM of the decode step and the encoder)
+  constexpr bool LEAN = EPI >= 64;   // 64 + (bias ? 1 : 0) + (residual ? 2 : 0) + (sum of squares ? 4 : 0)
+  const int e_act = GEN ? p.act : (LEAN ? 0 : (EPI >> 2));
+  const bool e_gated = GEN ? (p.gated != 0) : (!LEAN && ((EPI >> 1) & 1) != 0);
+  const bool e_f32 = GEN ? (p.out_f32 != 0) : (!LEAN && (EPI & 1) != 0);
   const bool e_tma = GEN ? (p.tma_store != 0) : (!e_gated && !e_f32);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -459,6 +582,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(0, 7);
   const int total_tiles = gstart[groups];
   // persistent walk: tile (CL == 1) or super-tile (CL > 1) index t = t_first, t_first + t_step, ...
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
@@ -561,6 +685,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const uint8_t* sa = smem + stage * L::STAGE_BYTES;
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+          if (kb == 0) TC_STAMP(j, 2);
           if constexpr (CL == 2) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
@@ -572,7 +697,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int k = 0; k < BK / 16; ++k)  // +32 B along K inside the 128 B swizzle row = +2 in the address field
               umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
             umma_commit(&empty_bar[stage]);                          // frees the smem slot when the MMAs retire
-            if (kb == num_kb - 1) umma_commit(&tmem_full_bar[buf]);  // accumulator complete -> epilogue
+            if (kb == num_kb - 1) {
+              umma_commit(&tmem_full_bar[buf]);  // accumulator complete -> epilogue
+              TC_STAMP(j, 3);
+            }
           }
         }
         __syncwarp();
@@ -622,9 +750,109 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         pre = rsqrtf(tot / (float)p.K + p.norm_eps);
       }
       constexpr int NCHUNK = BN / 32;
+      if constexpr (LEAN) {
+        // ---- LEAN tile epilogue (lean_half): the warp's CPW * 32 columns as 16-column halves, software-pipelined: the
+        // TMEM load of half g + 1 is in flight while half g is scaled / packed / staged, and the residual bytes are
+        // fetched three halves ahead (the first three before the accumulator is complete).  Bias / residual / sum of
+        // squares are COMPILE-TIME properties of the instance and everything that depends on kernel parameters is
+        // computed once per tile: the general path re-reads parameters through the uniform datapath and branches on
+        // them ~10 times per chunk (LDCU -> UISETP -> BRA chains, the `branch_resolving` / `wait` stalls of the ncu
+        // source view), which - not TMEM or shared-memory traffic - is what a 32-column chunk's ~1000 clk were made of
+        // (leave-out experiments + timeline: profiles/r02_gemm_epilogue_timeline.txt).
+        constexpr int H = 2 * CPW;                                   // halves per warp
+        constexpr int SRB = CPW * 64 > 128 ? 128 : CPW * 64;         // bytes per staged box row
+        constexpr bool LB = (EPI & 1) != 0, LR = (EPI & 2) != 0, LS = (EPI & 4) != 0;   // bias, residual, sum of squares
+        const int c_first = n0 + half * CPW * 32;                    // first accumulator column of this warp
+        const int n_cols = p.N;
+        // number of this warp's halves that hold real columns (N % 32 == 0: always even); 0: nothing to do
+        const int nv = (warp_tma && half * CPW < NCHUNK && c_first < n_cols) ? min(H, (n_cols - c_first) >> 4) : 0;
+        // rows past the end of the tile: loads clamped to the last row, the box store clips them
+        [[maybe_unused]] const __nv_bfloat16* Rrow = nullptr;
+        [[maybe_unused]] uint4 rq[4][2];                             // residual ring: half g lives in rq[g & 3]
+        if constexpr (LR) {
+          Rrow = static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)(row_ok ? r : row_end - 1) * p.ldr + c_first;
+#pragma unroll
+          for (int g = 0; g < 3 && g < H; ++g)
+            if (g < nv) lean_load_res16<false>(rq[g], Rrow + 16 * g);
+        }
+        [[maybe_unused]] const float* bias_w = LB ? bias + c_first : nullptr;
+        [[maybe_unused]] float* ss_w = LS ? p.ss_out + (int64_t)(row_ok ? r : row_end - 1) * p.ss_out_chunks + (c_first >> 5) : nullptr;
+        const float s1 = pre * rs;   // the host selects this instance only when one of the two factors is exactly 1
+        mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        [[maybe_unused]] const bool stamp = warp == 2 && lane == 0;
+        if (stamp) TC_STAMP(j, 4);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * CPW * 32);
+        uint32_t va[16], vb[16];
+        if (nv > 0) {
+          tmem_ld16_nowait(t_addr, va);
+          if (lane == 0) tma_store_wait_read<0>();   // the previous tile's box has left the staging buffer
+          __syncwarp();
+        } else {   // a warp without columns in this tile still releases the accumulator
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if constexpr (CL == 2) mbar_arrive_cluster(mapa_u32(&tmem_empty_bar[buf], 0));
+          else mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        float2 ssacc = make_float2(0.f, 0.f);
+        const uint32_t dst = smem_u32(stg) + (uint32_t)stg_row;
+#pragma unroll
+        for (int g = 0; g < H; ++g) {
+          if (g < nv) {                                             // warp-uniform
+            constexpr bool kNewBoxPossible = true;
+            const bool new_box = kNewBoxPossible && g > 0 && (g * 32) % SRB == 0;   // compile-time after unrolling
+            if (new_box) {
+              // this half opens the warp's next staging box: the finished one goes to the TMA engine; its read-out
+              // overlaps the TMEM wait below
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&mapC, stg, c_first + ((g * 32) / SRB - 1) * (SRB >> 1), m0 + quad * 32);
+                tma_store_commit();
+              }
+            }
+            if (g & 1) tmem_wait_ld(vb); else tmem_wait_ld(va);      // half g is in registers
+            if (g + 1 < nv) {
+              if (g & 1) tmem_ld16_nowait(t_addr + 16 * (g + 1), va); else tmem_ld16_nowait(t_addr + 16 * (g + 1), vb);
+            } else {
+              // that was this warp's last TMEM load of the tile: hand the accumulator back to the MMA warp
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              if constexpr (CL == 2) mbar_arrive_cluster(mapa_u32(&tmem_empty_bar[buf], 0));   // the LEADER's barrier
+              else mbar_arrive(&tmem_empty_bar[buf]);
+            }
+            if constexpr (LR) {
+              if (g + 3 < nv) lean_load_res16<false>(rq[(g + 3) & 3], Rrow + 16 * (g + 3));
+            }
+            if (new_box) {   // the buffer is rewritten only after the TMA engine has read the previous box
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            }
+            lean_half<LB, LR, LS>((g & 1) ? vb : va, s1, LB ? bias_w + 16 * g : nullptr, rq[g & 3], ssacc, dst,
+                                  ((g * 32) % SRB) >> 4, stg_xor);
+            if constexpr (LS) {
+              if (g & 1) {
+                if (row_ok) ss_w[g >> 1] = ssacc.x + ssacc.y;
+                ssacc = make_float2(0.f, 0.f);
+              }
+            }
+          }
+        }
+        if (nv > 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            // the box this warp wrote last (earlier ones left inside the loop); columns >= N / rows >= M are clipped
+            tma_store_2d(&mapC, stg, c_first + (((nv - 1) * 32) / SRB) * (SRB >> 1), m0 + quad * 32);
+            tma_store_commit();
+          }
+        }
+        if (stamp) TC_STAMP(j, 5);
+        continue;
+      }
       // (the per-row loads above do not depend on the accumulator: they are issued before the wait)
       mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      [[maybe_unused]] const bool stamp = warp == 2 && lane == 0;
+      if (stamp) TC_STAMP(j, 4);
       unsigned long long best_key = 0;   // fused greedy selection: best (logit, column) this thread produced
       const int c_first = n0 + half * CPW * 32;          // first accumulator column of this warp
       const bool stage_any = warp_tma && half * CPW < NCHUNK && c_first < p.N;   // warp-uniform
@@ -640,6 +868,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const bool last = k == CPW - 1;         // this warp's last round for this tile
         uint32_t v[32];
         bool box_in_flight = false;
+        if (stamp) TC_STAMP(j, 8 + 6 * k);
         __syncwarp();
         {
           // warp-uniform: this chunk opens the warp's NEXT staging box -> hand the finished one to the TMA engine
@@ -655,7 +884,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             box_in_flight = true;   // the buffer may be rewritten only after wait_read (below, after this chunk's math)
           }
         }
+        if (stamp) TC_STAMP(j, 9 + 6 * k);
         if (has_chunk) tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + ci * 32), v);
+        if (stamp) TC_STAMP(j, 10 + 6 * k);
         if (last) {
           // all TMEM reads of this warp for this tile are done: hand the buffer back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -694,10 +925,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
           }
         }
+        if (stamp) TC_STAMP(j, 11 + 6 * k);
         if (box_in_flight) {   // warp-uniform: the math above ran while the TMA engine read the previous box
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
         }
+        if (stamp) TC_STAMP(j, 12 + 6 * k);
         if (active) {
           {
             const int n_out = e_gated ? min(16, (p.N - c) >> 1) : min(32, p.N - c);
@@ -721,6 +954,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
           }
         }
+        if (stamp) TC_STAMP(j, 13 + 6 * k);
       }
       if (stage_any) {
         // generic-proxy smem writes -> visible to the async proxy, then one lane hands the box to the TMA engine
@@ -736,8 +970,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       }
       if (best_key) atomicMax(p.argmax_out + r, best_key);
+      if (stamp) TC_STAMP(j, 5);
     }
-    if (e_tma && lane == 0) tma_store_wait_all();   // smem sources read and writes complete before exit
+    if (e_tma && lane == 0) tma_store_wait_all();
+    if (warp == 2 && lane == 0) TC_STAMP(0, 6);   // smem sources read and writes complete before exit
   }
 
   // ---- teardown: everyone done with TMEM, then the allocating warp frees it ----
@@ -750,6 +986,386 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+  }
+}
+
+
+// =====================================================================================================================
+// GEMM CHAIN: several dependent GEMMs of the decode step in ONE persistent launch.
+//   phase 0:  C0 = epi0(A0 W0^T)      phase 1:  C1 = epi1(A1 W1^T)  with A1 = C0 (or an earlier output) ...
+// Tile order is ROW-TILE MAJOR: the grid is cut into groups of `split` CTAs; group g owns the 128-row tiles g, g + G, ...
+// and walks each of them through ALL phases, CTA l of the group taking the N tiles l, l + split, ... of every phase.
+// A row tile's data therefore stays with the same `split` SMs from the first GEMM to the last, no CTA ever waits for a
+// whole-grid wave to drain between two GEMMs, and the groups drift apart freely (the separate launches pay a launch,
+// a pipeline fill and a wave tail per GEMM for 1-3 tiles of work per SM).  The TMA ring / double-buffered TMEM
+// accumulator / epilogue warps, the barriers, the TMEM allocation and the tensor maps are set up ONCE for the chain.
+// Dependencies are per row tile: a tile (phase p, row tile m) may load its A operand only after ALL N tiles of
+// (phase p-1, m) have been stored.  A CTA publishes its share of (p, m) once, after its last N tile of that phase:
+// stores complete (TMA bulk groups waited for WRITE completion) and fenced, then one red.release adds the number of
+// tiles it produced to done[p][m]; the TMA producer of every CTA of the group polls done[p-1][m] with an acquire load
+// before the first A load of (p, m) - the W halves of the first ring stages are already in flight by then (they do not
+// depend on the previous phase).  Counters are monotonic: launch number `ordinal` (read from device memory = decode step
+// x layers + layer, so the captured CUDA graph needs no patching) waits for (ordinal + 1) x n_tiles.  No deadlock: a
+// CTA only waits for tiles of an earlier phase of the same row tile, all of which belong to CTAs of its own group,
+// which are resident (grid <= number of SMs, one CTA per SM) and walk the same list in the same order.
+// Memory: C leaves through TMA stores (async proxy) or direct stores; the producer's acquire + fence.proxy.async orders
+// them before the next phase's TMA loads; residual / sum-of-squares reads bypass L1 (a line cached earlier in
+// this launch may be stale).  Results are bit-identical to the separate launches (same tiles, same MMA order, same
+// epilogue arithmetic) - tests/test_t5_gpu.py::test_gemm_chain_is_bit_identical.
+// =====================================================================================================================
+constexpr int CHAIN_MAX_PHASES = 4;
+struct alignas(64) ChainPhase {
+  CUtensorMap mapA, mapW, mapC;
+  TcParams p;
+  int tile0, n_tiles, num_kb, dep;   // first tile index, N tiles, k-blocks, 1 = depends on the previous phase
+};
+struct alignas(64) ChainArgs {
+  ChainPhase ph[CHAIN_MAX_PHASES];
+  int n_phases, m_tiles, total_tiles, split;   // split = CTAs per row tile
+  int* done;               // [CHAIN_MAX_PHASES][m_tiles] completion counters, monotonic across launches
+  const int* epoch_ptr;    // device int (decode step counter) or null
+  int epoch_mul, epoch_add;
+  unsigned long long* trace;   // debug (ymt3_debug_chain_trace): [cta][16 tiles][32 events] globaltimer ns, or null
+};
+
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_chain_kernel(const __grid_constant__ ChainArgs a) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  using L = SmemLayout<BN, 1>;
+  constexpr int STAGES = L::STAGES;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < a.n_phases; ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.ph[i].mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.ph[i].mapW) : "memory");
+      if (a.ph[i].p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.ph[i].mapC) : "memory");
+    }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) chain_stamp(a.trace, 0, 7);
+
+  // this CTA's tile list: row tiles grp, grp + groups, ...; all phases of a row tile; N tiles ln, ln + split, ...
+  // body(j, phase, row tile, N tile, first, last): j = running tile number of this CTA, first / last = first / last N
+  // tile this CTA computes of (phase, row tile)
+  const int split = a.split, groups = (int)gridDim.x / split;
+  const int grp = (int)blockIdx.x / split, ln = (int)blockIdx.x % split;
+  auto walk = [&](auto&& body) {
+    int j = 0;
+    for (int mt = grp; mt < a.m_tiles; mt += groups)
+      for (int ph = 0; ph < a.n_phases; ++ph) {
+        const int nn = a.ph[ph].n_tiles;
+        for (int nt = ln; nt < nn; nt += split, ++j) body(j, ph, mt, nt, nt == ln, nt + split >= nn);
+      }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const int ordinal = (a.epoch_ptr ? *a.epoch_ptr : 0) * a.epoch_mul + a.epoch_add;
+      int stage = 0;
+      uint32_t phase = 0;
+      walk([&](int j, int ph, int mt, int nt, bool first, bool) {
+        const ChainPhase& P = a.ph[ph];
+        int kb0 = 0;
+        chain_stamp(a.trace, j, 0);
+        if (P.dep && first) {
+          // every N tile of the previous phase for this row tile has been stored (and fenced) by its CTA
+          const int* flag = a.done + (ph - 1) * a.m_tiles + mt;
+          const int want = (ordinal + 1) * a.ph[ph - 1].n_tiles;
+          if (ld_acquire_gpu(flag) < want) {
+            // not yet: put the W halves of the first ring stages in flight, wait, then add the A halves
+            const int npre = P.num_kb < STAGES ? P.num_kb : STAGES;
+            int st = stage;
+            uint32_t phs = phase;
+            for (int kb = 0; kb < npre; ++kb) {
+              mbar_wait(&empty_bar[st], phs ^ 1);
+              mbar_expect_tx(&full_bar[st], L::STAGE_BYTES);
+              tma_load_2d(&P.mapW, &full_bar[st], smem + st * L::STAGE_BYTES + L::A_BYTES, kb * BK, nt * BN);
+              if (++st == STAGES) {
+                st = 0;
+                phs ^= 1;
+              }
+            }
+            while (ld_acquire_gpu(flag) < want) __nanosleep(20);
+            asm volatile("fence.proxy.async;" ::: "memory");   // those writes -> visible to the TMA loads below
+            for (int kb = 0; kb < npre; ++kb) {
+              tma_load_2d(&P.mapA, &full_bar[stage], smem + stage * L::STAGE_BYTES, kb * BK, mt * BM);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            kb0 = npre;
+          } else {
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+        }
+        chain_stamp(a.trace, j, 1);
+        for (int kb = kb0; kb < P.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_2d(&P.mapA, &full_bar[stage], sa, kb * BK, mt * BM);
+          tma_load_2d(&P.mapW, &full_bar[stage], sb, kb * BK, nt * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      });
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    walk([&](int j, int ph, int, int, bool, bool) {
+      const int num_kb = a.ph[ph].num_kb;
+      const int buf = j & 1;
+      mbar_wait(&tmem_empty_bar[buf], ((j >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          if (kb == 0) chain_stamp(a.trace, j, 2);
+          const uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) {
+            umma_commit(&tmem_full_bar[buf]);
+            chain_stamp(a.trace, j, 3);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    });
+  } else {
+    // ===================== epilogue (8 warps) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int CPW = L::CPW;          // 4 chunks of 32 columns per warp
+    uint8_t* stg = smem + L::STG_OFF + (warp - 2) * L::STG_WARP_BYTES;
+    walk([&](int j, int ph, int mt, int nt, bool, bool last_nt) {
+      const TcParams& p = a.ph[ph].p;
+      const CUtensorMap* mapC = &a.ph[ph].mapC;
+      const bool e_gated = p.gated != 0;
+      const bool e_tma = p.tma_store != 0;
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int stg_rb_all = CPW * (e_gated ? 32 : 64);
+      const int stg_rb = stg_rb_all > 128 ? 128 : stg_rb_all;
+      const int stg_row = lane * stg_rb;
+      const int stg_xor = tma_swizzle_xor(lane, stg_rb);
+      const int buf = j & 1;
+      const int r = m0 + quad * 32 + lane;
+      const bool row_ok = r < p.M;
+      const bool warp_tma = e_tma && m0 + quad * 32 < p.M;
+      const float rs = p.out_scale;
+      mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 2 && lane == 0) chain_stamp(a.trace, j, 4);
+      // (every tile of this phase with a dependency was gated by the producer's acquire; the accumulator barrier
+      //  orders this thread after it; L1 is bypassed for data written earlier in this launch)
+      float pre = 1.0f;
+      if (p.norm_ss_in && row_ok) {
+        const float* sp = p.norm_ss_in + (int64_t)r * p.norm_ss_chunks;
+        float tot = 0.f;
+        for (int c4 = 0; c4 + 4 <= p.norm_ss_chunks; c4 += 4) {
+          const float4 s4 = __ldcg(reinterpret_cast<const float4*>(sp + c4));
+          tot += (s4.x + s4.y) + (s4.z + s4.w);
+        }
+        for (int c1 = p.norm_ss_chunks & ~3; c1 < p.norm_ss_chunks; ++c1) tot += __ldcg(sp + c1);
+        pre = rsqrtf(tot / (float)p.K + p.norm_eps);
+      }
+      const int c_first = n0 + half * CPW * 32;
+      const bool stage_any = warp_tma && c_first < p.N;
+      if (stage_any) {
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int k = 0; k < CPW; ++k) {
+        const int ci = half * CPW + k;
+        const bool last = k == CPW - 1;
+        uint32_t v[32];
+        bool box_in_flight = false;
+        const bool stamp = warp == 2 && lane == 0;
+        if (stamp) chain_stamp(a.trace, j, 8 + 6 * k);
+        __syncwarp();
+        {
+          const int b0k = k * (e_gated ? 32 : 64);
+          if (stage_any && b0k > 0 && b0k % stg_rb == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              const int cb = (e_gated ? (c_first >> 1) : c_first) + (b0k / stg_rb - 1) * (stg_rb >> 1);
+              if (cb < (e_gated ? (p.N >> 1) : p.N)) tma_store_2d(mapC, stg, cb, m0 + quad * 32);
+              tma_store_commit();
+            }
+            box_in_flight = true;
+          }
+        }
+        if (stamp) chain_stamp(a.trace, j, 9 + 6 * k);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + ci * 32), v);
+        if (stamp) chain_stamp(a.trace, j, 10 + 6 * k);
+        if (last) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        const int c = n0 + ci * 32;
+        const bool active = row_ok && c < p.N;
+        float f[32];
+        if (active) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]) * pre;
+          if (p.bias) {
+            if (c + 32 <= p.N) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + c) + q);
+                f[4 * q] += bq.x; f[4 * q + 1] += bq.y; f[4 * q + 2] += bq.z; f[4 * q + 3] += bq.w;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q)
+                if (c + q < p.N) f[q] += __ldg(p.bias + c + q);
+            }
+          }
+          epi_dispatch(f, rs, p.act, e_gated);
+        }
+        if (stamp) chain_stamp(a.trace, j, 11 + 6 * k);
+        if (box_in_flight) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        if (stamp) chain_stamp(a.trace, j, 12 + 6 * k);
+        if (active) {
+          const int n_out = e_gated ? min(16, (p.N - c) >> 1) : min(32, p.N - c);
+          const int64_t off = (int64_t)r * p.ldc + (e_gated ? (c >> 1) : c);
+          const int64_t roff = (int64_t)r * p.ldr + (e_gated ? (c >> 1) : c);
+          const __nv_bfloat16* R = p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + roff : nullptr;
+          // residual through L2 (__ldcg): the row may have been rewritten earlier in this launch
+          uint4 rr[4];
+          if (R) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (8 * q < n_out) rr[q] = __ldcg(reinterpret_cast<const uint4*>(R + 8 * q));
+          }
+          float sq = 0.f;
+          const bool want_ss = p.ss_out != nullptr;
+          __nv_bfloat16* Cd = static_cast<__nv_bfloat16*>(p.C) + off;
+          const int b0 = k * (e_gated ? 32 : 64);
+          uint8_t* dst = stg + stg_row;
+          const int u0 = (b0 % stg_rb) >> 4;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (8 * q4 >= n_out) break;
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+            if (R) {
+              const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&rr[q4]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                h[q] = __floats2bfloat162_rn(f[8 * q4 + 2 * q] + __bfloat162float(th[q].x),
+                                             f[8 * q4 + 2 * q + 1] + __bfloat162float(th[q].y));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * q4 + 2 * q], f[8 * q4 + 2 * q + 1]);
+            }
+            if (want_ss) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 v2 = __bfloat1622float2(h[q]);
+                sq = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, sq));
+              }
+            }
+            if (warp_tma) *reinterpret_cast<uint4*>(dst + ((((u0 + q4) << 4)) ^ stg_xor)) = pk;
+            else *reinterpret_cast<uint4*>(Cd + 8 * q4) = pk;
+          }
+          if (want_ss) p.ss_out[(int64_t)r * p.ss_out_chunks + (c >> 5)] = sq;
+        }
+        if (stamp) chain_stamp(a.trace, j, 13 + 6 * k);
+      }
+      if (stage_any) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          const int co = e_gated ? (c_first >> 1) : c_first;
+          const int n_out_cols = e_gated ? (p.N >> 1) : p.N;
+          const int b = (stg_rb_all - 1) / stg_rb;
+          if (co + b * (stg_rb >> 1) < n_out_cols) tma_store_2d(mapC, stg, co + b * (stg_rb >> 1), m0 + quad * 32);
+          tma_store_commit();
+        }
+      }
+      if (warp == 2 && lane == 0) chain_stamp(a.trace, j, 5);
+      if (last_nt) {
+        // publish this CTA's share of (phase, row tile): the bytes of all its tiles are WRITTEN (not only read out of
+        // shared memory), every epilogue thread's stores (C, sum-of-squares) are fenced, then one thread adds the count
+        if (e_tma && lane == 0) tma_store_wait_all();
+        __threadfence();
+        epi_bar_sync();
+        if (warp == 2 && lane == 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          red_release_gpu_add(a.done + ph * a.m_tiles + mt, (a.ph[ph].n_tiles - ln + split - 1) / split);
+          chain_stamp(a.trace, j, 6);
+        }
+      }
+    });
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 
@@ -826,6 +1442,9 @@ struct ConvGeom {
 // (decoder FFN) / gated SiLU (MoE experts); code = act * 4 + gated * 2 + out_f32
 constexpr int EPI_PLAIN_BF16 = 0, EPI_PLAIN_F32 = 1, EPI_GATED_GELU_NEW = YMT3_ACT_GELU_NEW * 4 + 2,
               EPI_GATED_SILU = YMT3_ACT_SILU * 4 + 2;
+// plain bf16 with every chunk on the lean path (N % 32 == 0, no groups, no arg-max, TMA store, one scale factor) - see the
+// kernel; + 1: bias, + 2: residual, + 4: sum-of-squares output
+constexpr int EPI_LEAN_BF16 = 64;
 
 template <int BN, bool CONV, int EPI, int CL>
 int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGeom& cg = ConvGeom()) {
@@ -859,6 +1478,9 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   t.M = p.M; t.N = p.N; t.K = p.K; t.act = p.act; t.gated = p.gated; t.out_scale = p.out_scale;
   t.norm_ss_in = p.norm_ss_in; t.norm_ss_chunks = p.norm_ss_chunks; t.norm_eps = p.norm_eps;
   t.ss_out = p.ss_out; t.ss_out_chunks = (p.N + 31) / 32;
+#ifdef YMT3_GEMM_TRACE
+  t.trace = g_chain_trace;
+#endif
   t.argmax_out = p.argmax_out; t.argmax_n = p.argmax_n;
   t.row_scale = p.row_scale; t.group_offsets = p.group_offsets; t.num_groups = groups; t.out_f32 = out_dtype == YMT3_F32;
   t.conv_T = cg.T; t.conv_F = cg.F; t.conv_cblocks = CONV ? cg.Cin / BK : 0;
@@ -931,6 +1553,79 @@ int cluster_size(const GemmParams& p, int64_t m_tiles) {
 
 }  // namespace
 
+// Host side of the GEMM chain (see gemm_chain_kernel).  phases[i]: an ordinary GemmParams (bf16 in / out, no groups,
+// no arg-max, no row scale); phase i > 0 depends on phase i - 1 per M tile.  done: device ints, CHAIN_MAX_PHASES x
+// ceil(M / 128), zeroed by the caller before the first launch of a run; launch ordinal = *epoch_ptr * epoch_mul +
+// epoch_add must count the launches that used `done` since then (0, 1, 2, ...).
+void gemm_chain_set_trace(unsigned long long* buf) { g_chain_trace = buf; }
+
+int gemm_chain_bf16(const GemmParams* phases, int n_phases, int* done, const int* epoch_ptr, int epoch_mul, int epoch_add,
+                    cudaStream_t stream) {
+  constexpr int BN = 256;
+  YMT3_REQUIRE(phases && n_phases >= 1 && n_phases <= CHAIN_MAX_PHASES && done, "gemm_chain: bad arguments");
+  const int M = phases[0].M;
+  if (M <= 0) return YMT3_OK;
+  ChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_phases = n_phases;
+  a.m_tiles = ymt3_div_up(M, BM);
+  a.done = done;
+  a.epoch_ptr = epoch_ptr; a.epoch_mul = epoch_mul; a.epoch_add = epoch_add;
+  a.trace = g_chain_trace;
+  int tile0 = 0, rc;
+  for (int i = 0; i < n_phases; ++i) {
+    const GemmParams& p = phases[i];
+    YMT3_REQUIRE(p.A && p.W && p.C && p.M == M && p.N > 0 && p.K > 0, "gemm_chain: phase %d: bad shape", i);
+    YMT3_REQUIRE(p.K % 8 == 0 && p.lda % 8 == 0 && p.ldw % 8 == 0 && p.ldc % 8 == 0 && (!p.residual || p.ldr % 8 == 0) &&
+                     p.N % (p.gated ? 16 : 8) == 0,
+                 "gemm_chain: phase %d: alignment", i);
+    YMT3_REQUIRE(!p.group_offsets && !p.argmax_out && !p.row_scale, "gemm_chain: phase %d: unsupported epilogue option", i);
+    YMT3_REQUIRE(!p.ss_out || (!p.gated && p.N % 32 == 0), "gemm_chain: phase %d: sum-of-squares output needs N %% 32 == 0", i);
+    YMT3_REQUIRE(!p.norm_ss_in || (p.norm_ss_chunks > 0 && p.norm_ss_chunks % 4 == 0), "gemm_chain: phase %d: norm partials", i);
+    ChainPhase& P = a.ph[i];
+    if ((rc = make_map(&P.mapA, p.A, p.M, p.K, p.lda, BM))) return rc;
+    if ((rc = make_map(&P.mapW, p.W, p.N, p.K, p.ldw, BN))) return rc;
+    const int tma_store = p.gated ? 0 : 1;
+    if (tma_store && (rc = make_out_map(&P.mapC, p.C, p.M, p.N, p.ldc, 128))) return rc;
+    TcParams& t = P.p;
+    t.tma_store = tma_store;
+    t.C = p.C; t.ldc = p.ldc; t.bias = p.bias; t.residual = p.residual; t.ldr = p.ldr;
+    t.M = p.M; t.N = p.N; t.K = p.K; t.act = p.act; t.gated = p.gated; t.out_scale = p.out_scale;
+    t.norm_ss_in = p.norm_ss_in; t.norm_ss_chunks = p.norm_ss_chunks; t.norm_eps = p.norm_eps;
+    t.ss_out = p.ss_out; t.ss_out_chunks = (p.N + 31) / 32;
+    t.num_groups = 1;
+    P.tile0 = tile0;
+    P.n_tiles = ymt3_div_up(p.N, BN);
+    P.num_kb = ymt3_div_up(p.K, BK);
+    P.dep = i > 0;
+    tile0 += a.m_tiles * P.n_tiles;
+  }
+  a.total_tiles = tile0;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  YMT3_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    YMT3_CUDA_CHECK(cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN, 1>::TOTAL));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int sms = ymt3_num_sms();
+  // one CTA per SM, all co-resident (the dependency waits rely on it): never more CTAs than SMs.  `split` CTAs share a
+  // row tile: as many as the SM count allows, at most the widest phase's N tiles.
+  int max_nt = 1;
+  for (int i = 0; i < n_phases; ++i) max_nt = a.ph[i].n_tiles > max_nt ? a.ph[i].n_tiles : max_nt;
+  int split = sms / a.m_tiles;
+  if (const char* e = getenv("YMT3_GEMM_CHAIN_SPLIT")) split = atoi(e);
+  split = split < 1 ? 1 : (split > max_nt ? max_nt : split);
+  if (split > sms) split = sms;
+  a.split = split;
+  const int groups = a.m_tiles < sms / split ? a.m_tiles : sms / split;
+  const int grid = groups * split;
+  YMT3_CUDA_CHECK(ymt3_launch_pdl(gemm_chain_kernel, dim3(grid), dim3(THREADS), SmemLayout<BN, 1>::TOTAL, stream, a));
+  return YMT3_OK;
+}
+
+int gemm_chain_counters(int M) { return CHAIN_MAX_PHASES * ymt3_div_up(M, BM); }
+
 int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   YMT3_REQUIRE(p.A && p.W && p.C, "gemm_bf16_tc: null pointer");
   if (p.M <= 0 || p.N <= 0) return YMT3_OK;
@@ -963,8 +1658,16 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   const int bn = gemm_choose_bn(mt, p.N, sms, max_bn);   // index_maps.h
   static const bool generic_only = getenv("YMT3_GEMM_DIRECT_STORE") || getenv("YMT3_GEMM_TMA_GATED") ||
                                    getenv("YMT3_GEMM_GENERIC");   // A/B switches act on the run-time kernel
-  const int code = generic_only ? -1 : p.act * 4 + (p.gated ? 2 : 0) + (out_dtype == YMT3_F32 ? 1 : 0);
+  int code = generic_only ? -1 : p.act * 4 + (p.gated ? 2 : 0) + (out_dtype == YMT3_F32 ? 1 : 0);
+  static const bool no_lean = getenv("YMT3_GEMM_NO_LEAN") != nullptr;   // A/B aid
   const bool cl2 = cluster_size(p, mt) == 2;
+  // lean epilogue instances (single CTA): every chunk full, ONE scale factor (the other exactly 1), compile-time bias /
+  // residual / sum-of-squares flags - the combinations the model's GEMMs use
+  if (code == EPI_PLAIN_BF16 && !no_lean && !cl2 && p.N % 32 == 0 && !p.group_offsets && !p.argmax_out && !p.row_scale &&
+      (p.out_scale == 1.0f || (!p.norm_ss_in && !p.bias))) {
+    const int flags = (p.bias ? 1 : 0) | (p.residual ? 2 : 0) | (p.ss_out ? 4 : 0);
+    if (flags != 4 && flags != 5) code = EPI_LEAN_BF16 + flags;
+  }
 #define YMT3_TC_LAUNCH(EPI)                                                                                      \
   switch (bn) {                                                                                                  \
     case 256: return cl2 ? launch<256, false, EPI, 2>(p, out_dtype, stream) : launch<256, false, EPI, 1>(p, out_dtype, stream); \
@@ -973,6 +1676,20 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
     default: return cl2 ? launch<32, false, EPI, 2>(p, out_dtype, stream) : launch<32, false, EPI, 1>(p, out_dtype, stream);  \
   }
   switch (code) {
+#define YMT3_TC_LAUNCH_LEAN(EPI)                                                  \
+  switch (bn) {                                                                  \
+    case 256: return launch<256, false, EPI, 1>(p, out_dtype, stream);           \
+    case 128: return launch<128, false, EPI, 1>(p, out_dtype, stream);           \
+    case 64: return launch<64, false, EPI, 1>(p, out_dtype, stream);             \
+    default: return launch<32, false, EPI, 1>(p, out_dtype, stream);             \
+  }
+    case EPI_LEAN_BF16 + 0: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 0)
+    case EPI_LEAN_BF16 + 1: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 1)
+    case EPI_LEAN_BF16 + 2: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 2)
+    case EPI_LEAN_BF16 + 3: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 3)
+    case EPI_LEAN_BF16 + 6: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 6)
+    case EPI_LEAN_BF16 + 7: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 7)
+#undef YMT3_TC_LAUNCH_LEAN
     case EPI_PLAIN_BF16: YMT3_TC_LAUNCH(EPI_PLAIN_BF16)
     case EPI_PLAIN_F32: YMT3_TC_LAUNCH(EPI_PLAIN_F32)
     case EPI_GATED_GELU_NEW: YMT3_TC_LAUNCH(EPI_GATED_GELU_NEW)

@@ -67,6 +67,14 @@ struct GemmParams {
 
 int gemm_f32(const GemmParams& p, cudaStream_t stream);            // SIMT fp32 FFMA
 int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream);  // tcgen05/TMEM/TMA
+// Several dependent bf16 GEMMs in ONE persistent tcgen05 launch (gemm_bf16_tc.cu, gemm_chain_kernel): phase i > 0 reads
+// what phase i - 1 wrote, dependencies tracked per 128-row tile through `done` (gemm_chain_counters(M) device ints,
+// zeroed by the caller at the start of a run); launch ordinal = *epoch_ptr * epoch_mul + epoch_add (0, 1, 2, ... over
+// the launches that share `done`).  Same arithmetic, tile by tile, as the separate launches.
+int gemm_chain_bf16(const GemmParams* phases, int n_phases, int* done, const int* epoch_ptr, int epoch_mul, int epoch_add,
+                    cudaStream_t stream);
+int gemm_chain_counters(int M);
+void gemm_chain_set_trace(unsigned long long* buf);   // debug: per-CTA event timestamps, (SMs x 16 x 32) words or null
 // 3x3 same-padding convolution on NHWC bf16 input as an implicit GEMM (tcgen05; TMA 4-D tiles with
 // zero-filled halo); `epi` carries W (Cout, 9*Cin), N=Cout, C/ldc, bias, act, residual/ldr, out_scale.
 int conv3x3_bf16_tc(const void* x, int B, int T, int F, int Cin, const GemmParams& epi, int out_dtype,

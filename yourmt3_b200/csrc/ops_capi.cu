@@ -75,6 +75,33 @@ extern "C" int ymt3_op_linear_normfused(const void* A, int64_t lda, const void* 
   return gemm_bf16_tc(p, out_dtype, (cudaStream_t)stream);
 }
 
+extern "C" int ymt3_debug_chain_trace(uint64_t* device_buf) {
+  gemm_chain_set_trace(reinterpret_cast<unsigned long long*>(device_buf));
+  return YMT3_OK;
+}
+
+extern "C" int64_t ymt3_op_linear_chain_counters(int64_t M) {
+  return M > 0 && M < (1ll << 31) ? gemm_chain_counters((int)M) : 0;
+}
+
+extern "C" int ymt3_op_linear_chain(const ymt3_chain_phase_t* phases, int32_t n_phases, int64_t M, int32_t* counters,
+                                    int32_t ordinal, void* stream) {
+  YMT3_REQUIRE(phases && n_phases >= 1 && n_phases <= 4 && counters && ordinal >= 0, "op_linear_chain: bad arguments");
+  YMT3_REQUIRE(M >= 0 && M < (1ll << 31), "op_linear_chain: bad shape");
+  GemmParams g[4];
+  for (int i = 0; i < n_phases; ++i) {
+    const ymt3_chain_phase_t& q = phases[i];
+    YMT3_REQUIRE(q.N > 0 && q.N < (1ll << 31) && q.K > 0 && q.K < (1ll << 31), "op_linear_chain: phase %d: bad shape", i);
+    GemmParams p{};
+    p.A = q.A; p.lda = q.lda; p.W = q.W; p.ldw = q.ldw; p.C = q.C; p.ldc = q.ldc; p.bias = q.bias;
+    p.residual = q.residual; p.ldr = q.ldr; p.M = (int)M; p.N = (int)q.N; p.K = (int)q.K;
+    p.act = q.act; p.gated = q.gated; p.out_scale = q.out_scale;
+    p.norm_ss_in = q.ss_in; p.norm_ss_chunks = (int)q.chunks; p.norm_eps = q.eps; p.ss_out = q.ss_out;
+    g[i] = p;
+  }
+  return gemm_chain_bf16(g, n_phases, counters, nullptr, 0, ordinal, (cudaStream_t)stream);
+}
+
 extern "C" int ymt3_op_linear_argmax(int32_t dtype, const void* A, int64_t lda, const void* W, int64_t ldw,
                                      const float* bias, float* logits, int64_t ldc, int64_t M, int64_t N, int64_t K,
                                      int64_t V, float out_scale, uint64_t* keys, void* stream) {

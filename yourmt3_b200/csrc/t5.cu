@@ -244,6 +244,8 @@ struct ymt3_t5dec {
   cudaGraphExec_t graph = nullptr;
   int64_t graph_N = -1, graph_T = -1, graph_L = -1;
   int graph_stop = -1, graph_prefix = -1, graph_score = -1;
+  bool use_chain = false;       // bf16 + fused norm: the GEMMs between the attention kernels run as two chained launches per layer
+  int* chain_done = nullptr;    // completion counters of the two chains (gemm_chain_counters each)
   int32_t* tok_buf = nullptr;   // (cap_N, cap_L) tokens of the running call: the graph writes here (stable pointer), one
                                 // D2D copy hands them to the caller's buffer, so a fresh output tensor per call does
                                 // not re-instantiate the graph
@@ -340,6 +342,7 @@ extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
     }
   }
   d->fuse_norm = cfg->precision == YMT3_BF16 && D % 128 == 0 && getenv("YMT3_NO_FUSED_NORM") == nullptr;
+  d->use_chain = d->fuse_norm && getenv("YMT3_NO_GEMM_CHAIN") == nullptr;
   if (!rc) {
     d->d_step = (int*)d->weights.alloc(64);
     d->d_unfinished = d->d_step + 4;
@@ -418,8 +421,9 @@ int dec_ensure(ymt3_t5dec* d, int64_t N, int64_t T, int64_t Lmax, int latent, cu
   d->d_fin = (int*)d->ws.alloc(cN * 4);
   d->d_amax = (unsigned long long*)d->ws.alloc(cN * 8);
   d->tok_buf = (int32_t*)d->ws.alloc((size_t)cN * cL * 4);
+  d->chain_done = d->use_chain ? (int*)d->ws.alloc((size_t)2 * gemm_chain_counters((int)cN) * 4) : nullptr;
   for (int i = 0; i < 3; ++i) d->ss[i] = d->fuse_norm ? (float*)d->ws.alloc((size_t)cN * (D / 32) * 4) : nullptr;
-  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->d_amax && d->tok_buf && d->kv_tmp &&
+  bool ok = d->x && d->h && d->qkv && d->attn && d->qx && d->g && d->logits && d->d_cur && d->d_fin && d->d_amax && d->tok_buf && d->kv_tmp && (!d->use_chain || d->chain_done) &&
             (!d->fuse_norm || (d->ss[0] && d->ss[1] && d->ss[2]));
   d->selfK.assign(c.num_layers, nullptr);
   d->selfV.assign(c.num_layers, nullptr);
@@ -477,6 +481,51 @@ int dec_step(ymt3_t5dec* d, int64_t N, int64_t T, int Lmax, int stop_at_eos, int
   };
   float *sA = d->ss[0], *sB = d->ss[1], *sC = d->ss[2];
   if ((rc = embed_pos(d->d_cur, d->embed, d->pos, d->d_step, d->x, (int)N, D, dt, s, fuse ? sA : nullptr))) return rc;
+  if (d->use_chain && fuse && !skip) {
+    // CHAINED decode step: the GEMMs between two attention kernels run as ONE persistent launch each
+    //   chain A = [o-proj (+x) -> cross-q],   chain B = [cross-o (+x) -> wi (gated GELU) -> wo (+x) -> qkv of the next layer]
+    // (4 launches per layer instead of 8; dependencies per 128-row tile inside the kernel, gemm_bf16_tc.cu).
+    auto gp = [&](const void* A, int lda, const Linear& W, void* C, int ldc, int act, int gated, bool residual,
+                  const float* ss_in, float* ss_out) {
+      GemmParams p{};
+      p.A = A; p.lda = lda; p.W = W.W; p.ldw = W.K; p.C = C; p.ldc = ldc; p.bias = W.bias;
+      p.residual = residual ? C : nullptr; p.ldr = ldc;
+      p.M = (int)N; p.N = W.N; p.K = W.K; p.act = act; p.gated = gated; p.out_scale = 1.f;
+      p.norm_ss_in = ss_in; p.norm_ss_chunks = ss_in ? ch : 0; p.norm_eps = c.layer_norm_eps; p.ss_out = ss_out;
+      return p;
+    };
+    const int nc = gemm_chain_counters((int)d->cap_N);
+    if ((rc = linear_fwd(dt, d->x, D, d->layers[0].qkv_n, d->qkv, 3 * inner, (int)N, 0, 0, nullptr, 0, 1.f, dt, s, consume(sA))))
+      return rc;
+    for (int i = 0; i < c.num_layers; ++i) {
+      const T5Layer& L = d->layers[i];
+      if ((rc = decode_attention(d->qkv, 3 * inner, (char*)d->qkv + inner * es, (char*)d->qkv + 2 * inner * es, 3 * inner,
+                                 d->selfK[i], d->selfV[i], (int64_t)H * d->cap_L * dk, (int64_t)d->cap_L * dk, dk, Lmax + n_prefix,
+                                 d->d_step, 0, 1.0f, d->attn, inner, (int)N, H, dk, dt, s, d->rel_bias, d->rel_P)))
+        return rc;
+      GemmParams ca[2], cb[4];
+      const int HZ = H * d->zdim;
+      ca[0] = gp(d->attn, inner, L.o, d->x, D, 0, 0, true, nullptr, sB);
+      ca[1] = latent ? gp(d->x, D, L.xq_abs_n, d->qz, HZ, 0, 0, false, sB, nullptr)
+                     : gp(d->x, D, L.xq_n, d->qx, inner, 0, 0, false, sB, nullptr);
+      if ((rc = gemm_chain_bf16(ca, 2, d->chain_done, d->d_step, c.num_layers, i, s))) return rc;
+      if (latent) {
+        if ((rc = cross_attn_absorbed(d->qz, HZ, d->zbuf, d->cz, HZ, N, H, (int)T, (int)((T + 15) / 16 * 16), d->zdim, s))) return rc;
+        cb[0] = gp(d->cz, HZ, L.xo_abs, d->x, D, 0, 0, true, nullptr, sC);
+      } else {
+        if ((rc = decode_attention(d->qx, inner, nullptr, nullptr, 0, d->crossKV[i],
+                                   (char*)d->crossKV[i] + (size_t)N * inner * T * es, (int64_t)H * T * dk, T * dk, dk, 0,
+                                   d->d_step, (int)T, 1.0f, d->attn, inner, (int)N, H, dk, dt, s)))
+          return rc;
+        cb[0] = gp(d->attn, inner, L.xo, d->x, D, 0, 0, true, nullptr, sC);
+      }
+      cb[1] = gp(d->x, D, L.wi_n, d->g, F, YMT3_ACT_GELU_NEW, 1, false, sC, nullptr);
+      cb[2] = gp(d->g, F, L.wo, d->x, D, 0, 0, true, nullptr, sA);
+      int nb = 3;
+      if (i + 1 < c.num_layers) cb[nb++] = gp(d->x, D, d->layers[i + 1].qkv_n, d->qkv, 3 * inner, 0, 0, false, sA, nullptr);
+      if ((rc = gemm_chain_bf16(cb, nb, d->chain_done + nc, d->d_step, c.num_layers, i, s))) return rc;
+    }
+  } else
   for (int i = 0; i < c.num_layers; ++i) {
     const T5Layer& L = d->layers[i];
     // self-attention over the device-resident cache (modeling_t5.py:269-305, 356-377)
@@ -601,6 +650,7 @@ int generate_impl(ymt3_t5dec_t* d, const void* enc_hs, int64_t N, int64_t T, int
   if ((rc = fill_i32(d->d_cur, c.start_id, N, s))) return rc;
   if ((rc = fill_i32(d->d_fin, 0, N, s))) return rc;
   YMT3_CUDA_CHECK(cudaMemsetAsync(d->d_amax, 0, (size_t)N * 8, s));
+  if (d->chain_done) YMT3_CUDA_CHECK(cudaMemsetAsync(d->chain_done, 0, (size_t)2 * gemm_chain_counters((int)d->cap_N) * 4, s));
   if ((rc = fill_i32(d->tok_buf, c.pad_id, N * max_len, s))) return rc;
   int32_t* score_buf = nullptr;
   if (scoring && score->argmax_out) {

@@ -92,10 +92,10 @@ def test_gemm_chain_bit_identical_absorbed(cuda_device, native_lib, monkeypatch)
     x = torch.from_numpy(synth_noise(12, seed=31)).unsqueeze(1).to(cuda_device)
     out = {}
     for mode in ("chain", "separate"):
-        if mode == "separate":
-            monkeypatch.setenv("YMT3_NO_GEMM_CHAIN", "1")
+        if mode == "chain":
+            monkeypatch.setenv("YMT3_GEMM_CHAIN", "1")
         else:
-            monkeypatch.delenv("YMT3_NO_GEMM_CHAIN", raising=False)
+            monkeypatch.delenv("YMT3_GEMM_CHAIN", raising=False)
         m = small_model("yptf_moe_multi", "bf16", blocks=1, dec_layers=3, event_length=24, seed=5).to(cuda_device)
         assert m._absorbed()
         toks = m.inference(x, stop_at_eos=False).cpu()

@@ -206,15 +206,15 @@ def test_bf16_note_onset_f1_vs_fp32(cuda_device, native_lib):
 def test_gemm_chain_is_bit_identical(cuda_device, native_lib, monkeypatch, n_rows):
     """The chained decode step (gemm_chain_kernel: [o-proj -> cross-q] and [cross-o -> wi -> wo -> next qkv] as ONE
     persistent launch each, dependencies per 128-row tile) computes tile by tile what the separate launches compute:
-    tokens AND last-step logits are bit-identical with the chain on and off (YMT3_NO_GEMM_CHAIN, read when the
+    tokens AND last-step logits are bit-identical with the chain on and off (YMT3_GEMM_CHAIN=1, read when the
     decoder runtime is created); 300 rows = 3 row tiles, the last one ragged."""
     enc_hs = torch.randn(n_rows, 40, 512, generator=torch.Generator().manual_seed(5)).to(cuda_device)
     out = {}
     for mode in ("chain", "separate"):
-        if mode == "separate":
-            monkeypatch.setenv("YMT3_NO_GEMM_CHAIN", "1")
+        if mode == "chain":
+            monkeypatch.setenv("YMT3_GEMM_CHAIN", "1")
         else:
-            monkeypatch.delenv("YMT3_NO_GEMM_CHAIN", raising=False)
+            monkeypatch.delenv("YMT3_GEMM_CHAIN", raising=False)
         m = ymt3.YourMT3(model_cfg=small_cfg(n_layers=3), precision="bf16")
         ymt3.init_nondegenerate_(m, seed=0)
         m = m.to(cuda_device)

@@ -1,10 +1,10 @@
 #!/bin/bash
-# Same-box alternating A/B of the chained decode-step GEMM launches (YMT3_NO_GEMM_CHAIN=1 = separate launches).
+# Same-box alternating A/B of the chained decode-step GEMM launches (YMT3_GEMM_CHAIN=1 = chained, default = separate launches).
 # usage (on the GPU box): tools/ab_gemm_chain.sh > gpurun_out/r02_ab_gemm_chain.txt
 for rep in 1 2; do
   for mode in chain separate; do
     echo "# mode=$mode rep=$rep"
-    if [ $mode = separate ]; then export YMT3_NO_GEMM_CHAIN=1; else unset YMT3_NO_GEMM_CHAIN; fi
+    if [ $mode = chain ]; then export YMT3_GEMM_CHAIN=1; else unset YMT3_GEMM_CHAIN; fi
     timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:

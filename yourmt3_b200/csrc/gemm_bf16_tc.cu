@@ -422,6 +422,30 @@ __device__ __forceinline__ void lean_half(const uint32_t (&v)[16], float s, cons
                  "r"(h[4 * q + 1]), "r"(h[4 * q + 2]), "r"(h[4 * q + 3])
                  : "memory");
 }
+// gated form: v = 16 accumulator columns = 8 (activated, linear) pairs; h = 8 bf16 outputs act(a_even) * a_odd * rs with
+// a = v * pre + bias - the per-element operations of epi_math<ACT, true>
+template <int ACT, bool BIAS>
+__device__ __forceinline__ void lean_half_gated(const uint32_t (&v)[16], float pre, float rs, const float* bias_c, uint32_t (&h)[4]) {
+  float2 a[8];
+  const float2 p2 = make_float2(pre, pre);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) a[q] = lean_mul2(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), p2);
+  if constexpr (BIAS) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias_c) + q);
+      a[2 * q] = lean_add2(a[2 * q], make_float2(b.x, b.y));
+      a[2 * q + 1] = lean_add2(a[2 * q + 1], make_float2(b.z, b.w));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float o0 = act_fast<ACT>(a[2 * q].x) * a[2 * q].y * rs;
+    const float o1 = act_fast<ACT>(a[2 * q + 1].x) * a[2 * q + 1].y * rs;
+    const __nv_bfloat162 b2 = __floats2bfloat162_rn(o0, o1);
+    h[q] = *reinterpret_cast<const uint32_t*>(&b2);
+  }
+}
 // the residual bytes of one row segment of 16 bf16 - issued early, consumed by lean_half
 template <bool L2_ONLY>
 __device__ __forceinline__ void lean_load_res16(uint4 (&rr)[2], const __nv_bfloat16* R) {
@@ -523,10 +547,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   // EPI_LEAN_BF16: plain bf16 output, N % 32 == 0, no groups / arg-max, TMA store: ONLY the lean chunk path is compiled
   // (epi_chunk_lean; the host picks it whenever the shape allows - every plain GEMM of the decode step and the encoder)
   constexpr bool LEAN = EPI >= 64;   // 64 + (bias ? 1 : 0) + (residual ? 2 : 0) + (sum of squares ? 4 : 0)
-  const int e_act = GEN ? p.act : (LEAN ? 0 : (EPI >> 2));
-  const bool e_gated = GEN ? (p.gated != 0) : (!LEAN && ((EPI >> 1) & 1) != 0);
+  constexpr bool LG = EPI >= 80;     // gated lean: 80 + (bias ? 1 : 0) + (SiLU ? 2 : 0) (else gelu_new)
+  const int e_act = GEN ? p.act : (LEAN ? (LG ? ((EPI & 2) ? YMT3_ACT_SILU : YMT3_ACT_GELU_NEW) : 0) : (EPI >> 2));
+  const bool e_gated = GEN ? (p.gated != 0) : (LEAN ? LG : ((EPI >> 1) & 1) != 0);
   const bool e_f32 = GEN ? (p.out_f32 != 0) : (!LEAN && (EPI & 1) != 0);
-  const bool e_tma = GEN ? (p.tma_store != 0) : (!e_gated && !e_f32);
+  const bool e_tma = GEN ? (p.tma_store != 0) : (LEAN || (!e_gated && !e_f32));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -760,12 +785,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // source view), which - not TMEM or shared-memory traffic - is what a 32-column chunk's ~1000 clk were made of
         // (leave-out experiments + timeline: profiles/r02_gemm_epilogue_timeline.txt).
         constexpr int H = 2 * CPW;                                   // halves per warp
-        constexpr int SRB = CPW * 64 > 128 ? 128 : CPW * 64;         // bytes per staged box row
-        constexpr bool LB = (EPI & 1) != 0, LR = (EPI & 2) != 0, LS = (EPI & 4) != 0;   // bias, residual, sum of squares
+        constexpr int SRB = LG ? (CPW * 32 > 128 ? 128 : CPW * 32)   // bytes per staged box row (gated: 8 outputs per half)
+                               : (CPW * 64 > 128 ? 128 : CPW * 64);
+        constexpr bool LB = (EPI & 1) != 0, LR = !LG && (EPI & 2) != 0, LS = !LG && (EPI & 4) != 0;   // bias, residual, sum of squares
+        constexpr int G_ACT = (EPI & 2) ? YMT3_ACT_SILU : YMT3_ACT_GELU_NEW;   // (gated instances)
         const int c_first = n0 + half * CPW * 32;                    // first accumulator column of this warp
         const int n_cols = p.N;
+        // a ragged last slab of a group (grouped gated GEMM) cannot leave through the box store (it would spill into the
+        // next group's rows): direct 16-byte stores for its rows
+        const bool slab_rows = m0 + quad * 32 < row_end;             // this warp's slab has rows in the tile at all
+        [[maybe_unused]] const bool slab_direct = LG && slab_rows && !warp_tma;
         // number of this warp's halves that hold real columns (N % 32 == 0: always even); 0: nothing to do
-        const int nv = (warp_tma && half * CPW < NCHUNK && c_first < n_cols) ? min(H, (n_cols - c_first) >> 4) : 0;
+        const int nv = (slab_rows && (warp_tma || slab_direct) && half * CPW < NCHUNK && c_first < n_cols)
+            ? min(H, (n_cols - c_first) >> 4) : 0;
         // rows past the end of the tile: loads clamped to the last row, the box store clips them
         [[maybe_unused]] const __nv_bfloat16* Rrow = nullptr;
         [[maybe_unused]] uint4 rq[4][2];                             // residual ring: half g lives in rq[g & 3]
@@ -777,7 +809,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         [[maybe_unused]] const float* bias_w = LB ? bias + c_first : nullptr;
         [[maybe_unused]] float* ss_w = LS ? p.ss_out + (int64_t)(row_ok ? r : row_end - 1) * p.ss_out_chunks + (c_first >> 5) : nullptr;
-        const float s1 = pre * rs;   // the host selects this instance only when one of the two factors is exactly 1
+        const float s1 = LG ? pre : pre * rs;   // plain: the host selects this instance only when one factor is exactly 1
+        [[maybe_unused]] __nv_bfloat16* Cdir = nullptr;   // gated, ragged slab: this thread's output row segment
+        if constexpr (LG) {
+          if (slab_direct) Cdir = static_cast<__nv_bfloat16*>(p.C) + (int64_t)(row_ok ? r : row_end - 1) * p.ldc + (c_first >> 1);
+        }
         mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         [[maybe_unused]] const bool stamp = warp == 2 && lane == 0;
@@ -798,8 +834,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
         for (int g = 0; g < H; ++g) {
           if (g < nv) {                                             // warp-uniform
-            constexpr bool kNewBoxPossible = true;
-            const bool new_box = kNewBoxPossible && g > 0 && (g * 32) % SRB == 0;   // compile-time after unrolling
+            const bool new_box = !LG && g > 0 && (g * 32) % SRB == 0;   // compile-time after unrolling
             if (new_box) {
               // this half opens the warp's next staging box: the finished one goes to the TMA engine; its read-out
               // overlaps the TMEM wait below
@@ -826,8 +861,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               if (lane == 0) tma_store_wait_read<0>();
               __syncwarp();
             }
-            lean_half<LB, LR, LS>((g & 1) ? vb : va, s1, LB ? bias_w + 16 * g : nullptr, rq[g & 3], ssacc, dst,
-                                  ((g * 32) % SRB) >> 4, stg_xor);
+            if constexpr (LG) {
+              uint32_t h4[4];
+              lean_half_gated<G_ACT, LB>((g & 1) ? vb : va, s1, rs, LB ? bias_w + 16 * g : nullptr, h4);
+              if (!slab_direct)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((g << 4) ^ stg_xor)), "r"(h4[0]),
+                             "r"(h4[1]), "r"(h4[2]), "r"(h4[3])
+                             : "memory");
+              else if (row_ok)
+                *reinterpret_cast<uint4*>(Cdir + 8 * g) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+            } else {
+              lean_half<LB, LR, LS>((g & 1) ? vb : va, s1, LB ? bias_w + 16 * g : nullptr, rq[g & 3], ssacc, dst,
+                                    ((g * 32) % SRB) >> 4, stg_xor);
+            }
             if constexpr (LS) {
               if (g & 1) {
                 if (row_ok) ss_w[g >> 1] = ssacc.x + ssacc.y;
@@ -836,12 +882,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
           }
         }
-        if (nv > 0) {
+        if (nv > 0 && !slab_direct) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
             // the box this warp wrote last (earlier ones left inside the loop); columns >= N / rows >= M are clipped
-            tma_store_2d(&mapC, stg, c_first + (((nv - 1) * 32) / SRB) * (SRB >> 1), m0 + quad * 32);
+            if constexpr (LG) tma_store_2d(&mapC, stg, c_first >> 1, m0 + quad * 32);
+            else tma_store_2d(&mapC, stg, c_first + (((nv - 1) * 32) / SRB) * (SRB >> 1), m0 + quad * 32);
             tma_store_commit();
           }
         }
@@ -1445,6 +1492,8 @@ constexpr int EPI_PLAIN_BF16 = 0, EPI_PLAIN_F32 = 1, EPI_GATED_GELU_NEW = YMT3_A
 // plain bf16 with every chunk on the lean path (N % 32 == 0, no groups, no arg-max, TMA store, one scale factor) - see the
 // kernel; + 1: bias, + 2: residual, + 4: sum-of-squares output
 constexpr int EPI_LEAN_BF16 = 64;
+// gated (gelu_new / SiLU) bf16 output on the lean path (N % 32 == 0, tile width >= 64, groups allowed): + 1: bias, + 2: SiLU
+constexpr int EPI_LEAN_GATED = 80;
 
 template <int BN, bool CONV, int EPI, int CL>
 int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGeom& cg = ConvGeom()) {
@@ -1467,7 +1516,7 @@ int launch(const GemmParams& p, int out_dtype, cudaStream_t stream, const ConvGe
   // (gated epilogues keep the direct stores: measured 383 -> 401 us on the MoE expert GEMM with 64-byte box rows,
   //  its limiter is the epilogue math, not the stores - profiles/r01_ab_gemm_tma_store.txt)
   static const bool tma_gated = getenv("YMT3_GEMM_TMA_GATED") != nullptr;
-  const int tma_store = out_dtype == YMT3_BF16 && !direct_store && (!p.gated || tma_gated);
+  const int tma_store = EPI >= EPI_LEAN_BF16 || (out_dtype == YMT3_BF16 && !direct_store && (!p.gated || tma_gated));
   const int out_row_bytes = SmemLayout<BN, CL>::CPW * (p.gated ? 32 : 64);
   if (tma_store && (rc = make_out_map(&mapC, p.C, p.M, p.gated ? p.N / 2 : p.N, p.ldc,
                                       out_row_bytes > 128 ? 128 : out_row_bytes)))
@@ -1668,6 +1717,9 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
     const int flags = (p.bias ? 1 : 0) | (p.residual ? 2 : 0) | (p.ss_out ? 4 : 0);
     if (flags != 4 && flags != 5) code = EPI_LEAN_BF16 + flags;
   }
+  if ((code == EPI_GATED_GELU_NEW || code == EPI_GATED_SILU) && !no_lean && !cl2 && bn >= 64 && p.N % 32 == 0 && !p.argmax_out &&
+      !p.residual && !p.ss_out)
+    code = EPI_LEAN_GATED + (p.bias ? 1 : 0) + (code == EPI_GATED_SILU ? 2 : 0);
 #define YMT3_TC_LAUNCH(EPI)                                                                                      \
   switch (bn) {                                                                                                  \
     case 256: return cl2 ? launch<256, false, EPI, 2>(p, out_dtype, stream) : launch<256, false, EPI, 1>(p, out_dtype, stream); \
@@ -1689,6 +1741,17 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
     case EPI_LEAN_BF16 + 3: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 3)
     case EPI_LEAN_BF16 + 6: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 6)
     case EPI_LEAN_BF16 + 7: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 7)
+#define YMT3_TC_LAUNCH_LEAN_G(EPI)                                                \
+  switch (bn) {                                                                  \
+    case 256: return launch<256, false, EPI, 1>(p, out_dtype, stream);           \
+    case 128: return launch<128, false, EPI, 1>(p, out_dtype, stream);           \
+    default: return launch<64, false, EPI, 1>(p, out_dtype, stream);             \
+  }
+    case EPI_LEAN_GATED + 0: YMT3_TC_LAUNCH_LEAN_G(EPI_LEAN_GATED + 0)
+    case EPI_LEAN_GATED + 1: YMT3_TC_LAUNCH_LEAN_G(EPI_LEAN_GATED + 1)
+    case EPI_LEAN_GATED + 2: YMT3_TC_LAUNCH_LEAN_G(EPI_LEAN_GATED + 2)
+    case EPI_LEAN_GATED + 3: YMT3_TC_LAUNCH_LEAN_G(EPI_LEAN_GATED + 3)
+#undef YMT3_TC_LAUNCH_LEAN_G
 #undef YMT3_TC_LAUNCH_LEAN
     case EPI_PLAIN_BF16: YMT3_TC_LAUNCH(EPI_PLAIN_BF16)
     case EPI_PLAIN_F32: YMT3_TC_LAUNCH(EPI_PLAIN_F32)

@@ -342,7 +342,7 @@ extern "C" int ymt3_t5dec_create(const ymt3_t5_cfg_t* cfg, const ymt3_tensor_t* 
     }
   }
   d->fuse_norm = cfg->precision == YMT3_BF16 && D % 128 == 0 && getenv("YMT3_NO_FUSED_NORM") == nullptr;
-  d->use_chain = d->fuse_norm && getenv("YMT3_NO_GEMM_CHAIN") == nullptr;
+  d->use_chain = d->fuse_norm && getenv("YMT3_GEMM_CHAIN") != nullptr;   // opt-in until it beats the separate launches
   if (!rc) {
     d->d_step = (int*)d->weights.alloc(64);
     d->d_unfinished = d->d_step + 4;

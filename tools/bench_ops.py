@@ -90,8 +90,8 @@ if what == "chain728":
     ncnt = int(lib.ymt3_op_linear_chain_counters(M))
 
     def mk():
-        return dict(x=x0.clone(), qz=torch.empty(M, HZ, device=dev, dtype=torch.bfloat16), gbuf=torch.empty(M, F, device=dev, dtype=torch.bfloat16),
-                    qkv=torch.empty(M, 3 * INNER, device=dev, dtype=torch.bfloat16), sA=torch.zeros(M, 16, device=dev), sB=torch.zeros(M, 16, device=dev),
+        return dict(x=x0.clone(), qz=torch.zeros(M, HZ, device=dev, dtype=torch.bfloat16), gbuf=torch.zeros(M, F, device=dev, dtype=torch.bfloat16),
+                    qkv=torch.zeros(M, 3 * INNER, device=dev, dtype=torch.bfloat16), sA=torch.zeros(M, 16, device=dev), sB=torch.zeros(M, 16, device=dev),
                     sC=torch.zeros(M, 16, device=dev))
 
     def phases(b, which):

@@ -383,14 +383,14 @@ __device__ __forceinline__ float2 lean_fma2(float2 a, float2 b, float2 c) {
 // (s = the one scale factor of the general path that is not exactly 1).  rr: the 32 residual bytes of this row segment.
 // ssacc: running (even, odd column) sums of squares of the rounded outputs of the chunk.  dst / u0 / sx: staging row,
 // first 16-byte unit (compile-time after unrolling), swizzle.
-template <bool BIAS, bool RES, bool SS>
-__device__ __forceinline__ void lean_half(const uint32_t (&v)[16], float s, const float* bias_c, const uint4 (&rr)[2],
-                                          float2& ssacc, uint32_t dst, int u0, int sx) {
+// (BIAS / RES / SS: compile-time constants in the single-GEMM instances, warp-uniform register predicates in the chain)
+__device__ __forceinline__ void lean_half(const bool BIAS, const bool RES, const bool SS, const uint32_t (&v)[16], float s,
+                                          const float* bias_c, const uint4 (&rr)[2], float2& ssacc, uint32_t dst, int u0, int sx) {
   float2 f[8];
   const float2 a1 = make_float2(s, s);
 #pragma unroll
   for (int q = 0; q < 8; ++q) f[q] = lean_mul2(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), a1);
-  if constexpr (BIAS) {
+  if (BIAS) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(bias_c) + q);
@@ -398,7 +398,7 @@ __device__ __forceinline__ void lean_half(const uint32_t (&v)[16], float s, cons
       f[2 * q + 1] = lean_add2(f[2 * q + 1], make_float2(b.z, b.w));
     }
   }
-  if constexpr (RES) {
+  if (RES) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(&rr[0]);
 #pragma unroll
     for (int q = 0; q < 8; ++q) f[q] = lean_add2(f[q], bf16x2_as_f2(w[q]));
@@ -409,7 +409,7 @@ __device__ __forceinline__ void lean_half(const uint32_t (&v)[16], float s, cons
     const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[q].x, f[q].y);
     h[q] = *reinterpret_cast<const uint32_t*>(&b2);
   }
-  if constexpr (SS) {
+  if (SS) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float2 u = bf16x2_as_f2(h[q]);
@@ -506,6 +506,165 @@ struct SmemLayout {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// ---- context of one tile for lean_tile (everything it needs from the kernel around it)
+struct LeanCtx {
+  const CUtensorMap* mapC;
+  int N; const void* residual; int64_t ldr; float* ss_out; int ss_out_chunks; void* C; int64_t ldc;
+  const float* bias;
+  int m0, row_end, n0, r; bool row_ok, warp_tma; float pre, rs;
+  uint32_t tmem_base; int buf; uint64_t* full_bar; uint64_t* empty_bar; uint32_t full_parity;
+  uint8_t* stg; int quad, half, lane, j; bool stamp; unsigned long long* trace;
+  int flags;   // EPI == 72 only: bias | residual << 1 | sum of squares << 2
+};
+#define LEAN_STAMP(j, e) chain_stamp(c.trace, j, e)
+// ---- LEAN tile epilogue (lean_half): the warp's CPW * 32 columns as 16-column halves, software-pipelined: the
+// TMEM load of half g + 1 is in flight while half g is scaled / packed / staged, and the residual bytes are
+// fetched three halves ahead (the first three before the accumulator is complete).  Bias / residual / sum of
+// squares are COMPILE-TIME properties of the instance and everything that depends on kernel parameters is
+// computed once per tile: the general path re-reads parameters through the uniform datapath and branches on
+// them ~10 times per chunk (LDCU -> UISETP -> BRA chains, the `branch_resolving` / `wait` stalls of the ncu
+// source view), which - not TMEM or shared-memory traffic - is what a 32-column chunk's ~1000 clk were made of
+// (leave-out experiments + timeline: profiles/r02_gemm_epilogue_timeline.txt).
+// EPI: 64 + flags (plain) / 80 + flags (gated) as in the kernel; L2: residual reads bypass L1 and start only after the
+// accumulator barrier (chained launches: the rows were written earlier in the SAME launch, possibly by another SM).
+template <int BN, int EPI, int CL, bool L2>
+__device__ __forceinline__ void lean_tile(const LeanCtx& c) {
+  constexpr bool LG = EPI >= 80;
+  constexpr int CPW = SmemLayout<BN, CL>::CPW;
+  constexpr int NCHUNK = BN / 32;
+  const LeanCtx& p = c;
+  const CUtensorMap& mapC = *c.mapC;
+  const int m0 = c.m0, row_end = c.row_end, n0 = c.n0, r = c.r, quad = c.quad, half = c.half, lane = c.lane, buf = c.buf;
+  [[maybe_unused]] const int j = c.j;
+  const bool row_ok = c.row_ok, warp_tma = c.warp_tma;
+  const float pre = c.pre, rs = c.rs;
+  [[maybe_unused]] const float* bias = c.bias;
+  const uint32_t tmem_base = c.tmem_base;
+  uint8_t* stg = c.stg;
+  constexpr int H = 2 * CPW;                                   // halves per warp
+  constexpr int SRB = LG ? (CPW * 32 > 128 ? 128 : CPW * 32)   // bytes per staged box row (gated: 8 outputs per half)
+                         : (CPW * 64 > 128 ? 128 : CPW * 64);
+  const int sxor = tma_swizzle_xor(lane, SRB);   // index_maps.h
+  // bias, residual, sum of squares: compile-time, or (EPI == 72: the chained kernel's plain phases) run-time flags that
+  // live in predicate registers for the whole tile
+  constexpr bool RT = EPI == 72;
+  const bool LB = RT ? (c.flags & 1) != 0 : (EPI & 1) != 0;
+  const bool LR = RT ? (c.flags & 2) != 0 : (!LG && (EPI & 2) != 0);
+  const bool LS = RT ? (c.flags & 4) != 0 : (!LG && (EPI & 4) != 0);
+  constexpr int G_ACT = (EPI & 2) ? YMT3_ACT_SILU : YMT3_ACT_GELU_NEW;   // (gated instances)
+  const int c_first = n0 + half * CPW * 32;                    // first accumulator column of this warp
+  const int n_cols = p.N;
+  // a ragged last slab of a group (grouped gated GEMM) cannot leave through the box store (it would spill into the
+  // next group's rows): direct 16-byte stores for its rows
+  const bool slab_rows = m0 + quad * 32 < row_end;             // this warp's slab has rows in the tile at all
+  [[maybe_unused]] const bool slab_direct = LG && slab_rows && !warp_tma;
+  // number of this warp's halves that hold real columns (N % 32 == 0: always even); 0: nothing to do
+  const int nv = (slab_rows && (warp_tma || slab_direct) && half * CPW < NCHUNK && c_first < n_cols)
+      ? min(H, (n_cols - c_first) >> 4) : 0;
+  // rows past the end of the tile: loads clamped to the last row, the box store clips them
+  [[maybe_unused]] const __nv_bfloat16* Rrow = nullptr;
+  [[maybe_unused]] uint4 rq[4][2];                             // residual ring: half g lives in rq[g & 3]
+  if (LR) {
+    Rrow = static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)(row_ok ? r : row_end - 1) * p.ldr + c_first;
+    if constexpr (!L2) {   // (chained launch: the rows may still be in flight from another SM until the accumulator barrier)
+#pragma unroll
+      for (int g = 0; g < 3 && g < H; ++g)
+        if (g < nv) lean_load_res16<L2>(rq[g], Rrow + 16 * g);
+    }
+  }
+  [[maybe_unused]] const float* bias_w = LB ? bias + c_first : nullptr;
+  [[maybe_unused]] float* ss_w = LS ? p.ss_out + (int64_t)(row_ok ? r : row_end - 1) * p.ss_out_chunks + (c_first >> 5) : nullptr;
+  const float s1 = LG ? pre : pre * rs;   // plain: the host selects this instance only when one factor is exactly 1
+  [[maybe_unused]] __nv_bfloat16* Cdir = nullptr;   // gated, ragged slab: this thread's output row segment
+  if constexpr (LG) {
+    if (slab_direct) Cdir = static_cast<__nv_bfloat16*>(p.C) + (int64_t)(row_ok ? r : row_end - 1) * p.ldc + (c_first >> 1);
+  }
+  mbar_wait(c.full_bar, c.full_parity);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (c.stamp) LEAN_STAMP(j, 4);
+  if (LR && L2) {
+#pragma unroll
+    for (int g = 0; g < 3 && g < H; ++g)
+      if (g < nv) lean_load_res16<L2>(rq[g], Rrow + 16 * g);
+  }
+  const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * CPW * 32);
+  uint32_t va[16], vb[16];
+  if (nv > 0) {
+    tmem_ld16_nowait(t_addr, va);
+    if (lane == 0) tma_store_wait_read<0>();   // the previous tile's box has left the staging buffer
+    __syncwarp();
+  } else {   // a warp without columns in this tile still releases the accumulator
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if constexpr (CL == 2) mbar_arrive_cluster(mapa_u32(c.empty_bar, 0));
+    else mbar_arrive(c.empty_bar);
+  }
+  float2 ssacc = make_float2(0.f, 0.f);
+  const uint32_t dst = smem_u32(stg) + (uint32_t)(lane * SRB);
+#pragma unroll
+  for (int g = 0; g < H; ++g) {
+    if (g < nv) {                                             // warp-uniform
+      const bool new_box = !LG && g > 0 && (g * 32) % SRB == 0;   // compile-time after unrolling
+      if (new_box) {
+        // this half opens the warp's next staging box: the finished one goes to the TMA engine; its read-out
+        // overlaps the TMEM wait below
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&mapC, stg, c_first + ((g * 32) / SRB - 1) * (SRB >> 1), m0 + quad * 32);
+          tma_store_commit();
+        }
+      }
+      if (g & 1) tmem_wait_ld(vb); else tmem_wait_ld(va);      // half g is in registers
+      if (g + 1 < nv) {
+        if (g & 1) tmem_ld16_nowait(t_addr + 16 * (g + 1), va); else tmem_ld16_nowait(t_addr + 16 * (g + 1), vb);
+      } else {
+        // that was this warp's last TMEM load of the tile: hand the accumulator back to the MMA warp
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if constexpr (CL == 2) mbar_arrive_cluster(mapa_u32(c.empty_bar, 0));   // the LEADER's barrier
+        else mbar_arrive(c.empty_bar);
+      }
+      if (LR) {
+        if (g + 3 < nv) lean_load_res16<L2>(rq[(g + 3) & 3], Rrow + 16 * (g + 3));
+      }
+      if (new_box) {   // the buffer is rewritten only after the TMA engine has read the previous box
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
+      if constexpr (LG) {
+        uint32_t h4[4];
+        lean_half_gated<G_ACT, (EPI & 1) != 0>((g & 1) ? vb : va, s1, rs, LB ? bias_w + 16 * g : nullptr, h4);
+        if (!slab_direct)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((g << 4) ^ sxor)), "r"(h4[0]),
+                       "r"(h4[1]), "r"(h4[2]), "r"(h4[3])
+                       : "memory");
+        else if (row_ok)
+          *reinterpret_cast<uint4*>(Cdir + 8 * g) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+      } else {
+        lean_half(LB, LR, LS, (g & 1) ? vb : va, s1, LB ? bias_w + 16 * g : nullptr, rq[g & 3], ssacc, dst,
+                              ((g * 32) % SRB) >> 4, sxor);
+      }
+      if (LS) {
+        if (g & 1) {
+          if (row_ok) ss_w[g >> 1] = ssacc.x + ssacc.y;
+          ssacc = make_float2(0.f, 0.f);
+        }
+      }
+    }
+  }
+  if (nv > 0 && !slab_direct) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      // the box this warp wrote last (earlier ones left inside the loop); columns >= N / rows >= M are clipped
+      if constexpr (LG) tma_store_2d(&mapC, stg, c_first >> 1, m0 + quad * 32);
+      else tma_store_2d(&mapC, stg, c_first + (((nv - 1) * 32) / SRB) * (SRB >> 1), m0 + quad * 32);
+      tma_store_commit();
+    }
+  }
+  if (c.stamp) LEAN_STAMP(j, 5);
+}
+#undef LEAN_STAMP
 
 // Persistent kernel: one CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).  The TMA
 // producer runs ahead across tiles through a STAGES-deep smem ring; the accumulator is DOUBLE-BUFFERED in
@@ -776,123 +935,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
       constexpr int NCHUNK = BN / 32;
       if constexpr (LEAN) {
-        // ---- LEAN tile epilogue (lean_half): the warp's CPW * 32 columns as 16-column halves, software-pipelined: the
-        // TMEM load of half g + 1 is in flight while half g is scaled / packed / staged, and the residual bytes are
-        // fetched three halves ahead (the first three before the accumulator is complete).  Bias / residual / sum of
-        // squares are COMPILE-TIME properties of the instance and everything that depends on kernel parameters is
-        // computed once per tile: the general path re-reads parameters through the uniform datapath and branches on
-        // them ~10 times per chunk (LDCU -> UISETP -> BRA chains, the `branch_resolving` / `wait` stalls of the ncu
-        // source view), which - not TMEM or shared-memory traffic - is what a 32-column chunk's ~1000 clk were made of
-        // (leave-out experiments + timeline: profiles/r02_gemm_epilogue_timeline.txt).
-        constexpr int H = 2 * CPW;                                   // halves per warp
-        constexpr int SRB = LG ? (CPW * 32 > 128 ? 128 : CPW * 32)   // bytes per staged box row (gated: 8 outputs per half)
-                               : (CPW * 64 > 128 ? 128 : CPW * 64);
-        constexpr bool LB = (EPI & 1) != 0, LR = !LG && (EPI & 2) != 0, LS = !LG && (EPI & 4) != 0;   // bias, residual, sum of squares
-        constexpr int G_ACT = (EPI & 2) ? YMT3_ACT_SILU : YMT3_ACT_GELU_NEW;   // (gated instances)
-        const int c_first = n0 + half * CPW * 32;                    // first accumulator column of this warp
-        const int n_cols = p.N;
-        // a ragged last slab of a group (grouped gated GEMM) cannot leave through the box store (it would spill into the
-        // next group's rows): direct 16-byte stores for its rows
-        const bool slab_rows = m0 + quad * 32 < row_end;             // this warp's slab has rows in the tile at all
-        [[maybe_unused]] const bool slab_direct = LG && slab_rows && !warp_tma;
-        // number of this warp's halves that hold real columns (N % 32 == 0: always even); 0: nothing to do
-        const int nv = (slab_rows && (warp_tma || slab_direct) && half * CPW < NCHUNK && c_first < n_cols)
-            ? min(H, (n_cols - c_first) >> 4) : 0;
-        // rows past the end of the tile: loads clamped to the last row, the box store clips them
-        [[maybe_unused]] const __nv_bfloat16* Rrow = nullptr;
-        [[maybe_unused]] uint4 rq[4][2];                             // residual ring: half g lives in rq[g & 3]
-        if constexpr (LR) {
-          Rrow = static_cast<const __nv_bfloat16*>(p.residual) + (int64_t)(row_ok ? r : row_end - 1) * p.ldr + c_first;
-#pragma unroll
-          for (int g = 0; g < 3 && g < H; ++g)
-            if (g < nv) lean_load_res16<false>(rq[g], Rrow + 16 * g);
-        }
-        [[maybe_unused]] const float* bias_w = LB ? bias + c_first : nullptr;
-        [[maybe_unused]] float* ss_w = LS ? p.ss_out + (int64_t)(row_ok ? r : row_end - 1) * p.ss_out_chunks + (c_first >> 5) : nullptr;
-        const float s1 = LG ? pre : pre * rs;   // plain: the host selects this instance only when one factor is exactly 1
-        [[maybe_unused]] __nv_bfloat16* Cdir = nullptr;   // gated, ragged slab: this thread's output row segment
-        if constexpr (LG) {
-          if (slab_direct) Cdir = static_cast<__nv_bfloat16*>(p.C) + (int64_t)(row_ok ? r : row_end - 1) * p.ldc + (c_first >> 1);
-        }
-        mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        [[maybe_unused]] const bool stamp = warp == 2 && lane == 0;
-        if (stamp) TC_STAMP(j, 4);
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * CPW * 32);
-        uint32_t va[16], vb[16];
-        if (nv > 0) {
-          tmem_ld16_nowait(t_addr, va);
-          if (lane == 0) tma_store_wait_read<0>();   // the previous tile's box has left the staging buffer
-          __syncwarp();
-        } else {   // a warp without columns in this tile still releases the accumulator
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if constexpr (CL == 2) mbar_arrive_cluster(mapa_u32(&tmem_empty_bar[buf], 0));
-          else mbar_arrive(&tmem_empty_bar[buf]);
-        }
-        float2 ssacc = make_float2(0.f, 0.f);
-        const uint32_t dst = smem_u32(stg) + (uint32_t)stg_row;
-#pragma unroll
-        for (int g = 0; g < H; ++g) {
-          if (g < nv) {                                             // warp-uniform
-            const bool new_box = !LG && g > 0 && (g * 32) % SRB == 0;   // compile-time after unrolling
-            if (new_box) {
-              // this half opens the warp's next staging box: the finished one goes to the TMA engine; its read-out
-              // overlaps the TMEM wait below
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&mapC, stg, c_first + ((g * 32) / SRB - 1) * (SRB >> 1), m0 + quad * 32);
-                tma_store_commit();
-              }
-            }
-            if (g & 1) tmem_wait_ld(vb); else tmem_wait_ld(va);      // half g is in registers
-            if (g + 1 < nv) {
-              if (g & 1) tmem_ld16_nowait(t_addr + 16 * (g + 1), va); else tmem_ld16_nowait(t_addr + 16 * (g + 1), vb);
-            } else {
-              // that was this warp's last TMEM load of the tile: hand the accumulator back to the MMA warp
-              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              if constexpr (CL == 2) mbar_arrive_cluster(mapa_u32(&tmem_empty_bar[buf], 0));   // the LEADER's barrier
-              else mbar_arrive(&tmem_empty_bar[buf]);
-            }
-            if constexpr (LR) {
-              if (g + 3 < nv) lean_load_res16<false>(rq[(g + 3) & 3], Rrow + 16 * (g + 3));
-            }
-            if (new_box) {   // the buffer is rewritten only after the TMA engine has read the previous box
-              if (lane == 0) tma_store_wait_read<0>();
-              __syncwarp();
-            }
-            if constexpr (LG) {
-              uint32_t h4[4];
-              lean_half_gated<G_ACT, LB>((g & 1) ? vb : va, s1, rs, LB ? bias_w + 16 * g : nullptr, h4);
-              if (!slab_direct)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((g << 4) ^ stg_xor)), "r"(h4[0]),
-                             "r"(h4[1]), "r"(h4[2]), "r"(h4[3])
-                             : "memory");
-              else if (row_ok)
-                *reinterpret_cast<uint4*>(Cdir + 8 * g) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-            } else {
-              lean_half<LB, LR, LS>((g & 1) ? vb : va, s1, LB ? bias_w + 16 * g : nullptr, rq[g & 3], ssacc, dst,
-                                    ((g * 32) % SRB) >> 4, stg_xor);
-            }
-            if constexpr (LS) {
-              if (g & 1) {
-                if (row_ok) ss_w[g >> 1] = ssacc.x + ssacc.y;
-                ssacc = make_float2(0.f, 0.f);
-              }
-            }
-          }
-        }
-        if (nv > 0 && !slab_direct) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            // the box this warp wrote last (earlier ones left inside the loop); columns >= N / rows >= M are clipped
-            if constexpr (LG) tma_store_2d(&mapC, stg, c_first >> 1, m0 + quad * 32);
-            else tma_store_2d(&mapC, stg, c_first + (((nv - 1) * 32) / SRB) * (SRB >> 1), m0 + quad * 32);
-            tma_store_commit();
-          }
-        }
-        if (stamp) TC_STAMP(j, 5);
+        LeanCtx lc;
+        lc.mapC = &mapC;
+        lc.N = p.N; lc.residual = p.residual; lc.ldr = p.ldr; lc.ss_out = p.ss_out; lc.ss_out_chunks = p.ss_out_chunks;
+        lc.C = p.C; lc.ldc = p.ldc; lc.bias = bias;
+        lc.m0 = m0; lc.row_end = row_end; lc.n0 = n0; lc.r = r; lc.row_ok = row_ok; lc.warp_tma = warp_tma; lc.pre = pre; lc.rs = rs;
+        lc.tmem_base = tmem_base; lc.buf = buf; lc.full_bar = &tmem_full_bar[buf]; lc.empty_bar = &tmem_empty_bar[buf];
+        lc.full_parity = (uint32_t)((j >> 1) & 1);
+        lc.stg = stg; lc.quad = quad; lc.half = half; lc.lane = lane; lc.j = j; lc.stamp = false; lc.trace = nullptr; lc.flags = 0;
+#ifdef YMT3_GEMM_TRACE
+        lc.stamp = warp == 2 && lane == 0; lc.trace = p.trace;
+#endif
+        lean_tile<BN, EPI, CL, false>(lc);
         continue;
       }
       // (the per-row loads above do not depend on the accumulator: they are issued before the wait)
@@ -1065,6 +1119,7 @@ struct alignas(64) ChainPhase {
   CUtensorMap mapA, mapW, mapC;
   TcParams p;
   int tile0, n_tiles, num_kb, dep;   // first tile index, N tiles, k-blocks, 1 = depends on the previous phase
+  int kind;                          // lean epilogue instance (EPI_LEAN_BF16 + flags / EPI_LEAN_GATED)
 };
 struct alignas(64) ChainArgs {
   ChainPhase ph[CHAIN_MAX_PHASES];
@@ -1236,34 +1291,31 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_chain_kernel(const __grid_con
       }
     });
   } else {
-    // ===================== epilogue (8 warps) =====================
+    // ===================== epilogue (8 warps): lean_tile, the kind of the phase selected once per tile ================
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    constexpr int CPW = L::CPW;          // 4 chunks of 32 columns per warp
     uint8_t* stg = smem + L::STG_OFF + (warp - 2) * L::STG_WARP_BYTES;
     walk([&](int j, int ph, int mt, int nt, bool, bool last_nt) {
       const TcParams& p = a.ph[ph].p;
-      const CUtensorMap* mapC = &a.ph[ph].mapC;
-      const bool e_gated = p.gated != 0;
-      const bool e_tma = p.tma_store != 0;
-      const int m0 = mt * BM, n0 = nt * BN;
-      const int stg_rb_all = CPW * (e_gated ? 32 : 64);
-      const int stg_rb = stg_rb_all > 128 ? 128 : stg_rb_all;
-      const int stg_row = lane * stg_rb;
-      const int stg_xor = tma_swizzle_xor(lane, stg_rb);
       const int buf = j & 1;
-      const int r = m0 + quad * 32 + lane;
-      const bool row_ok = r < p.M;
-      const bool warp_tma = e_tma && m0 + quad * 32 < p.M;
-      const float rs = p.out_scale;
-      mbar_wait(&tmem_full_bar[buf], (j >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (warp == 2 && lane == 0) chain_stamp(a.trace, j, 4);
-      // (every tile of this phase with a dependency was gated by the producer's acquire; the accumulator barrier
-      //  orders this thread after it; L1 is bypassed for data written earlier in this launch)
+      const int m0 = mt * BM;
+      LeanCtx lc;
+      lc.mapC = &a.ph[ph].mapC;
+      lc.N = p.N; lc.residual = p.residual; lc.ldr = p.ldr; lc.ss_out = p.ss_out; lc.ss_out_chunks = p.ss_out_chunks;
+      lc.C = p.C; lc.ldc = p.ldc; lc.bias = p.bias;
+      lc.m0 = m0; lc.row_end = p.M; lc.n0 = nt * BN; lc.r = m0 + quad * 32 + lane; lc.row_ok = lc.r < p.M;
+      lc.warp_tma = m0 + quad * 32 < p.M;
+      lc.rs = p.out_scale;
+      lc.tmem_base = tmem_base; lc.buf = buf; lc.full_bar = &tmem_full_bar[buf]; lc.empty_bar = &tmem_empty_bar[buf];
+      lc.full_parity = (uint32_t)((j >> 1) & 1);
+      lc.stg = stg; lc.quad = quad; lc.half = half; lc.lane = lane; lc.j = j;
+      lc.stamp = warp == 2 && lane == 0; lc.trace = a.trace;
+      // the accumulator barrier also orders this thread after the producer's acquire of the previous phase: only now may
+      // the sum-of-squares partials (written earlier in this launch, L1 bypassed) be read
+      mbar_wait(lc.full_bar, lc.full_parity);
       float pre = 1.0f;
-      if (p.norm_ss_in && row_ok) {
-        const float* sp = p.norm_ss_in + (int64_t)r * p.norm_ss_chunks;
+      if (p.norm_ss_in && lc.row_ok) {
+        const float* sp = p.norm_ss_in + (int64_t)lc.r * p.norm_ss_chunks;
         float tot = 0.f;
         for (int c4 = 0; c4 + 4 <= p.norm_ss_chunks; c4 += 4) {
           const float4 s4 = __ldcg(reinterpret_cast<const float4*>(sp + c4));
@@ -1272,131 +1324,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_chain_kernel(const __grid_con
         for (int c1 = p.norm_ss_chunks & ~3; c1 < p.norm_ss_chunks; ++c1) tot += __ldcg(sp + c1);
         pre = rsqrtf(tot / (float)p.K + p.norm_eps);
       }
-      const int c_first = n0 + half * CPW * 32;
-      const bool stage_any = warp_tma && c_first < p.N;
-      if (stage_any) {
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-      }
-#pragma unroll 1
-      for (int k = 0; k < CPW; ++k) {
-        const int ci = half * CPW + k;
-        const bool last = k == CPW - 1;
-        uint32_t v[32];
-        bool box_in_flight = false;
-        const bool stamp = warp == 2 && lane == 0;
-        if (stamp) chain_stamp(a.trace, j, 8 + 6 * k);
-        __syncwarp();
-        {
-          const int b0k = k * (e_gated ? 32 : 64);
-          if (stage_any && b0k > 0 && b0k % stg_rb == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-              const int cb = (e_gated ? (c_first >> 1) : c_first) + (b0k / stg_rb - 1) * (stg_rb >> 1);
-              if (cb < (e_gated ? (p.N >> 1) : p.N)) tma_store_2d(mapC, stg, cb, m0 + quad * 32);
-              tma_store_commit();
-            }
-            box_in_flight = true;
-          }
-        }
-        if (stamp) chain_stamp(a.trace, j, 9 + 6 * k);
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + ci * 32), v);
-        if (stamp) chain_stamp(a.trace, j, 10 + 6 * k);
-        if (last) {
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(&tmem_empty_bar[buf]);
-        }
-        const int c = n0 + ci * 32;
-        const bool active = row_ok && c < p.N;
-        float f[32];
-        if (active) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]) * pre;
-          if (p.bias) {
-            if (c + 32 <= p.N) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + c) + q);
-                f[4 * q] += bq.x; f[4 * q + 1] += bq.y; f[4 * q + 2] += bq.z; f[4 * q + 3] += bq.w;
-              }
-            } else {
-#pragma unroll
-              for (int q = 0; q < 32; ++q)
-                if (c + q < p.N) f[q] += __ldg(p.bias + c + q);
-            }
-          }
-          epi_dispatch(f, rs, p.act, e_gated);
-        }
-        if (stamp) chain_stamp(a.trace, j, 11 + 6 * k);
-        if (box_in_flight) {
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
-        }
-        if (stamp) chain_stamp(a.trace, j, 12 + 6 * k);
-        if (active) {
-          const int n_out = e_gated ? min(16, (p.N - c) >> 1) : min(32, p.N - c);
-          const int64_t off = (int64_t)r * p.ldc + (e_gated ? (c >> 1) : c);
-          const int64_t roff = (int64_t)r * p.ldr + (e_gated ? (c >> 1) : c);
-          const __nv_bfloat16* R = p.residual ? static_cast<const __nv_bfloat16*>(p.residual) + roff : nullptr;
-          // residual through L2 (__ldcg): the row may have been rewritten earlier in this launch
-          uint4 rr[4];
-          if (R) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (8 * q < n_out) rr[q] = __ldcg(reinterpret_cast<const uint4*>(R + 8 * q));
-          }
-          float sq = 0.f;
-          const bool want_ss = p.ss_out != nullptr;
-          __nv_bfloat16* Cd = static_cast<__nv_bfloat16*>(p.C) + off;
-          const int b0 = k * (e_gated ? 32 : 64);
-          uint8_t* dst = stg + stg_row;
-          const int u0 = (b0 % stg_rb) >> 4;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            if (8 * q4 >= n_out) break;
-            uint4 pk;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-            if (R) {
-              const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&rr[q4]);
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                h[q] = __floats2bfloat162_rn(f[8 * q4 + 2 * q] + __bfloat162float(th[q].x),
-                                             f[8 * q4 + 2 * q + 1] + __bfloat162float(th[q].y));
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[8 * q4 + 2 * q], f[8 * q4 + 2 * q + 1]);
-            }
-            if (want_ss) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 v2 = __bfloat1622float2(h[q]);
-                sq = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, sq));
-              }
-            }
-            if (warp_tma) *reinterpret_cast<uint4*>(dst + ((((u0 + q4) << 4)) ^ stg_xor)) = pk;
-            else *reinterpret_cast<uint4*>(Cd + 8 * q4) = pk;
-          }
-          if (want_ss) p.ss_out[(int64_t)r * p.ss_out_chunks + (c >> 5)] = sq;
-        }
-        if (stamp) chain_stamp(a.trace, j, 13 + 6 * k);
-      }
-      if (stage_any) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          const int co = e_gated ? (c_first >> 1) : c_first;
-          const int n_out_cols = e_gated ? (p.N >> 1) : p.N;
-          const int b = (stg_rb_all - 1) / stg_rb;
-          if (co + b * (stg_rb >> 1) < n_out_cols) tma_store_2d(mapC, stg, co + b * (stg_rb >> 1), m0 + quad * 32);
-          tma_store_commit();
-        }
-      }
-      if (warp == 2 && lane == 0) chain_stamp(a.trace, j, 5);
+      lc.pre = pre;
+      const int kind = a.ph[ph].kind;   // warp-uniform, once per tile
+      lc.flags = kind & 7;
+      if (kind < 80) lean_tile<BN, 72, 1, true>(lc);   // plain: bias / residual / sum-of-squares flags in registers
+      else lean_tile<BN, 80, 1, true>(lc);             // gated gelu_new
       if (last_nt) {
         // publish this CTA's share of (phase, row tile): the bytes of all its tiles are WRITTEN (not only read out of
         // shared memory), every epilogue thread's stores (C, sum-of-squares) are fenced, then one thread adds the count
-        if (e_tma && lane == 0) tma_store_wait_all();
+        if (lane == 0) tma_store_wait_all();
         __threadfence();
         epi_bar_sync();
         if (warp == 2 && lane == 0) {
@@ -1629,13 +1565,22 @@ int gemm_chain_bf16(const GemmParams* phases, int n_phases, int* done, const int
                      p.N % (p.gated ? 16 : 8) == 0,
                  "gemm_chain: phase %d: alignment", i);
     YMT3_REQUIRE(!p.group_offsets && !p.argmax_out && !p.row_scale, "gemm_chain: phase %d: unsupported epilogue option", i);
+    // every phase runs a lean epilogue instance (lean_tile): full 32-column chunks, one scale factor
+    YMT3_REQUIRE(p.N % 32 == 0 && p.out_scale == 1.0f, "gemm_chain: phase %d: needs N %% 32 == 0 and out_scale 1", i);
+    const int flags = (p.bias ? 1 : 0) | (p.residual ? 2 : 0) | (p.ss_out ? 4 : 0);
+    if (p.gated)
+      YMT3_REQUIRE(p.act == YMT3_ACT_GELU_NEW && flags == 0, "gemm_chain: phase %d: gated phases are gelu_new without bias / residual", i);
+    else
+      YMT3_REQUIRE(p.act == YMT3_ACT_NONE && (flags == 0 || flags == 1 || flags == 6 || flags == 7),
+                   "gemm_chain: phase %d: unsupported bias / residual / sum-of-squares combination %d", i, flags);
     YMT3_REQUIRE(!p.ss_out || (!p.gated && p.N % 32 == 0), "gemm_chain: phase %d: sum-of-squares output needs N %% 32 == 0", i);
     YMT3_REQUIRE(!p.norm_ss_in || (p.norm_ss_chunks > 0 && p.norm_ss_chunks % 4 == 0), "gemm_chain: phase %d: norm partials", i);
     ChainPhase& P = a.ph[i];
     if ((rc = make_map(&P.mapA, p.A, p.M, p.K, p.lda, BM))) return rc;
     if ((rc = make_map(&P.mapW, p.W, p.N, p.K, p.ldw, BN))) return rc;
-    const int tma_store = p.gated ? 0 : 1;
-    if (tma_store && (rc = make_out_map(&P.mapC, p.C, p.M, p.N, p.ldc, 128))) return rc;
+    const int tma_store = 1;
+    if ((rc = make_out_map(&P.mapC, p.C, p.M, p.gated ? p.N / 2 : p.N, p.ldc, 128))) return rc;
+    P.kind = p.gated ? 80 : 64 + flags;
     TcParams& t = P.p;
     t.tma_store = tma_store;
     t.C = p.C; t.ldc = p.ldc; t.bias = p.bias; t.residual = p.residual; t.ldr = p.ldr;

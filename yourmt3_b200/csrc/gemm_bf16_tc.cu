@@ -1657,12 +1657,12 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   const bool cl2 = cluster_size(p, mt) == 2;
   // lean epilogue instances (single CTA): every chunk full, ONE scale factor (the other exactly 1), compile-time bias /
   // residual / sum-of-squares flags - the combinations the model's GEMMs use
-  if (code == EPI_PLAIN_BF16 && !no_lean && !cl2 && p.N % 32 == 0 && !p.group_offsets && !p.argmax_out && !p.row_scale &&
+  if (code == EPI_PLAIN_BF16 && !no_lean && p.N % 32 == 0 && !p.group_offsets && !p.argmax_out && !p.row_scale &&
       (p.out_scale == 1.0f || (!p.norm_ss_in && !p.bias))) {
     const int flags = (p.bias ? 1 : 0) | (p.residual ? 2 : 0) | (p.ss_out ? 4 : 0);
     if (flags != 4 && flags != 5) code = EPI_LEAN_BF16 + flags;
   }
-  if ((code == EPI_GATED_GELU_NEW || code == EPI_GATED_SILU) && !no_lean && !cl2 && bn >= 64 && p.N % 32 == 0 && !p.argmax_out &&
+  if ((code == EPI_GATED_GELU_NEW || code == EPI_GATED_SILU) && !no_lean && bn >= 64 && p.N % 32 == 0 && !p.argmax_out &&
       !p.residual && !p.ss_out)
     code = EPI_LEAN_GATED + (p.bias ? 1 : 0) + (code == EPI_GATED_SILU ? 2 : 0);
 #define YMT3_TC_LAUNCH(EPI)                                                                                      \
@@ -1675,8 +1675,8 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   switch (code) {
 #define YMT3_TC_LAUNCH_LEAN(EPI)                                                  \
   switch (bn) {                                                                  \
-    case 256: return launch<256, false, EPI, 1>(p, out_dtype, stream);           \
-    case 128: return launch<128, false, EPI, 1>(p, out_dtype, stream);           \
+    case 256: return cl2 ? launch<256, false, EPI, 2>(p, out_dtype, stream) : launch<256, false, EPI, 1>(p, out_dtype, stream); \
+    case 128: return cl2 ? launch<128, false, EPI, 2>(p, out_dtype, stream) : launch<128, false, EPI, 1>(p, out_dtype, stream); \
     case 64: return launch<64, false, EPI, 1>(p, out_dtype, stream);             \
     default: return launch<32, false, EPI, 1>(p, out_dtype, stream);             \
   }
@@ -1688,8 +1688,8 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
     case EPI_LEAN_BF16 + 7: YMT3_TC_LAUNCH_LEAN(EPI_LEAN_BF16 + 7)
 #define YMT3_TC_LAUNCH_LEAN_G(EPI)                                                \
   switch (bn) {                                                                  \
-    case 256: return launch<256, false, EPI, 1>(p, out_dtype, stream);           \
-    case 128: return launch<128, false, EPI, 1>(p, out_dtype, stream);           \
+    case 256: return cl2 ? launch<256, false, EPI, 2>(p, out_dtype, stream) : launch<256, false, EPI, 1>(p, out_dtype, stream); \
+    case 128: return cl2 ? launch<128, false, EPI, 2>(p, out_dtype, stream) : launch<128, false, EPI, 1>(p, out_dtype, stream); \
     default: return launch<64, false, EPI, 1>(p, out_dtype, stream);             \
   }
     case EPI_LEAN_GATED + 0: YMT3_TC_LAUNCH_LEAN_G(EPI_LEAN_GATED + 0)

@@ -59,6 +59,22 @@ def test_op_argument_validation_without_gpu(native_lib):
     assert b"encoder length" in native_lib.ymt3_last_error()
     assert native_lib.ymt3_op_cross_attn_absorbed(p, p, p, 4, 9, 110, 112, None) != 0
     assert b"heads" in native_lib.ymt3_last_error()
+    # chained linears: 1..4 phases, counters given; every phase needs N % 32 == 0 and out_scale 1; gated phases are
+    # gelu_new without bias / residual
+    P = _lib.ChainPhase
+    ok = P(p, 64, p, 64, None, None, 0, 0.0, p, 64, None, 0, None, 64, 64, 0, 0, 1.0)
+    arr = (P * 1)(ok)
+    assert native_lib.ymt3_op_linear_chain(arr, 0, 8, p, 0, None) != 0
+    assert b"bad arguments" in native_lib.ymt3_last_error()
+    assert native_lib.ymt3_op_linear_chain(arr, 1, 8, None, 0, None) != 0
+    assert b"bad arguments" in native_lib.ymt3_last_error()
+    arr = (P * 1)(P(p, 64, p, 64, None, None, 0, 0.0, p, 72, None, 0, None, 72, 64, 0, 0, 1.0))
+    assert native_lib.ymt3_op_linear_chain(arr, 1, 8, p, 0, None) != 0
+    assert b"N % 32" in native_lib.ymt3_last_error()
+    arr = (P * 1)(P(p, 64, p, 64, None, None, 0, 0.0, p, 32, p, 32, None, 64, 64, 1, 1, 1.0))
+    assert native_lib.ymt3_op_linear_chain(arr, 1, 8, p, 0, None) != 0
+    assert b"gated phases" in native_lib.ymt3_last_error()
+    assert native_lib.ymt3_op_linear_chain_counters(300) == 4 * 3
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

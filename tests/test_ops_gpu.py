@@ -392,3 +392,48 @@ def test_decode_attention_step_beyond_capacity_writes_nothing(cuda_device, nativ
                                             _lib.current_stream_ptr()), "decode_attention")
     torch.cuda.synchronize()
     assert not bool((out == 7.0).any()) and torch.equal(buf[:, N * H * Lcap * 64:], before[:, N * H * Lcap * 64:])
+
+
+@pytest.mark.parametrize("M", [100, 1000])
+def test_linear_chain_matches_separate_launches(cuda_device, native_lib, M):
+    """ymt3_op_linear_chain (one persistent launch, per-row-tile dependency counters) == the same phases issued one by
+    one through ymt3_op_linear_normfused, bit for bit: [A0 W0^T + bias + x -> x (sum of squares out)] ->
+    [norm(x) W1^T, gated gelu_new] -> [g W2^T + x -> x (sum of squares out)] -> [norm(x) W3^T]; three launches on the
+    same counters (launch ordinal 0, 1, 2), M = 1000: eight row tiles, the last ragged."""
+    D, K0, F, N3 = 512, 384, 1024, 1152
+    g = torch.Generator().manual_seed(M)
+    rnd = lambda *sh, sc=1.0: (torch.randn(*sh, generator=g) * sc).to(cuda_device, torch.bfloat16)  # noqa: E731
+    a0, x0 = rnd(M, K0), rnd(M, D)
+    W0, W1, W2, W3 = rnd(D, K0, sc=.05), rnd(2 * F, D, sc=.05), rnd(D, F, sc=.03), rnd(N3, D, sc=.05)
+    b0 = (torch.randn(D, generator=g) * 0.1).to(cuda_device)
+    s_ = _lib.current_stream_ptr()
+
+    def bufs():
+        return dict(x=x0.clone(), gbuf=torch.zeros(M, F, device=cuda_device, dtype=torch.bfloat16),
+                    out=torch.zeros(M, N3, device=cuda_device, dtype=torch.bfloat16),
+                    s1=torch.zeros(M, D // 32, device=cuda_device), s2=torch.zeros(M, D // 32, device=cuda_device))
+
+    def phases(b):
+        P = _lib.ChainPhase
+        return [P(a0.data_ptr(), K0, W0.data_ptr(), K0, b0.data_ptr(), None, 0, 0.0, b["x"].data_ptr(), D, b["x"].data_ptr(), D,
+                  b["s1"].data_ptr(), D, K0, 0, 0, 1.0),
+                P(b["x"].data_ptr(), D, W1.data_ptr(), D, None, b["s1"].data_ptr(), D // 32, 1e-6, b["gbuf"].data_ptr(), F, None, 0,
+                  None, 2 * F, D, 1, 1, 1.0),
+                P(b["gbuf"].data_ptr(), F, W2.data_ptr(), F, None, None, 0, 0.0, b["x"].data_ptr(), D, b["x"].data_ptr(), D,
+                  b["s2"].data_ptr(), D, F, 0, 0, 1.0),
+                P(b["x"].data_ptr(), D, W3.data_ptr(), D, None, b["s2"].data_ptr(), D // 32, 1e-6, b["out"].data_ptr(), N3, None, 0,
+                  None, N3, D, 0, 0, 1.0)]
+
+    ref, got = bufs(), bufs()
+    pr, pg = phases(ref), phases(got)
+    arr = (_lib.ChainPhase * 4)(*pg)
+    cnt = torch.zeros(int(native_lib.ymt3_op_linear_chain_counters(M)), device=cuda_device, dtype=torch.int32)
+    for ordinal in range(3):
+        for q in pr:
+            _lib.check(native_lib.ymt3_op_linear_normfused(q.A, q.lda, q.W, q.ldw, q.bias, q.ss_in, q.chunks, q.eps, q.C, q.ldc,
+                                                           q.residual, q.ldr, q.ss_out, M, q.N, q.K, q.act, q.gated, 1.0, 1, s_))
+        _lib.check(native_lib.ymt3_op_linear_chain(arr, 4, M, cnt.data_ptr(), ordinal, s_))
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(ref[k], got[k]), (ordinal, k)
+    assert float(ref["out"].float().abs().mean()) > 1e-3

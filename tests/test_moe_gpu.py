@@ -11,7 +11,7 @@ from oracle import perceiver_tf as OPTF
 from yourmt3_b200 import _lib
 
 pytestmark = pytest.mark.gpu
-ACT = {"silu": 3, "gelu": 4}
+ACT = {"silu": 3, "gelu": 4, "gelu_new": 1}
 
 
 def _weights(E, D, I, seed):
@@ -114,3 +114,21 @@ def test_moe_ff_bf16_flip_rate(cuda_device, native_lib):
     assert float(err.median()) < 4e-3
     assert not bool(flipped[sure].any())
     assert rate < 0.006                             # measured rate + margin
+
+
+@pytest.mark.parametrize("N,act", [(20000, "silu"), (333, "gelu_new"), (40, "silu")])
+def test_moe_fused_expert_kernel_is_bit_identical(cuda_device, native_lib, monkeypatch, N, act):
+    """moe_expert_fused_kernel (both expert GEMMs in one kernel, hidden tile in shared memory; d_model 128 / hidden 512)
+    == the two grouped tcgen05 GEMMs it replaces (YMT3_NO_MOE_FUSED=1), bit for bit: same k order of the accumulations,
+    hidden activations rounded to bf16 at the same point.  N = 40: experts with 0-20 rows (ragged / empty groups)."""
+    D, I, E, topk = 128, 512, 8, 2
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(N, D, generator=g)
+    res = torch.randn(N, D, generator=g)
+    sd = _weights(E, D, I, seed=7)
+    monkeypatch.delenv("YMT3_NO_MOE_FUSED", raising=False)
+    fused = moe_native(native_lib, cuda_device, x, res, sd, E, topk, act, _lib.DTYPE_BF16)
+    monkeypatch.setenv("YMT3_NO_MOE_FUSED", "1")
+    plain = moe_native(native_lib, cuda_device, x, res, sd, E, topk, act, _lib.DTYPE_BF16)
+    assert float((plain - res).abs().max()) > 1e-2
+    assert torch.equal(fused, plain)

@@ -1092,6 +1092,302 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
 
 // =====================================================================================================================
+// FUSED MoE EXPERT MLP (Perceiver-TF feed-forward, model/ff_layer.py MoE experts = HF modeling_mixtral.py:62-85):
+//   ys[slot, :] = slot_w[slot] * ( act(xs W1_e^T) * (xs W3_e^T) ) W2_e^T        for the rows of every expert e
+// in ONE kernel: the hidden tile never leaves the SM.  The two grouped GEMMs it replaces write and re-read the
+// (2 N, I) hidden matrix (4.3 GB + 4.3 GB per layer at 728 segments: GEMM1 is bound by that write).
+// Shapes are compile-time: d_model 128, hidden 512 (the model's), rows of W13 interleaved (2j = activated, 2j+1 = linear).
+// One CTA per SM walks the 128-row tiles of the expert-sorted rows (ragged last tile per expert: rows of the next
+// expert are computed and not stored).  Per tile, with X = the tile's rows (2 k-blocks, resident), H = HALF of the
+// hidden tile (4 k-blocks of 128 x 64 bf16 in the tensor core's K-major 128-byte-swizzle layout):
+//   MMA job list   c0 c1 c2 c3 c4 g0 c5 c6 c7 g1
+//     c_i : acc[i & 1] (128 TMEM columns) = X  W13[e, 128 i .. 128 i + 127, :]^T      (2 k-blocks, N = 128)
+//     g_h : Y (128 TMEM columns)        += H_h W2[e, :, 256 h .. 256 h + 255]^T      (4 k-blocks, N = 128)
+//   epilogue warps, chunk i: acc[i & 1] -> act(even) * odd -> 64 bf16 outputs per row -> H slot (i & 3); after chunk 3 / 7
+//   the half is published to the MMA warp; after g1: Y * slot_w -> bf16 -> global.
+// Every weight block (W13 128 x 64, W2 128 x 64: 16 KB) streams through one 8-stage TMA ring in job order.
+// Same arithmetic as the two grouped GEMMs (same k order of the accumulations, H rounded to bf16 exactly as the hidden
+// matrix was): bit-identical outputs (tests/test_moe_gpu.py).
+// =====================================================================================================================
+namespace moefused {
+constexpr int D = 128, I = 512;
+constexpr int STAGE = 16384;                 // one 128 x 64 bf16 block
+constexpr int X_OFF = 0, H_OFF = 2 * STAGE, RING_OFF = 6 * STAGE, NST = 8;
+constexpr int BAR_OFF = RING_OFF + NST * STAGE;
+constexpr int TOTAL = BAR_OFF + 1024 + 1024;   // barriers / tables, alignment slack
+static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+constexpr int MAX_E = 32;
+}  // namespace moefused
+
+template <int ACT>
+__global__ void __launch_bounds__(THREADS, 1)
+moe_expert_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW13,
+                        const __grid_constant__ CUtensorMap mapW2, const int* __restrict__ offsets, int E,
+                        const float* __restrict__ slot_w, __nv_bfloat16* __restrict__ ys) {
+  using namespace moefused;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* ring_full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* ring_empty = ring_full + NST;
+  uint64_t* x_full = ring_empty + NST;
+  uint64_t* x_empty = x_full + 1;
+  uint64_t* acc_full = x_empty + 1;     // [2]
+  uint64_t* acc_empty = acc_full + 2;   // [2]
+  uint64_t* h_full = acc_empty + 2;     // half of the hidden tile written (all epilogue threads arrive)
+  uint64_t* h_empty = h_full + 1;       // the MMAs that read it have retired
+  uint64_t* y_full = h_empty + 1;
+  uint64_t* y_empty = y_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
+  int* goff = reinterpret_cast<int*>(tmem_slot + 2);   // [E + 1] row offsets of the experts
+  int* gstart = goff + MAX_E + 1;                      // [E + 1] tile-index prefix
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW13) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW2) : "memory");
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&ring_full[i], 1);
+      mbar_init(&ring_empty[i], 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], EPI_THREADS);
+    }
+    mbar_init(h_full, EPI_THREADS);
+    mbar_init(h_empty, 1);
+    mbar_init(y_full, 1);
+    mbar_init(y_empty, EPI_THREADS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    int acc = 0;
+    for (int e = 0; e < E; ++e) {
+      const int o = offsets[e];
+      goff[e] = o;
+      gstart[e] = acc;
+      acc += (offsets[e + 1] - o + BM - 1) / BM;
+    }
+    goff[E] = offsets[E];
+    gstart[E] = acc;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = gstart[E];
+
+  auto decode_tile = [&](int t, int& e, int& m0, int& row_end) {
+    e = 0;
+    while (e + 1 < E && t >= gstart[e + 1]) ++e;
+    m0 = goff[e] + (t - gstart[e]) * BM;
+    row_end = goff[e + 1];
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      auto push = [&](const CUtensorMap* map, int c0, int c1) {
+        mbar_wait(&ring_empty[stage], phase ^ 1);
+        mbar_expect_tx(&ring_full[stage], STAGE);
+        tma_load_2d(map, &ring_full[stage], smem + RING_OFF + stage * STAGE, c0, c1);
+        if (++stage == NST) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        int e, m0, row_end;
+        decode_tile(t, e, m0, row_end);
+        mbar_wait(x_empty, (uint32_t)(it & 1) ^ 1);
+        mbar_expect_tx(x_full, 2 * STAGE);
+        tma_load_2d(&mapX, x_full, smem + X_OFF, 0, m0);
+        tma_load_2d(&mapX, x_full, smem + X_OFF + STAGE, BK, m0);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          // job order of the MMA warp: c0 c1 c2 c3 c4 g0 | c5 c6 c7 g1
+          const int c_lo = h == 0 ? 0 : 5, c_hi = h == 0 ? 4 : 7;
+          for (int c = c_lo; c <= c_hi; ++c)
+            for (int kb = 0; kb < 2; ++kb) push(&mapW13, kb * BK, e * (2 * I) + c * 128);
+          for (int kb = 0; kb < 4; ++kb) push(&mapW2, (h * 4 + kb) * BK, e * D);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t n_acc[2] = {0, 0};   // uses of each accumulator buffer so far
+    uint32_t n_h = 0;             // halves of the hidden tile consumed so far
+    int it = 0;
+    const uint64_t xdesc0 = umma_desc_sw128(smem + X_OFF), xdesc1 = umma_desc_sw128(smem + X_OFF + STAGE);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      mbar_wait(x_full, (uint32_t)(it & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      auto chunk = [&](int c) {
+        const int buf = c & 1;
+        mbar_wait(&acc_empty[buf], (n_acc[buf] & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 128);
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(&ring_full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            const uint64_t adesc = kb ? xdesc1 : xdesc0;
+            const uint64_t bdesc = umma_desc_sw128(smem + RING_OFF + stage * STAGE);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_commit(&ring_empty[stage]);
+            if (kb == 1) {
+              umma_commit(&acc_full[buf]);
+              if (c == 7) umma_commit(x_empty);   // the tile's rows are no longer read: the next tile's may land
+            }
+          }
+          __syncwarp();
+          if (++stage == NST) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ++n_acc[buf];
+      };
+      auto second = [&](int h) {
+        mbar_wait(h_full, n_h & 1);                    // this half of the hidden tile is in shared memory
+        if (h == 0) mbar_wait(y_empty, (uint32_t)(it & 1) ^ 1);   // the previous tile's output has been read out of TMEM
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_y = tmem_base + 256u;
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&ring_full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            const uint64_t adesc = umma_desc_sw128(smem + H_OFF + kb * STAGE);
+            const uint64_t bdesc = umma_desc_sw128(smem + RING_OFF + stage * STAGE);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_y, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (h | kb | k) ? 1u : 0u);
+            umma_commit(&ring_empty[stage]);
+            if (kb == 3) {
+              umma_commit(h_empty);
+              if (h == 1) umma_commit(y_full);
+            }
+          }
+          __syncwarp();
+          if (++stage == NST) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ++n_h;
+      };
+      chunk(0); chunk(1); chunk(2); chunk(3); chunk(4);
+      second(0);
+      chunk(5); chunk(6); chunk(7);
+      second(1);
+    }
+  } else {
+    // ===================== epilogue (8 warps) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;           // which 64 of a chunk's 128 accumulator columns
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t h_row = smem_u32(smem + H_OFF) + (uint32_t)(row_in_tile * 128);
+    const uint32_t sx = (uint32_t)((lane & 7) << 4);
+    uint32_t n_acc[2] = {0, 0};
+    uint32_t n_hw = 0;                           // halves written so far
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int e, m0, row_end;
+      decode_tile(t, e, m0, row_end);
+      const int r = m0 + row_in_tile;
+      const bool row_ok = r < row_end;
+      const float sw = row_ok ? slot_w[r] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        const int buf = c & 1;
+        if ((c & 3) == 0) {
+          // first chunk of a half: the MMAs that read the previous contents of the hidden buffer have retired
+          mbar_wait(h_empty, (n_hw & 1) ^ 1);
+        }
+        mbar_wait(&acc_full[buf], n_acc[buf] & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + half * 64);
+        const uint32_t h_blk = h_row + (uint32_t)((c & 3) * STAGE);
+        uint32_t va[16], vb[16];
+        tmem_ld16_nowait(t_addr, va);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g & 1) tmem_wait_ld(vb); else tmem_wait_ld(va);
+          if (g < 3) {
+            if (g & 1) tmem_ld16_nowait(t_addr + 16 * (g + 1), va); else tmem_ld16_nowait(t_addr + 16 * (g + 1), vb);
+          } else {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[buf]);
+          }
+          uint32_t h4[4];
+          lean_half_gated<ACT, false>((g & 1) ? vb : va, 1.0f, 1.0f, nullptr, h4);
+          // 8 outputs = one 16-byte unit of the K-major swizzled row: unit (half * 4 + g) ^ (row & 7)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_blk + ((uint32_t)((half * 4 + g) << 4) ^ sx)),
+                       "r"(h4[0]), "r"(h4[1]), "r"(h4[2]), "r"(h4[3])
+                       : "memory");
+        }
+        ++n_acc[buf];
+        if ((c & 3) == 3) {
+          // the half is complete: generic-proxy writes -> visible to the tensor core's reads, then publish
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(h_full);
+          ++n_hw;
+        }
+      }
+      // ---- output: Y * slot weight -> bf16 -> global (each thread owns 64 contiguous columns of its row)
+      mbar_wait(y_full, (uint32_t)(it & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t y_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + half * 64);
+      __nv_bfloat16* yrow = ys + (int64_t)(row_ok ? r : 0) * D + half * 64;
+      uint32_t va[16], vb[16];
+      tmem_ld16_nowait(y_addr, va);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g & 1) tmem_wait_ld(vb); else tmem_wait_ld(va);
+        if (g < 3) {
+          if (g & 1) tmem_ld16_nowait(y_addr + 16 * (g + 1), va); else tmem_ld16_nowait(y_addr + 16 * (g + 1), vb);
+        } else {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(y_empty);
+        }
+        const uint32_t(&v)[16] = (g & 1) ? vb : va;
+        uint32_t o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[2 * q]) * sw, __uint_as_float(v[2 * q + 1]) * sw);
+          o[q] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        if (row_ok) {
+          *reinterpret_cast<uint4*>(yrow + 16 * g) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(yrow + 16 * g + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// =====================================================================================================================
 // GEMM CHAIN: several dependent GEMMs of the decode step in ONE persistent launch.
 //   phase 0:  C0 = epi0(A0 W0^T)      phase 1:  C1 = epi1(A1 W1^T)  with A1 = C0 (or an earlier output) ...
 // Tile order is ROW-TILE MAJOR: the grid is cut into groups of `split` CTAs; group g owns the 128-row tiles g, g + G, ...
@@ -1619,6 +1915,43 @@ int gemm_chain_bf16(const GemmParams* phases, int n_phases, int* done, const int
 }
 
 int gemm_chain_counters(int M) { return CHAIN_MAX_PHASES * ymt3_div_up(M, BM); }
+
+// Fused MoE expert MLP (moe_expert_fused_kernel): xs (S, 128) bf16 expert-sorted, w13 (E, 1024, 128), w2 (E, 128, 512),
+// offsets (E + 1) device ints, slot_w (S) fp32, ys (S, 128) bf16.  Returns YMT3_ERR_* ; shapes other than d_model 128 /
+// hidden 512 / SiLU or gelu_new are the caller's business (two grouped GEMMs).
+int moe_expert_fused(const void* xs, int64_t S, const void* w13, const void* w2, const int* offsets, int E,
+                     const float* slot_w, void* ys, int act, cudaStream_t stream) {
+  using namespace moefused;
+  YMT3_REQUIRE(xs && w13 && w2 && offsets && slot_w && ys, "moe_expert_fused: null pointer");
+  YMT3_REQUIRE(E >= 1 && E <= MAX_E && S >= 0 && S < (1ll << 31), "moe_expert_fused: bad shape");
+  YMT3_REQUIRE(act == YMT3_ACT_SILU || act == YMT3_ACT_GELU_NEW, "moe_expert_fused: activation %d", act);
+  if (S == 0) return YMT3_OK;
+  CUtensorMap mapX, mapW13, mapW2;
+  int rc;
+  if ((rc = make_map(&mapX, xs, S, D, D, BM))) return rc;
+  if ((rc = make_map(&mapW13, w13, (int64_t)E * 2 * I, D, D, 128))) return rc;
+  if ((rc = make_map(&mapW2, w2, (int64_t)E * D, I, I, 128))) return rc;
+  static bool attr_set[64][2] = {};
+  int dev = 0;
+  YMT3_CUDA_CHECK(cudaGetDevice(&dev));
+  const int ai = act == YMT3_ACT_SILU ? 0 : 1;
+  if (dev < 0 || dev >= 64 || !attr_set[dev][ai]) {
+    if (ai == 0)
+      YMT3_CUDA_CHECK(cudaFuncSetAttribute(moe_expert_fused_kernel<YMT3_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    else
+      YMT3_CUDA_CHECK(cudaFuncSetAttribute(moe_expert_fused_kernel<YMT3_ACT_GELU_NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    if (dev >= 0 && dev < 64) attr_set[dev][ai] = true;
+  }
+  const int sms = ymt3_num_sms();
+  const int64_t max_tiles = S / BM + E;   // upper bound of the tile count (one ragged tile per expert)
+  const int grid = (int)(max_tiles < sms ? max_tiles : sms);
+  if (ai == 0)
+    moe_expert_fused_kernel<YMT3_ACT_SILU><<<grid, THREADS, TOTAL, stream>>>(mapX, mapW13, mapW2, offsets, E, slot_w, (__nv_bfloat16*)ys);
+  else
+    moe_expert_fused_kernel<YMT3_ACT_GELU_NEW><<<grid, THREADS, TOTAL, stream>>>(mapX, mapW13, mapW2, offsets, E, slot_w, (__nv_bfloat16*)ys);
+  YMT3_CUDA_CHECK(cudaGetLastError());
+  return YMT3_OK;
+}
 
 int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream) {
   YMT3_REQUIRE(p.A && p.W && p.C, "gemm_bf16_tc: null pointer");

@@ -271,20 +271,28 @@ int moe_forward(int precision, const void* x, const void* residual, void* out, i
                                                          cursor, (__nv_bfloat16*)xs, slot_w, tok_slot);
   }
   YMT3_CUDA_CHECK(cudaGetLastError());
-  // grouped GEMM 1: hs = act(xs W1^T) * (xs W3^T)   (rows of w13 interleaved per expert)
-  GemmParams g{};
-  g.A = xs; g.lda = D; g.W = w.w13; g.ldw = D; g.C = hs; g.ldc = I;
-  g.M = (int)S; g.N = 2 * I; g.K = D; g.act = w.act; g.gated = 1; g.out_scale = 1.f;
-  g.group_offsets = offsets; g.num_groups = E; g.strideW = (int64_t)2 * I * D;
-  int rc = precision == YMT3_F32 ? gemm_f32(g, s) : gemm_bf16_tc(g, precision, s);
-  if (rc) return rc;
-  // grouped GEMM 2: ys = slot_w * (hs W2^T)
-  GemmParams h{};
-  h.A = hs; h.lda = I; h.W = w.w2; h.ldw = I; h.C = ys; h.ldc = D;
-  h.M = (int)S; h.N = D; h.K = I; h.out_scale = 1.f; h.row_scale = slot_w;
-  h.group_offsets = offsets; h.num_groups = E; h.strideW = (int64_t)D * I;
-  rc = precision == YMT3_F32 ? gemm_f32(h, s) : gemm_bf16_tc(h, precision, s);
-  if (rc) return rc;
+  // bf16, d_model 128, hidden 512: both expert GEMMs in one kernel, the hidden tile never leaves the SM
+  // (moe_expert_fused_kernel; bit-identical to the two grouped GEMMs below; YMT3_NO_MOE_FUSED=1 = A/B aid)
+  const bool no_fused = getenv("YMT3_NO_MOE_FUSED") != nullptr;   // (read per call: the tests toggle it)
+  if (precision == YMT3_BF16 && !no_fused && D == 128 && I == 512 && E <= 32 &&
+      (w.act == YMT3_ACT_SILU || w.act == YMT3_ACT_GELU_NEW)) {
+    if (int rf = moe_expert_fused(xs, S, w.w13, w.w2, offsets, E, slot_w, ys, w.act, s)) return rf;
+  } else {
+    // grouped GEMM 1: hs = act(xs W1^T) * (xs W3^T)   (rows of w13 interleaved per expert)
+    GemmParams g{};
+    g.A = xs; g.lda = D; g.W = w.w13; g.ldw = D; g.C = hs; g.ldc = I;
+    g.M = (int)S; g.N = 2 * I; g.K = D; g.act = w.act; g.gated = 1; g.out_scale = 1.f;
+    g.group_offsets = offsets; g.num_groups = E; g.strideW = (int64_t)2 * I * D;
+    int rc = precision == YMT3_F32 ? gemm_f32(g, s) : gemm_bf16_tc(g, precision, s);
+    if (rc) return rc;
+    // grouped GEMM 2: ys = slot_w * (hs W2^T)
+    GemmParams h{};
+    h.A = hs; h.lda = I; h.W = w.w2; h.ldw = I; h.C = ys; h.ldc = D;
+    h.M = (int)S; h.N = D; h.K = I; h.out_scale = 1.f; h.row_scale = slot_w;
+    h.group_offsets = offsets; h.num_groups = E; h.strideW = (int64_t)D * I;
+    rc = precision == YMT3_F32 ? gemm_f32(h, s) : gemm_bf16_tc(h, precision, s);
+    if (rc) return rc;
+  }
   YMT3_REQUIRE(D % 8 == 0, "moe: d_model must be a multiple of 8");
   const int64_t vec = 16 / (int64_t)es;
   const unsigned gc = (unsigned)(((int64_t)N * D / vec + 255) / 256);

@@ -74,6 +74,10 @@ int gemm_bf16_tc(const GemmParams& p, int out_dtype, cudaStream_t stream);  // t
 int gemm_chain_bf16(const GemmParams* phases, int n_phases, int* done, const int* epoch_ptr, int epoch_mul, int epoch_add,
                     cudaStream_t stream);
 int gemm_chain_counters(int M);
+// Fused MoE expert MLP (gemm_bf16_tc.cu, moe_expert_fused_kernel): both grouped GEMMs of the experts in one kernel, the
+// hidden tile stays in shared memory.  d_model 128, hidden 512, SiLU / gelu_new, bf16 only.
+int moe_expert_fused(const void* xs, int64_t S, const void* w13, const void* w2, const int* offsets, int E,
+                     const float* slot_w, void* ys, int act, cudaStream_t stream);
 void gemm_chain_set_trace(unsigned long long* buf);   // debug: per-CTA event timestamps, (SMs x 16 x 32) words or null
 // 3x3 same-padding convolution on NHWC bf16 input as an implicit GEMM (tcgen05; TMA 4-D tiles with
 // zero-filled halo); `epi` carries W (Cout, 9*Cin), N=Cout, C/ldc, bias, act, residual/ldr, out_scale.

@@ -279,7 +279,15 @@ template <int ACT>
 __device__ __forceinline__ float act_fast(float x) {
   if constexpr (ACT == YMT3_ACT_GELU_NEW) return 0.5f * x * (1.0f + fast_tanh(0.7978845608028654f * (x + 0.044715f * x * x * x)));
   else if constexpr (ACT == YMT3_ACT_RELU) return fmaxf(x, 0.f);
-  else if constexpr (ACT == YMT3_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
+  else if constexpr (ACT == YMT3_ACT_SILU) {
+    // x * 1 / (1 + 2^(-x log2 e)) with the two MUFU approximations issued directly: 3 FMUL + FADD + 2 MUFU per element
+    // (__fdividef(x, 1 + __expf(-x)) spends ~11 instructions on range fix-ups that cannot trigger here: the
+    // denominator is >= 1, and +inf gives 0)
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+  }
   else if constexpr (ACT == YMT3_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
   else return x;
 }
@@ -424,12 +432,16 @@ __device__ __forceinline__ void lean_half(const bool BIAS, const bool RES, const
 }
 // gated form: v = 16 accumulator columns = 8 (activated, linear) pairs; h = 8 bf16 outputs act(a_even) * a_odd * rs with
 // a = v * pre + bias - the per-element operations of epi_math<ACT, true>
-template <int ACT, bool BIAS>
+// (SCALE false: pre and rs are known to be exactly 1 and are not applied)
+template <int ACT, bool BIAS, bool SCALE = true>
 __device__ __forceinline__ void lean_half_gated(const uint32_t (&v)[16], float pre, float rs, const float* bias_c, uint32_t (&h)[4]) {
   float2 a[8];
   const float2 p2 = make_float2(pre, pre);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) a[q] = lean_mul2(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), p2);
+  for (int q = 0; q < 8; ++q) {
+    a[q] = make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+    if constexpr (SCALE) a[q] = lean_mul2(a[q], p2);
+  }
   if constexpr (BIAS) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -440,8 +452,12 @@ __device__ __forceinline__ void lean_half_gated(const uint32_t (&v)[16], float p
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float o0 = act_fast<ACT>(a[2 * q].x) * a[2 * q].y * rs;
-    const float o1 = act_fast<ACT>(a[2 * q + 1].x) * a[2 * q + 1].y * rs;
+    float o0 = act_fast<ACT>(a[2 * q].x) * a[2 * q].y;
+    float o1 = act_fast<ACT>(a[2 * q + 1].x) * a[2 * q + 1].y;
+    if constexpr (SCALE) {
+      o0 *= rs;
+      o1 *= rs;
+    }
     const __nv_bfloat162 b2 = __floats2bfloat162_rn(o0, o1);
     h[q] = *reinterpret_cast<const uint32_t*>(&b2);
   }
@@ -1098,8 +1114,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 // (2 N, I) hidden matrix (4.3 GB + 4.3 GB per layer at 728 segments: GEMM1 is bound by that write).
 // Shapes are compile-time: d_model 128, hidden 512 (the model's), rows of W13 interleaved (2j = activated, 2j+1 = linear).
 // One CTA per SM walks the 128-row tiles of the expert-sorted rows (ragged last tile per expert: rows of the next
-// expert are computed and not stored).  Per tile, with X = the tile's rows (2 k-blocks, resident), H = HALF of the
-// hidden tile (4 k-blocks of 128 x 64 bf16 in the tensor core's K-major 128-byte-swizzle layout):
+// expert are computed and not stored).  Per tile, with X = the tile's rows (2 k-blocks, resident), H = k-blocks of the
+// hidden tile (128 x 64 bf16 in the tensor core's K-major 128-byte-swizzle layout, HALF a tile per g job):
 //   MMA job list   c0 c1 c2 c3 c4 g0 c5 c6 c7 g1
 //     c_i : acc[i & 1] (128 TMEM columns) = X  W13[e, 128 i .. 128 i + 127, :]^T      (2 k-blocks, N = 128)
 //     g_h : Y (128 TMEM columns)        += H_h W2[e, :, 256 h .. 256 h + 255]^T      (4 k-blocks, N = 128)
@@ -1112,7 +1128,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 namespace moefused {
 constexpr int D = 128, I = 512;
 constexpr int STAGE = 16384;                 // one 128 x 64 bf16 block
-constexpr int X_OFF = 0, H_OFF = 2 * STAGE, RING_OFF = 6 * STAGE, NST = 8;
+constexpr int HSLOTS = 5;                    // hidden k-blocks in shared memory: 4 being read by a g job + 1 being written
+constexpr int X_OFF = 0, H_OFF = 2 * STAGE, RING_OFF = (2 + HSLOTS) * STAGE, NST = 7;
 constexpr int BAR_OFF = RING_OFF + NST * STAGE;
 constexpr int TOTAL = BAR_OFF + 1024 + 1024;   // barriers / tables, alignment slack
 static_assert(TOTAL <= 227 * 1024, "shared memory budget");
@@ -1271,7 +1288,7 @@ moe_expert_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
           mbar_wait(&ring_full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
-            const uint64_t adesc = umma_desc_sw128(smem + H_OFF + kb * STAGE);
+            const uint64_t adesc = umma_desc_sw128(smem + H_OFF + (int)((4 * n_h + kb) % HSLOTS) * STAGE);
             const uint64_t bdesc = umma_desc_sw128(smem + RING_OFF + stage * STAGE);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
@@ -1303,56 +1320,20 @@ moe_expert_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
     const uint32_t h_row = smem_u32(smem + H_OFF) + (uint32_t)(row_in_tile * 128);
     const uint32_t sx = (uint32_t)((lane & 7) << 4);
     uint32_t n_acc[2] = {0, 0};
-    uint32_t n_hw = 0;                           // halves written so far
+    uint32_t n_chunk = 0;                        // chunks written so far (all tiles): chunk n lives in slot n % HSLOTS
+    uint32_t g_seen = 0;                         // g jobs (halves consumed by the MMA warp) known to have retired
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      int e, m0, row_end;
-      decode_tile(t, e, m0, row_end);
-      const int r = m0 + row_in_tile;
-      const bool row_ok = r < row_end;
-      const float sw = row_ok ? slot_w[r] : 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        const int buf = c & 1;
-        if ((c & 3) == 0) {
-          // first chunk of a half: the MMAs that read the previous contents of the hidden buffer have retired
-          mbar_wait(h_empty, (n_hw & 1) ^ 1);
-        }
-        mbar_wait(&acc_full[buf], n_acc[buf] & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + half * 64);
-        const uint32_t h_blk = h_row + (uint32_t)((c & 3) * STAGE);
-        uint32_t va[16], vb[16];
-        tmem_ld16_nowait(t_addr, va);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g & 1) tmem_wait_ld(vb); else tmem_wait_ld(va);
-          if (g < 3) {
-            if (g & 1) tmem_ld16_nowait(t_addr + 16 * (g + 1), va); else tmem_ld16_nowait(t_addr + 16 * (g + 1), vb);
-          } else {
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc_empty[buf]);
-          }
-          uint32_t h4[4];
-          lean_half_gated<ACT, false>((g & 1) ? vb : va, 1.0f, 1.0f, nullptr, h4);
-          // 8 outputs = one 16-byte unit of the K-major swizzled row: unit (half * 4 + g) ^ (row & 7)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_blk + ((uint32_t)((half * 4 + g) << 4) ^ sx)),
-                       "r"(h4[0]), "r"(h4[1]), "r"(h4[2]), "r"(h4[3])
-                       : "memory");
-        }
-        ++n_acc[buf];
-        if ((c & 3) == 3) {
-          // the half is complete: generic-proxy writes -> visible to the tensor core's reads, then publish
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(h_full);
-          ++n_hw;
-        }
-      }
+    // the output of tile i is read out of TMEM after the first two chunks of tile i + 1 (its MMAs retire meanwhile)
+    bool y_pending = false;
+    int y_r = 0, y_it = 0;
+    bool y_ok = false;
+    float y_sw = 0.f;
+    auto y_epilogue = [&]() {
       // ---- output: Y * slot weight -> bf16 -> global (each thread owns 64 contiguous columns of its row)
-      mbar_wait(y_full, (uint32_t)(it & 1));
+      mbar_wait(y_full, (uint32_t)(y_it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t y_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + half * 64);
-      __nv_bfloat16* yrow = ys + (int64_t)(row_ok ? r : 0) * D + half * 64;
+      __nv_bfloat16* yrow = ys + (int64_t)(y_ok ? y_r : 0) * D + half * 64;
       uint32_t va[16], vb[16];
       tmem_ld16_nowait(y_addr, va);
 #pragma unroll
@@ -1368,15 +1349,67 @@ moe_expert_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
         uint32_t o[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[2 * q]) * sw, __uint_as_float(v[2 * q + 1]) * sw);
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[2 * q]) * y_sw, __uint_as_float(v[2 * q + 1]) * y_sw);
           o[q] = *reinterpret_cast<const uint32_t*>(&b2);
         }
-        if (row_ok) {
+        if (y_ok) {
           *reinterpret_cast<uint4*>(yrow + 16 * g) = make_uint4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<uint4*>(yrow + 16 * g + 8) = make_uint4(o[4], o[5], o[6], o[7]);
         }
       }
+      y_pending = false;
+    };
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int e, m0, row_end;
+      decode_tile(t, e, m0, row_end);
+      const int r = m0 + row_in_tile;
+      const bool row_ok = r < row_end;
+      const float sw = row_ok ? slot_w[r] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c, ++n_chunk) {
+        if (c == 2 && y_pending) y_epilogue();
+        const int buf = c & 1;
+        if (n_chunk >= (uint32_t)HSLOTS) {
+          // the slot's previous contents (chunk n - HSLOTS) were read by g job (n - HSLOTS) / 4: it must have retired
+          const uint32_t need = (n_chunk - HSLOTS) / 4;
+          while (g_seen <= need) {
+            mbar_wait(h_empty, g_seen & 1);
+            ++g_seen;
+          }
+        }
+        mbar_wait(&acc_full[buf], n_acc[buf] & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + half * 64);
+        const uint32_t h_blk = h_row + (n_chunk % HSLOTS) * (uint32_t)STAGE;
+        uint32_t va[16], vb[16];
+        tmem_ld16_nowait(t_addr, va);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g & 1) tmem_wait_ld(vb); else tmem_wait_ld(va);
+          if (g < 3) {
+            if (g & 1) tmem_ld16_nowait(t_addr + 16 * (g + 1), va); else tmem_ld16_nowait(t_addr + 16 * (g + 1), vb);
+          } else {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[buf]);
+          }
+          uint32_t h4[4];
+          lean_half_gated<ACT, false, false>((g & 1) ? vb : va, 1.0f, 1.0f, nullptr, h4);
+          // 8 outputs = one 16-byte unit of the K-major swizzled row: unit (half * 4 + g) ^ (row & 7)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_blk + ((uint32_t)((half * 4 + g) << 4) ^ sx)),
+                       "r"(h4[0]), "r"(h4[1]), "r"(h4[2]), "r"(h4[3])
+                       : "memory");
+        }
+        ++n_acc[buf];
+        if ((c & 3) == 3) {
+          // the half is complete: generic-proxy writes -> visible to the tensor core's reads, then publish
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(h_full);
+        }
+      }
+      y_pending = true;
+      y_r = r; y_ok = row_ok; y_sw = sw; y_it = it;
     }
+    if (y_pending) y_epilogue();
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -1089,6 +1089,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (best_key) atomicMax(p.argmax_out + r, best_key);
       if (stamp) TC_STAMP(j, 5);
     }
+    // (waiting only for the shared-memory sources to be read - `.read` - measured neutral: the grid is not complete
+    //  before the writes are, profiles/r02_experiments_not_kept.md)
     if (e_tma && lane == 0) tma_store_wait_all();
     if (warp == 2 && lane == 0) TC_STAMP(0, 6);   // smem sources read and writes complete before exit
   }

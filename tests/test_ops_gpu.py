@@ -437,3 +437,62 @@ def test_linear_chain_matches_separate_launches(cuda_device, native_lib, M):
         for k in ref:
             assert torch.equal(ref[k], got[k]), (ordinal, k)
     assert float(ref["out"].float().abs().mean()) > 1e-3
+
+
+_LEAN_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+from yourmt3_b200 import _lib
+lib = _lib.load()
+dev = torch.device("cuda")
+g = torch.Generator().manual_seed(3)
+outs = {}
+s_ = None
+for name, (M, N, K, gated, act, bias, res, ss, norm) in {
+        "plain": (300, 1152, 512, 0, 0, 0, 0, 0, 0), "bias": (1000, 384, 128, 0, 0, 1, 0, 0, 0),
+        "res_ss": (333, 512, 384, 0, 0, 0, 1, 1, 0), "bias_res_ss": (700, 512, 1536, 0, 0, 1, 1, 1, 0),
+        "bias_res": (129, 128, 128, 0, 0, 1, 1, 0, 0), "norm_plain": (9464, 1536, 512, 0, 0, 0, 0, 0, 1),
+        "gated_gelu": (300, 2048, 512, 1, 1, 0, 0, 0, 1), "gated_silu_bias": (5000, 1024, 128, 1, 3, 1, 0, 0, 0)}.items():
+    A = torch.randn(M, K, generator=g).to(dev, torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(dev, torch.bfloat16)
+    No = N // 2 if gated else N
+    C = torch.randn(M, No, generator=g).to(dev, torch.bfloat16)          # also the residual (in place)
+    b = (torch.randn(N, generator=g) * 0.1).to(dev) if bias else None
+    sso = torch.zeros(M, No // 32, device=dev) if ss else None
+    ssi = (A.float() ** 2).view(M, K // 32, 32).sum(-1).contiguous() if norm else None
+    _lib.check(lib.ymt3_op_linear_normfused(A.data_ptr(), K, W.data_ptr(), K, b.data_ptr() if bias else None,
+                                            ssi.data_ptr() if norm else None, K // 32 if norm else 0, 1e-6, C.data_ptr(), No,
+                                            C.data_ptr() if res else None, No, sso.data_ptr() if ss else None, M, N, K, act, gated,
+                                            1.0, 1, s_))
+    torch.cuda.synchronize()
+    outs[name] = C.cpu()
+    if ss:
+        outs[name + "_ss"] = sso.cpu()
+torch.save(outs, sys.argv[2])
+"""
+
+
+def test_lean_epilogue_bit_identical_to_general(cuda_device, native_lib, tmp_path):
+    """The lean GEMM epilogue instances (compile-time bias / residual / sum-of-squares / gated flags, packed f32x2 math,
+    pipelined 16-column halves) produce the same BITS as the general epilogue path (YMT3_GEMM_NO_LEAN=1, read once per
+    process -> two subprocesses): plain, bias, residual + sum of squares, gated gelu_new / SiLU, fused-norm consumer;
+    ragged M, partially filled last N tile (1152 = 4.5 x 256)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("lean", "general"):
+        env = dict(os.environ)
+        env.pop("YMT3_GEMM_NO_LEAN", None)
+        if mode == "general":
+            env["YMT3_GEMM_NO_LEAN"] = "1"
+        out = tmp_path / f"{mode}.pt"
+        r = subprocess.run([sys.executable, "-c", _LEAN_SCRIPT, root, str(out)], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[mode] = torch.load(out)
+    assert set(res["lean"]) == set(res["general"])
+    for k in res["lean"]:
+        a, b = res["lean"][k], res["general"][k]
+        assert float(a.float().abs().mean()) > 1e-3, k
+        assert torch.equal(a, b), (k, float((a.float() - b.float()).abs().max()))

@@ -10,6 +10,16 @@
 //              tcgen05.ld -> registers -> compile-time specialised epilogue math -> 16-byte stores
 // The accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the
 // MMAs of tile i+1.
+//
+// Contents of this translation unit (everything that shares the PTX helpers and the operand layouts):
+//   1. PTX helpers: mbarrier, TMA load / store, tcgen05 alloc / mma / commit / ld, descriptors
+//   2. epilogue math: general path (epi_math / epi_pack_bf16 / epi_store) and the LEAN path (lean_half, lean_half_gated,
+//      lean_tile: compile-time flags, pipelined 16-column TMEM halves - the instances every model GEMM runs)
+//   3. gemm_bf16_tc_kernel<BN, CONV, EPI, CL>: the persistent GEMM / implicit-GEMM convolution (CL = 2: CTA pair)
+//   4. moe_expert_fused_kernel<ACT>: both expert GEMMs of the MoE feed-forward, hidden tile kept in shared memory
+//   5. gemm_chain_kernel: several dependent decode-step GEMMs in one persistent launch (opt-in)
+//   6. host side: tensor maps, tile-width / cluster rules, instance dispatch (gemm_bf16_tc, conv3x3_bf16_tc,
+//      gemm_chain_bf16, moe_expert_fused)
 #include "ops.cuh"
 #include <cuda.h>
 #include <cstring>
@@ -22,10 +32,11 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 
-// epilogue warps: EPI_GROUPS warps per TMEM lane quadrant, each owning an interleaved share of the tile's 32-column
-// chunks.  The epilogue is latency-bound per warp (ncu on the K = 128 gated GEMM, profiles/r02_gemm_moe1_gated_silu_
-// ncu_full.txt: ~1400 warp instructions per warp and 128 x 256 tile at ~0.22 IPC, issue slots 47 % busy with 2.5
-// warps per scheduler).  MEASURED with EPI_GROUPS = 4 (16 epilogue warps, 576 threads): the register cap drops to 96
+// epilogue warps: EPI_GROUPS warps per TMEM lane quadrant, each owning an adjacent share of the tile's 32-column
+// chunks.  (First reading of the slow epilogue - ncu on the K = 128 gated GEMM, profiles/r02_gemm_moe1_gated_silu_
+// ncu_full.txt: ~1400 warp instructions per warp and 128 x 256 tile at ~0.22 IPC - was "latency-bound per warp, add
+// warps"; the per-CTA timeline later located the cost in uniform-datapath parameter / branch chains, see lean_tile.)
+// MEASURED with EPI_GROUPS = 4 (16 epilogue warps, 576 threads): the register cap drops to 96
 // per thread, every epilogue spills (100-680 bytes) and the K = 128 gated GEMM goes 252 -> 380 us, the bench 1324 ->
 // 1416 ms (profiles/r02_experiments_not_kept.md); two groups (8 warps, 168 registers, no spills) stay.
 constexpr int EPI_GROUPS = 2;

@@ -84,6 +84,21 @@ def test_tma_staging_offsets_follow_the_hardware_swizzle_and_are_conflict_free(e
     assert len(seen) == 32 * units                      # a bijection onto the box
 
 
+def test_operand_block_offsets_are_the_128_byte_swizzle_of_a_128_row_k_major_tile(emu):
+    """moe_expert_fused_kernel writes the hidden activations straight into shared memory as a tcgen05 A operand: a
+    128-row x 64-column bf16 block, rows of 128 bytes, SWIZZLE_128B (what a TMA load of that block produces and what
+    the shared-memory descriptor describes: 8-row groups 1024 bytes apart, 16-byte units XOR-ed with row & 7)."""
+    seen = set()
+    for row in range(128):
+        for unit in range(8):
+            off = emu.emu_tma_box_offset(row, unit, 128)
+            lin = row * 128 + unit * 16
+            assert off == lin ^ (((lin >> 7) & 7) << 4)
+            assert off // 1024 == row // 8 and (off % 1024) // 128 == row % 8     # 8-row groups of 1024 bytes
+            seen.add(off)
+    assert seen == set(range(0, 128 * 128, 16))                                   # a bijection onto the 16 KB block
+
+
 def test_tile_width_rule_is_the_argmin_of_the_cost_model(emu):
     sms = 148
     for m_tiles in (1, 7, 26, 52, 74, 313, 1430, 2860):

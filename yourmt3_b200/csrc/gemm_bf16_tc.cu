@@ -1330,8 +1330,7 @@ moe_expert_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;           // which 64 of a chunk's 128 accumulator columns
     const int row_in_tile = quad * 32 + lane;
-    const uint32_t h_row = smem_u32(smem + H_OFF) + (uint32_t)(row_in_tile * 128);
-    const uint32_t sx = (uint32_t)((lane & 7) << 4);
+    const uint32_t h_base = smem_u32(smem + H_OFF);
     uint32_t n_acc[2] = {0, 0};
     uint32_t n_chunk = 0;                        // chunks written so far (all tiles): chunk n lives in slot n % HSLOTS
     uint32_t g_seen = 0;                         // g jobs (halves consumed by the MMA warp) known to have retired
@@ -1393,7 +1392,7 @@ moe_expert_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
         mbar_wait(&acc_full[buf], n_acc[buf] & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + half * 64);
-        const uint32_t h_blk = h_row + (n_chunk % HSLOTS) * (uint32_t)STAGE;
+        const uint32_t h_blk = h_base + (n_chunk % HSLOTS) * (uint32_t)STAGE;
         uint32_t va[16], vb[16];
         tmem_ld16_nowait(t_addr, va);
 #pragma unroll
@@ -1407,8 +1406,10 @@ moe_expert_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
           }
           uint32_t h4[4];
           lean_half_gated<ACT, false, false>((g & 1) ? vb : va, 1.0f, 1.0f, nullptr, h4);
-          // 8 outputs = one 16-byte unit of the K-major swizzled row: unit (half * 4 + g) ^ (row & 7)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_blk + ((uint32_t)((half * 4 + g) << 4) ^ sx)),
+          // 8 outputs = 16-byte unit (half * 4 + g) of this row of the 128 x 64 K-major operand block, placed where the
+          // 128-byte swizzle of the tensor core's shared-memory descriptor expects it (tma_box_offset, index_maps.h:
+          // the layout a TMA load of the same block would produce; pinned on the CPU in tests/test_index_maps_emu.py)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_blk + (uint32_t)tma_box_offset(row_in_tile, half * 4 + g, 128)),
                        "r"(h4[0]), "r"(h4[1]), "r"(h4[2]), "r"(h4[3])
                        : "memory");
         }
